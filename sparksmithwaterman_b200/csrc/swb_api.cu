@@ -1,0 +1,725 @@
+// swb_api.cu -- the C ABI (include/swb200.h): contexts, HBM-resident reference sets and
+// read batches, the align driver (batching, kernel sequencing, timing) and result access.
+// No CPU fallback: every compute entry needs a CUDA device and fails loudly without one.
+#include "swb_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+
+using namespace swb;
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+int cuda_fail(cudaError_t e, const char *what)
+{
+    g_err = std::string(what) + ": " + cudaGetErrorString(e);
+    return SWB_E_CUDA;
+}
+#define CU(x)                                                                  \
+    do {                                                                       \
+        cudaError_t e_ = (x);                                                  \
+        if (e_ != cudaSuccess) return cuda_fail(e_, #x);                       \
+    } while (0)
+
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count)
+    {
+        release();
+        if (count == 0) count = 1;
+        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+        if (e == cudaSuccess) n = count;
+        return e;
+    }
+};
+
+inline int upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+}  // namespace
+
+struct swb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int64_t ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::recursive_mutex mu;
+};
+
+struct swb_refset {
+    swb_ctx *ctx = nullptr;
+    int64_t n_refs = 0, total_bases = 0, blocks_per_rp = 0;
+    int32_t max_len = 0;
+    int n_symbols = 0;
+    uint8_t code_of[128];                       // upper-cased ASCII byte -> code, 0xFF = not in the set
+    std::vector<int32_t> len_orig;
+    DevBuf<uint32_t> words, word_off;
+    DevBuf<int32_t> len, orig, sorted_of;
+    DevBuf<int64_t> blk_off;
+};
+
+struct swb_reads {
+    swb_ctx *ctx = nullptr;
+    const swb_refset *rs = nullptr;
+    int64_t n_reads = 0;
+    std::vector<int32_t> len;
+    DevBuf<uint8_t> codes;
+    DevBuf<int64_t> off;
+};
+
+namespace {
+struct BatchOut {
+    int K = 0;
+    uint32_t n_cells = 0;
+    int ops_stride = 0;
+    DevBuf<uint64_t> keys;
+    DevBuf<int32_t> beg, oplen;
+    DevBuf<uint32_t> ops;
+    // host copies (after fetch)
+    std::vector<uint64_t> h_keys;
+    std::vector<uint32_t> h_ops;
+};
+}  // namespace
+
+struct swb_result {
+    swb_ctx *ctx = nullptr;
+    int64_t n_refs = 0, n_reads = 0;
+    uint32_t flags = 0;
+    bool fetched = false;
+    std::vector<int32_t> ref_len, read_len;
+    DevBuf<int32_t> d_scores, d_totals, d_best;
+    std::vector<BatchOut> batches;
+    // host
+    std::vector<int32_t> scores, totals, best;
+    std::vector<int64_t> cell_off;
+    std::vector<int32_t> cells, beginnings, op_lens;
+    std::vector<uint32_t> cell_batch;            // per global cell: batch index
+    std::vector<uint32_t> cell_local;            // per global cell: index inside the batch
+    double stats[12] = {0};
+};
+
+extern "C" {
+
+int swb_abi_version(void) { return SWB_ABI_VERSION; }
+const char *swb_last_error(void) { return g_err.c_str(); }
+
+int swb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int swb_create(int device, int64_t workspace_bytes, swb_ctx **out)
+{
+    if (!out) return fail(SWB_E_INVALID, "swb_create: out is null");
+    *out = nullptr;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(SWB_E_CUDA, "swb_create: no CUDA device available (this engine has no CPU fallback)");
+    }
+    if (device < 0 || device >= n) return fail(SWB_E_INVALID, "swb_create: bad device index");
+    CU(cudaSetDevice(device));
+    cudaDeviceProp p;
+    CU(cudaGetDeviceProperties(&p, device));
+    if (p.major < 9) return fail(SWB_E_UNSUPPORTED, "swb_create: DPX kernels need sm_90+ (built for sm_100a)");
+    swb_ctx *c = new swb_ctx();
+    c->device = device;
+    c->sm_count = p.multiProcessorCount;
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    int64_t ws = workspace_bytes > 0 ? workspace_bytes : (int64_t)8 << 30;
+    ws = std::min<int64_t>(ws, (int64_t)(free_b / 2));
+    c->ws_bytes = ws;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaEventCreate(&c->ev[0]));
+    CU(cudaEventCreate(&c->ev[1]));
+    *out = c;
+    return SWB_OK;
+}
+
+void swb_destroy(swb_ctx *c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+    if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int check_offsets(const char *who, int64_t n, const char *bytes, const int64_t *off)
+{
+    if (n < 0) return fail(SWB_E_INVALID, std::string(who) + ": negative count");
+    if (!off) return fail(SWB_E_INVALID, std::string(who) + ": offsets is null");
+    if (off[0] < 0) return fail(SWB_E_INVALID, std::string(who) + ": negative offset");
+    for (int64_t k = 0; k < n; ++k)
+        if (off[k + 1] < off[k]) return fail(SWB_E_INVALID, std::string(who) + ": offsets not monotone");
+    if (off[n] > off[0] && !bytes) return fail(SWB_E_INVALID, std::string(who) + ": bytes is null");
+    return SWB_OK;
+}
+
+int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64_t *offsets, swb_refset **out)
+{
+    if (!ctx || !out) return fail(SWB_E_INVALID, "swb_refset_load: null argument");
+    *out = nullptr;
+    int rc = check_offsets("swb_refset_load", n_refs, bytes, offsets);
+    if (rc) return rc;
+    if (n_refs > (int64_t)1 << 30) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: more than 2^30 references");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+
+    std::unique_ptr<swb_refset> rs(new swb_refset());
+    rs->ctx = ctx;
+    rs->n_refs = n_refs;
+    rs->len_orig.resize((size_t)n_refs);
+    bool present[128] = {false};
+    for (int64_t k = 0; k < n_refs; ++k) {
+        const int64_t n = offsets[k + 1] - offsets[k];
+        if (n >= ((int64_t)1 << KEY_J_BITS))
+            return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference longer than 4,194,303 bases");
+        rs->len_orig[(size_t)k] = (int32_t)n;
+        rs->total_bases += n;
+        rs->max_len = std::max<int32_t>(rs->max_len, (int32_t)n);
+        const unsigned char *p = (const unsigned char *)bytes + offsets[k];
+        for (int64_t c = 0; c < n; ++c) {
+            if (p[c] >= 128) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: non-ASCII byte in a reference");
+            present[upper(p[c])] = true;
+        }
+    }
+    memset(rs->code_of, 0xFF, sizeof rs->code_of);
+    for (int c = 0; c < 128; ++c)
+        if (present[c]) {
+            if (rs->n_symbols == 4)
+                return fail(SWB_E_UNSUPPORTED,
+                            "swb_refset_load: more than 4 distinct (case-folded) symbols in the reference set; "
+                            "the 2-bit path cannot hold it");
+            rs->code_of[c] = (uint8_t)rs->n_symbols++;
+        }
+
+    // length buckets: descending length, stable
+    std::vector<int32_t> order((size_t)n_refs);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(),
+                     [&](int32_t a, int32_t b) { return rs->len_orig[(size_t)a] > rs->len_orig[(size_t)b]; });
+    std::vector<int32_t> sorted_of((size_t)n_refs), len_sorted((size_t)n_refs);
+    std::vector<uint32_t> word_off((size_t)n_refs);
+    std::vector<int64_t> blk_off((size_t)n_refs + 1);
+    uint64_t words_total = 0;
+    int64_t blocks = 0;
+    for (int64_t s = 0; s < n_refs; ++s) {
+        const int32_t o = order[(size_t)s];
+        const int32_t n = rs->len_orig[(size_t)o];
+        sorted_of[(size_t)o] = (int32_t)s;
+        len_sorted[(size_t)s] = n;
+        word_off[(size_t)s] = (uint32_t)words_total;
+        words_total += (uint64_t)(n + 15) / 16;
+        blk_off[(size_t)s] = blocks;
+        blocks += (n + GL - 1 + CB - 1) / CB > 0 ? (n + GL - 1 + CB - 1) / CB : 1;
+    }
+    blk_off[(size_t)n_refs] = blocks;
+    rs->blocks_per_rp = blocks;
+    if (words_total >= ((uint64_t)1 << 32)) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference set too large");
+    std::vector<uint32_t> words((size_t)words_total + 1, 0u);
+    for (int64_t s = 0; s < n_refs; ++s) {
+        const int32_t o = order[(size_t)s];
+        const unsigned char *p = (const unsigned char *)bytes + offsets[o];
+        uint32_t *w = words.data() + word_off[(size_t)s];
+        const int32_t n = len_sorted[(size_t)s];
+        for (int32_t c = 0; c < n; ++c) w[c >> 4] |= (uint32_t)rs->code_of[upper(p[c])] << (2 * (c & 15));
+    }
+    CU(rs->words.alloc(words.size()));
+    CU(rs->word_off.alloc((size_t)n_refs));
+    CU(rs->len.alloc((size_t)n_refs));
+    CU(rs->orig.alloc((size_t)n_refs));
+    CU(rs->sorted_of.alloc((size_t)n_refs));
+    CU(rs->blk_off.alloc((size_t)n_refs + 1));
+    CU(cudaMemcpy(rs->words.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+    if (n_refs) {
+        CU(cudaMemcpy(rs->word_off.p, word_off.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(rs->len.p, len_sorted.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(rs->orig.p, order.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(rs->sorted_of.p, sorted_of.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
+    }
+    CU(cudaMemcpy(rs->blk_off.p, blk_off.data(), ((size_t)n_refs + 1) * 8, cudaMemcpyHostToDevice));
+    *out = rs.release();
+    return SWB_OK;
+}
+
+void swb_refset_free(swb_refset *rs)
+{
+    if (!rs) return;
+    cudaSetDevice(rs->ctx->device);
+    delete rs;
+}
+int64_t swb_refset_count(const swb_refset *rs) { return rs ? rs->n_refs : 0; }
+int64_t swb_refset_total_bases(const swb_refset *rs) { return rs ? rs->total_bases : 0; }
+
+int swb_reads_upload(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const char *bytes, const int64_t *offsets,
+                     swb_reads **out)
+{
+    if (!ctx || !rs || !out) return fail(SWB_E_INVALID, "swb_reads_upload: null argument");
+    *out = nullptr;
+    int rc = check_offsets("swb_reads_upload", n_reads, bytes, offsets);
+    if (rc) return rc;
+    if (n_reads > (int64_t)1 << 30) return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: more than 2^30 reads");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    std::unique_ptr<swb_reads> rd(new swb_reads());
+    rd->ctx = ctx; rd->rs = rs; rd->n_reads = n_reads;
+    rd->len.resize((size_t)n_reads);
+    std::vector<int64_t> off((size_t)n_reads + 1);
+    int64_t total = 0;
+    for (int64_t k = 0; k < n_reads; ++k) {
+        off[(size_t)k] = total;
+        const int64_t m = offsets[k + 1] - offsets[k];
+        if (m > MAX_SHORT_ROWS)
+            return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: read longer than 256 bases (long-pair path not built yet)");
+        rd->len[(size_t)k] = (int32_t)m;
+        total += m;
+    }
+    off[(size_t)n_reads] = total;
+    std::vector<uint8_t> codes((size_t)total + 1);
+    for (int64_t k = 0; k < n_reads; ++k) {
+        const unsigned char *p = (const unsigned char *)bytes + offsets[k];
+        uint8_t *c = codes.data() + off[(size_t)k];
+        for (int32_t x = 0; x < rd->len[(size_t)k]; ++x) {
+            if (p[x] >= 128) return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: non-ASCII byte in a read");
+            c[x] = rs->code_of[upper(p[x])];
+        }
+    }
+    CU(rd->codes.alloc(codes.size()));
+    CU(rd->off.alloc(off.size()));
+    CU(cudaMemcpyAsync(rd->codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(rd->off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    *out = rd.release();
+    return SWB_OK;
+}
+
+void swb_reads_free(swb_reads *rd)
+{
+    if (!rd) return;
+    cudaSetDevice(rd->ctx->device);
+    delete rd;
+}
+int64_t swb_reads_count(const swb_reads *rd) { return rd ? rd->n_reads : 0; }
+
+static int pick_k(int m)
+{
+    for (int k = 0; k < kNumK; ++k)
+        if (GL * kKList[k] >= m) return kKList[k];
+    return 0;
+}
+
+int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, int32_t match, int32_t mismatch,
+                       int32_t gap, uint32_t flags, swb_result **out)
+{
+    if (!ctx || !rs || !rd || !out) return fail(SWB_E_INVALID, "swb_align: null argument");
+    *out = nullptr;
+    if (rd->rs != rs) return fail(SWB_E_INVALID, "swb_align: reads were encoded against a different reference set");
+    if (rs->ctx != ctx || rd->ctx != ctx) return fail(SWB_E_INVALID, "swb_align: handles belong to another context");
+    const int64_t n_refs = rs->n_refs, n_reads = rd->n_reads;
+    if (n_refs * n_reads >= ((int64_t)1 << 33)) return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^33 pairs per call");
+    int32_t max_m = 0;
+    for (int32_t m : rd->len) max_m = std::max(max_m, m);
+    // domain of the s16x2 kernels (the int32 long-pair path is not built yet)
+    if (gap >= 0) return fail(SWB_E_UNSUPPORTED, "swb_align: gap score must be negative on the s16x2 path");
+    if (std::abs((int64_t)match) > 8000 || std::abs((int64_t)mismatch) > 8000 || std::abs((int64_t)gap) > 8000)
+        return fail(SWB_E_UNSUPPORTED, "swb_align: |score| > 8000 not supported on the s16x2 path");
+    if ((int64_t)std::max(match, 0) * std::min<int64_t>(max_m, rs->max_len) > 16000)
+        return fail(SWB_E_UNSUPPORTED, "swb_align: match * min(m, n) exceeds the s16 range");
+
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    std::unique_ptr<swb_result> res(new swb_result());
+    res->ctx = ctx; res->n_refs = n_refs; res->n_reads = n_reads; res->flags = flags;
+    res->ref_len = rs->len_orig; res->read_len = rd->len;
+    const size_t n_pairs = (size_t)(n_refs * n_reads);
+    CU(res->d_scores.alloc(n_pairs));
+    CU(res->d_totals.alloc((size_t)n_refs));
+    CU(res->d_best.alloc((size_t)n_reads * 4));
+    CU(cudaMemsetAsync(res->d_scores.p, 0, std::max<size_t>(n_pairs, 1) * 4, st));
+
+    double t_fill = 0, t_locate = 0, t_trace = 0, ck_bytes = 0;
+    int launches = 1, n_batches = 0;
+    auto tic = [&]() { return cudaEventRecord(ctx->ev[0], st); };
+    auto toc = [&](double &acc) -> cudaError_t {
+        cudaError_t e = cudaEventRecord(ctx->ev[1], st);
+        if (e != cudaSuccess) return e;
+        e = cudaEventSynchronize(ctx->ev[1]);
+        if (e != cudaSuccess) return e;
+        float ms = 0;
+        e = cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+        acc += ms;
+        return e;
+    };
+
+    if (n_refs > 0 && n_reads > 0) {
+        // group reads by rows-per-lane class, longest first inside a class
+        std::vector<std::vector<int32_t>> classes(kNumK);
+        for (int64_t q = 0; q < n_reads; ++q) {
+            const int m = rd->len[(size_t)q];
+            if (m == 0) continue;                                  // score 0, no cells
+            const int K = pick_k(m);
+            for (int k = 0; k < kNumK; ++k) if (kKList[k] == K) classes[(size_t)k].push_back((int32_t)q);
+        }
+        DevBuf<int32_t> d_rp, d_slot;
+        DevBuf<uint32_t> d_ck, d_tmx, d_count;
+        DevBuf<TileTask> d_tasks;
+        DevBuf<uint64_t> d_keys_tmp;
+        DevBuf<uint8_t> d_sort_tmp;
+        CU(d_slot.alloc((size_t)n_reads));
+        CU(d_count.alloc(2));
+        std::vector<int32_t> h_slot((size_t)n_reads);
+
+        for (int kc = 0; kc < kNumK; ++kc) {
+            auto &idx = classes[(size_t)kc];
+            if (idx.empty()) continue;
+            const int K = kKList[kc];
+            const int KW = ((K + 1 + 3) / 4) * 4;
+            std::stable_sort(idx.begin(), idx.end(),
+                             [&](int32_t a, int32_t b) { return rd->len[(size_t)a] > rd->len[(size_t)b]; });
+            const int64_t n_rp_total = ((int64_t)idx.size() + 1) / 2;
+            const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)KW * GL * 4 + GL * 4);
+            int64_t rp_per_batch = std::max<int64_t>(1, ctx->ws_bytes / std::max<int64_t>(bytes_per_rp, 1));
+            rp_per_batch = std::min<int64_t>(rp_per_batch, 1 << 16);
+            if (rp_per_batch * rs->n_refs * 2 >= ((int64_t)1 << 31)) rp_per_batch = std::max<int64_t>(1, (((int64_t)1 << 31) - 1) / (rs->n_refs * 2));
+            for (int64_t rp0 = 0; rp0 < n_rp_total; rp0 += rp_per_batch) {
+                const int n_rp = (int)std::min<int64_t>(rp_per_batch, n_rp_total - rp0);
+                ++n_batches;
+                std::vector<int32_t> h_rp((size_t)n_rp * 2, -1);
+                std::fill(h_slot.begin(), h_slot.end(), -1);
+                int m_max = 0;
+                for (int r = 0; r < n_rp; ++r)
+                    for (int h = 0; h < 2; ++h) {
+                        const int64_t k = (rp0 + r) * 2 + h;
+                        if (k < (int64_t)idx.size()) {
+                            h_rp[(size_t)r * 2 + h] = idx[(size_t)k];
+                            h_slot[(size_t)idx[(size_t)k]] = r * 2 + h;
+                            m_max = std::max(m_max, rd->len[(size_t)idx[(size_t)k]]);
+                        }
+                    }
+                CU(d_rp.alloc(h_rp.size()));
+                CU(cudaMemcpyAsync(d_rp.p, h_rp.data(), h_rp.size() * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(d_slot.p, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
+                const size_t ck_words = (size_t)n_rp * rs->blocks_per_rp * KW * GL;
+                const size_t tmx_words = (size_t)n_rp * rs->blocks_per_rp * GL;
+                if (d_ck.n < ck_words) CU(d_ck.alloc(ck_words));
+                if (d_tmx.n < tmx_words) CU(d_tmx.alloc(tmx_words));
+                ck_bytes += (double)(ck_words + tmx_words) * 4;
+
+                BatchParams P;
+                P.ref_words = rs->words.p; P.ref_word_off = rs->word_off.p; P.ref_len = rs->len.p;
+                P.ref_orig = rs->orig.p; P.ref_sorted_of = rs->sorted_of.p; P.ref_blk_off = rs->blk_off.p;
+                P.n_refs = (int32_t)n_refs; P.blocks_per_rp = rs->blocks_per_rp;
+                P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = d_rp.p; P.read_slot = d_slot.p;
+                P.n_rp = n_rp; P.n_reads = n_reads;
+                P.match = match; P.mismatch = mismatch; P.gap = gap;
+                P.scores = res->d_scores.p; P.ck = d_ck.p; P.tmx = d_tmx.p;
+
+                CU(tic());
+                CU(launch_fill(K, P, ctx->sm_count, st));
+                ++launches;
+                CU(toc(t_fill));
+                if (flags & SWB_F_SCORES_ONLY) continue;
+
+                // ---- flagged tiles -> max cells -> sorted keys ---------------------------
+                CU(tic());
+                uint32_t n_tasks = 0, cap_tasks = (uint32_t)std::min<int64_t>((int64_t)n_rp * 2 * n_refs * 2 + 1024, (int64_t)1 << 31);
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    if (d_tasks.n < cap_tasks) CU(d_tasks.alloc(cap_tasks));
+                    CU(cudaMemsetAsync(d_count.p, 0, 8, st));
+                    CU(launch_flag_tiles(P, d_tasks.p, cap_tasks, d_count.p, st));
+                    ++launches;
+                    CU(cudaMemcpyAsync(&n_tasks, d_count.p, 4, cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    if (n_tasks <= cap_tasks) break;
+                    cap_tasks = n_tasks;
+                }
+                BatchOut bo;
+                bo.K = K;
+                uint32_t n_cells = 0, cap_cells = (uint32_t)std::min<int64_t>((int64_t)n_tasks * 2 + 4096, (int64_t)1 << 31);
+                for (int attempt = 0; attempt < 2; ++attempt) {
+                    if (d_keys_tmp.n < cap_cells) CU(d_keys_tmp.alloc(cap_cells));
+                    CU(cudaMemsetAsync(d_count.p + 1, 0, 4, st));
+                    CU(launch_locate(K, P, d_tasks.p, n_tasks, d_keys_tmp.p, cap_cells, d_count.p + 1, ctx->sm_count, st));
+                    ++launches;
+                    CU(cudaMemcpyAsync(&n_cells, d_count.p + 1, 4, cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    if (n_cells <= cap_cells) break;
+                    cap_cells = n_cells;
+                }
+                bo.n_cells = n_cells;
+                CU(bo.keys.alloc(n_cells));
+                const size_t tmp_bytes = sort_keys_tmp_bytes(n_cells);
+                if (d_sort_tmp.n < tmp_bytes) CU(d_sort_tmp.alloc(tmp_bytes));
+                CU(sort_keys(d_keys_tmp.p, bo.keys.p, n_cells, d_sort_tmp.p, tmp_bytes, st));
+                launches += 4;
+                CU(toc(t_locate));
+
+                // ---- traceback ----------------------------------------------------------
+                CU(tic());
+                const int64_t big = std::max({match, mismatch, 0});
+                int64_t lmax = (int64_t)m_max + (big * m_max - 1) / (-(int64_t)gap) + 1;
+                lmax = std::min<int64_t>(lmax, (int64_t)m_max + rs->max_len);
+                bo.ops_stride = (int)((lmax + 15) / 16);
+                CU(bo.beg.alloc(n_cells));
+                CU(bo.oplen.alloc(n_cells));
+                CU(bo.ops.alloc((size_t)n_cells * bo.ops_stride));
+                CU(launch_trace(K, P, bo.keys.p, n_cells, bo.beg.p, bo.oplen.p, bo.ops.p, bo.ops_stride, ctx->sm_count, st));
+                ++launches;
+                CU(toc(t_trace));
+                res->stats[8] += n_cells;
+                res->batches.push_back(std::move(bo));
+            }
+        }
+    }
+    CU(tic());
+    CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
+    CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, st));
+    launches += 2;
+    double t_misc = 0;
+    CU(toc(t_misc));
+
+    int64_t read_bases = 0;
+    for (int32_t m : rd->len) read_bases += m;
+    res->stats[1] = t_fill; res->stats[2] = t_locate; res->stats[3] = t_trace;
+    res->stats[5] = t_fill + t_locate + t_trace + t_misc;
+    res->stats[6] = (double)rs->total_bases * (double)read_bases;
+    res->stats[7] = (double)n_refs * (double)n_reads;
+    res->stats[9] = launches; res->stats[10] = ck_bytes; res->stats[11] = n_batches;
+    swb_result *r = res.release();
+    if (!(flags & SWB_F_NO_FETCH)) {
+        int rc = swb_result_fetch(r);
+        if (rc) { swb_result_free(r); return rc; }
+    }
+    *out = r;
+    return SWB_OK;
+}
+
+int swb_align(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const char *read_bytes, const int64_t *read_offsets,
+              int32_t match, int32_t mismatch, int32_t gap, uint32_t flags, swb_result **out)
+{
+    if (!out) return fail(SWB_E_INVALID, "swb_align: out is null");
+    *out = nullptr;
+    if (!ctx) return fail(SWB_E_INVALID, "swb_align: ctx is null");
+    swb_reads *rd = nullptr;
+    cudaEvent_t e0, e1;
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+    CU(cudaEventRecord(e0, ctx->stream));
+    int rc = swb_reads_upload(ctx, rs, n_reads, read_bytes, read_offsets, &rd);
+    if (rc) { cudaEventDestroy(e0); cudaEventDestroy(e1); return rc; }
+    cudaEventRecord(e1, ctx->stream);
+    cudaEventSynchronize(e1);
+    float h2d = 0;
+    cudaEventElapsedTime(&h2d, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    rc = swb_align_resident(ctx, rs, rd, match, mismatch, gap, flags, out);
+    swb_reads_free(rd);
+    if (rc == SWB_OK) (*out)->stats[0] = h2d;
+    return rc;
+}
+
+int swb_result_fetch(swb_result *res)
+{
+    if (!res) return fail(SWB_E_INVALID, "swb_result_fetch: null");
+    if (res->fetched) return SWB_OK;
+    swb_ctx *ctx = res->ctx;
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    CU(cudaEventRecord(ctx->ev[0], st));
+    const size_t n_pairs = (size_t)(res->n_refs * res->n_reads);
+    res->scores.resize(n_pairs);
+    res->totals.resize((size_t)res->n_refs);
+    res->best.resize((size_t)res->n_reads * 4);
+    if (n_pairs) CU(cudaMemcpyAsync(res->scores.data(), res->d_scores.p, n_pairs * 4, cudaMemcpyDeviceToHost, st));
+    if (res->n_refs) CU(cudaMemcpyAsync(res->totals.data(), res->d_totals.p, (size_t)res->n_refs * 4, cudaMemcpyDeviceToHost, st));
+    if (res->n_reads) CU(cudaMemcpyAsync(res->best.data(), res->d_best.p, (size_t)res->n_reads * 16, cudaMemcpyDeviceToHost, st));
+    size_t total_cells = 0;
+    std::vector<std::vector<int32_t>> h_beg(res->batches.size()), h_len(res->batches.size());
+    for (size_t b = 0; b < res->batches.size(); ++b) {
+        BatchOut &bo = res->batches[b];
+        bo.h_keys.resize(bo.n_cells);
+        bo.h_ops.resize((size_t)bo.n_cells * bo.ops_stride);
+        h_beg[b].resize(bo.n_cells); h_len[b].resize(bo.n_cells);
+        if (bo.n_cells) {
+            CU(cudaMemcpyAsync(bo.h_keys.data(), bo.keys.p, (size_t)bo.n_cells * 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_beg[b].data(), bo.beg.p, (size_t)bo.n_cells * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(h_len[b].data(), bo.oplen.p, (size_t)bo.n_cells * 4, cudaMemcpyDeviceToHost, st));
+            CU(cudaMemcpyAsync(bo.h_ops.data(), bo.ops.p, bo.h_ops.size() * 4, cudaMemcpyDeviceToHost, st));
+        }
+        total_cells += bo.n_cells;
+    }
+    CU(cudaEventRecord(ctx->ev[1], st));
+    CU(cudaStreamSynchronize(st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    res->stats[4] = ms;
+
+    // merge the batches (each already sorted by key) into pair-major order
+    struct Ent { uint64_t key; uint32_t b, k; };
+    std::vector<Ent> ents;
+    ents.reserve(total_cells);
+    for (size_t b = 0; b < res->batches.size(); ++b)
+        for (uint32_t k = 0; k < res->batches[b].n_cells; ++k) ents.push_back(Ent{res->batches[b].h_keys[k], (uint32_t)b, k});
+    if (res->batches.size() > 1)
+        std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) { return x.key < y.key; });
+    res->cells.resize(total_cells * 2);
+    res->beginnings.resize(total_cells);
+    res->op_lens.resize(total_cells);
+    res->cell_batch.resize(total_cells);
+    res->cell_local.resize(total_cells);
+    res->cell_off.assign(n_pairs + 1, 0);
+    for (size_t c = 0; c < total_cells; ++c) {
+        const Ent &e = ents[c];
+        res->cells[2 * c] = (int32_t)key_i(e.key);
+        res->cells[2 * c + 1] = (int32_t)key_j(e.key);
+        res->beginnings[c] = h_beg[e.b][e.k];
+        res->op_lens[c] = h_len[e.b][e.k];
+        res->cell_batch[c] = e.b; res->cell_local[c] = e.k;
+        res->cell_off[(size_t)key_pair(e.key) + 1] += 1;
+    }
+    for (size_t p = 0; p < n_pairs; ++p) res->cell_off[p + 1] += res->cell_off[p];
+    for (int64_t q = 0; q < res->n_reads; ++q) {
+        const int32_t ref = res->best[(size_t)q * 4 + 1];
+        if (ref < 0) continue;
+        const size_t p = (size_t)ref * res->n_reads + q;
+        if (res->cell_off[p + 1] > res->cell_off[p]) {
+            res->best[(size_t)q * 4 + 2] = res->cells[2 * (size_t)res->cell_off[p]];
+            res->best[(size_t)q * 4 + 3] = res->cells[2 * (size_t)res->cell_off[p] + 1];
+        }
+    }
+    if (res->n_reads) CU(cudaMemcpy(res->d_best.p, res->best.data(), (size_t)res->n_reads * 16, cudaMemcpyHostToDevice));
+    res->fetched = true;
+    return SWB_OK;
+}
+
+void swb_result_free(swb_result *res)
+{
+    if (!res) return;
+    cudaSetDevice(res->ctx->device);
+    delete res;
+}
+
+int64_t swb_result_n_refs(const swb_result *r) { return r ? r->n_refs : 0; }
+int64_t swb_result_n_reads(const swb_result *r) { return r ? r->n_reads : 0; }
+const int32_t *swb_result_scores(const swb_result *r) { return (r && r->fetched) ? r->scores.data() : nullptr; }
+const int32_t *swb_result_ref_totals(const swb_result *r) { return (r && r->fetched) ? r->totals.data() : nullptr; }
+const int32_t *swb_result_best_hits(const swb_result *r) { return (r && r->fetched) ? r->best.data() : nullptr; }
+const int64_t *swb_result_cell_offsets(const swb_result *r) { return (r && r->fetched) ? r->cell_off.data() : nullptr; }
+int64_t swb_result_total_cells(const swb_result *r) { return (r && r->fetched) ? (int64_t)r->beginnings.size() : 0; }
+const int32_t *swb_result_cells(const swb_result *r) { return (r && r->fetched) ? r->cells.data() : nullptr; }
+const int32_t *swb_result_beginnings(const swb_result *r) { return (r && r->fetched) ? r->beginnings.data() : nullptr; }
+const int32_t *swb_result_op_lens(const swb_result *r) { return (r && r->fetched) ? r->op_lens.data() : nullptr; }
+
+int64_t swb_result_pair_cell_count(const swb_result *r, int64_t pair)
+{
+    if (!r || !r->fetched || pair < 0 || pair >= r->n_refs * r->n_reads) return -1;
+    if (r->flags & SWB_F_SCORES_ONLY) return -1;
+    if (r->scores[(size_t)pair] == 0) {
+        const int64_t ref = pair / r->n_reads, rd = pair % r->n_reads;
+        return (int64_t)r->ref_len[(size_t)ref] * r->read_len[(size_t)rd];     // every cell ties at 0
+    }
+    return r->cell_off[(size_t)pair + 1] - r->cell_off[(size_t)pair];
+}
+
+int swb_result_pair_cell(const swb_result *r, int64_t pair, int64_t k, int32_t *i, int32_t *j, int32_t *beginning,
+                         int32_t *op_len)
+{
+    const int64_t cnt = swb_result_pair_cell_count(r, pair);
+    if (cnt < 0) return fail(SWB_E_RANGE, "swb_result_pair_cell: bad pair");
+    if (k < 0 || k >= cnt) return fail(SWB_E_RANGE, "swb_result_pair_cell: bad cell index");
+    if (r->scores[(size_t)pair] == 0) {
+        const int64_t n = r->ref_len[(size_t)(pair / r->n_reads)];
+        if (i) *i = (int32_t)(k / n + 1);
+        if (j) *j = (int32_t)(k % n + 1);
+        if (beginning) *beginning = 0;
+        if (op_len) *op_len = 0;
+        return SWB_OK;
+    }
+    const size_t c = (size_t)(r->cell_off[(size_t)pair] + k);
+    if (i) *i = r->cells[2 * c];
+    if (j) *j = r->cells[2 * c + 1];
+    if (beginning) *beginning = r->beginnings[c];
+    if (op_len) *op_len = r->op_lens[c];
+    return SWB_OK;
+}
+
+int swb_result_ops(const swb_result *r, int64_t cell, uint8_t *outp, int64_t cap)
+{
+    if (!r || !r->fetched || !outp) return fail(SWB_E_INVALID, "swb_result_ops: null / not fetched");
+    if (cell < 0 || cell >= (int64_t)r->beginnings.size()) return fail(SWB_E_RANGE, "swb_result_ops: bad cell");
+    const int32_t len = r->op_lens[(size_t)cell];
+    if (cap < len) return fail(SWB_E_RANGE, "swb_result_ops: buffer too small");
+    const BatchOut &bo = r->batches[r->cell_batch[(size_t)cell]];
+    const uint32_t *w = bo.h_ops.data() + (size_t)r->cell_local[(size_t)cell] * bo.ops_stride;
+    // the device stores the walk order (end -> start); hand out start -> end
+    for (int32_t k = 0; k < len; ++k) {
+        const int32_t src = len - 1 - k;
+        outp[k] = (uint8_t)((w[src >> 4] >> (2 * (src & 15))) & 3u);
+    }
+    return SWB_OK;
+}
+
+int swb_result_materialize(const swb_result *r, int64_t cell, const char *ref, int64_t ref_len, const char *read,
+                           int64_t read_len, char *ref_aln, char *read_aln, int64_t cap)
+{
+    if (!r || !r->fetched || !ref_aln || !read_aln) return fail(SWB_E_INVALID, "swb_result_materialize: null / not fetched");
+    if (cell < 0 || cell >= (int64_t)r->beginnings.size()) return fail(SWB_E_RANGE, "swb_result_materialize: bad cell");
+    const int32_t len = r->op_lens[(size_t)cell];
+    if (cap < (int64_t)len + 1) return fail(SWB_E_RANGE, "swb_result_materialize: buffer too small");
+    std::vector<uint8_t> ops((size_t)len + 1);
+    int rc = swb_result_ops(r, cell, ops.data(), len);
+    if (rc) return rc;
+    // walk the columns backwards from the end cell (SmithWaterman.java:380-409), fill forwards
+    int64_t i = r->cells[2 * (size_t)cell], j = r->cells[2 * (size_t)cell + 1];
+    if (i > read_len || j > ref_len) return fail(SWB_E_RANGE, "swb_result_materialize: sequences shorter than the cell");
+    for (int32_t k = len - 1; k >= 0; --k) {
+        const uint8_t op = ops[(size_t)k];
+        if (op == 1)      { if (i < 1 || j < 1) return fail(SWB_E_RANGE, "materialize: path leaves the matrix"); ref_aln[k] = ref[j - 1]; read_aln[k] = read[i - 1]; --i; --j; }
+        else if (op == 2) { if (i < 1) return fail(SWB_E_RANGE, "materialize: path leaves the matrix"); ref_aln[k] = '_'; read_aln[k] = read[i - 1]; --i; }
+        else              { if (j < 1) return fail(SWB_E_RANGE, "materialize: path leaves the matrix"); ref_aln[k] = ref[j - 1]; read_aln[k] = '_'; --j; }
+    }
+    ref_aln[len] = 0; read_aln[len] = 0;
+    return SWB_OK;
+}
+
+int swb_result_stats(const swb_result *r, double *outp, int n)
+{
+    if (!r || !outp) return fail(SWB_E_INVALID, "swb_result_stats: null");
+    for (int k = 0; k < n && k < 12; ++k) outp[k] = r->stats[k];
+    return SWB_OK;
+}
+
+int swb_result_device_ptr(const swb_result *r, int which, void **ptr, int64_t *n_elems)
+{
+    if (!r || !ptr) return fail(SWB_E_INVALID, "swb_result_device_ptr: null");
+    switch (which) {
+        case 0: *ptr = r->d_scores.p; if (n_elems) *n_elems = r->n_refs * r->n_reads; return SWB_OK;
+        case 1: *ptr = r->d_totals.p; if (n_elems) *n_elems = r->n_refs; return SWB_OK;
+        case 2: *ptr = r->d_best.p; if (n_elems) *n_elems = r->n_reads * 4; return SWB_OK;
+    }
+    return fail(SWB_E_RANGE, "swb_result_device_ptr: bad selector");
+}
+
+}  // extern "C"

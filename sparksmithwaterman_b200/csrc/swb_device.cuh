@@ -1,0 +1,95 @@
+// swb_device.cuh -- device helpers: DPX wrappers (inline PTX so that ptxas emits exactly
+// VIADDMNMX / VIMNMX3 / VIMNMX and no operand-repacking PRMTs), profile loads, checkpoints.
+#pragma once
+#include <cstdint>
+#include "swb_internal.h"
+
+namespace swb {
+
+__host__ __device__ __forceinline__ uint32_t pack2(int lo, int hi)
+{
+    return ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
+}
+
+// per-halfword max(a + b, c)            -> VIADDMNMX.S16x2
+__device__ __forceinline__ uint32_t viaddmax(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("{.reg .b32 t; add.s16x2 t, %1, %2; max.s16x2 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// per-halfword max(a + b, c, 0)         -> VIADDMNMX.S16x2.RELU
+__device__ __forceinline__ uint32_t viaddmax_relu(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("{.reg .b32 t; add.s16x2 t, %1, %2; max.s16x2.relu %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+// per-halfword max(a, b)                -> VIMNMX.S16x2
+__device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("max.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+// per-halfword max(a, b, c)             -> VIMNMX3.S16x2
+__device__ __forceinline__ uint32_t vmax3(uint32_t a, uint32_t b, uint32_t c)
+{
+    uint32_t r;
+    asm("{.reg .b32 t; max.s16x2 t, %1, %2; max.s16x2 %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+
+// running maximum over a lane's K cells of one column: ceil(K/2) VIMNMX3
+template <int K>
+__device__ __forceinline__ uint32_t colmax(uint32_t m, const uint32_t (&H)[K])
+{
+#pragma unroll
+    for (int r = 0; r + 1 < K; r += 2) m = vmax3(m, H[r], H[r + 1]);
+    if (K & 1) m = vmax2(m, H[K - 1]);
+    return m;
+}
+
+// KP profile words of one reference code for this lane: KP/4 conflict-free LDS.128
+template <int KP>
+__device__ __forceinline__ void load_profile(const uint32_t *p, uint32_t (&sv)[KP])
+{
+    const uint4 *p4 = reinterpret_cast<const uint4 *>(p);
+#pragma unroll
+    for (int q = 0; q < KP / 4; ++q) {
+        const uint4 v = p4[q];
+        sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
+    }
+}
+
+// checkpoint of one lane: words 0..K-1 = H, word K = diag.  Layout per block:
+// [KW/4 quads][GL lanes][4 words] so that each STG.128 of a group is 128 contiguous bytes.
+// `ck` already points at this lane's first quad (+ t*4 words).
+template <int K>
+__device__ __forceinline__ void store_checkpoint(uint32_t *ck, const uint32_t (&H)[K], uint32_t diag)
+{
+    constexpr int KW = Geo<K>::KW;
+#pragma unroll
+    for (int q = 0; q < KW / 4; ++q) {
+        uint4 v;
+        v.x = (4 * q + 0 < K) ? H[(4 * q + 0 < K) ? 4 * q + 0 : 0] : ((4 * q + 0 == K) ? diag : 0u);
+        v.y = (4 * q + 1 < K) ? H[(4 * q + 1 < K) ? 4 * q + 1 : 0] : ((4 * q + 1 == K) ? diag : 0u);
+        v.z = (4 * q + 2 < K) ? H[(4 * q + 2 < K) ? 4 * q + 2 : 0] : ((4 * q + 2 == K) ? diag : 0u);
+        v.w = (4 * q + 3 < K) ? H[(4 * q + 3 < K) ? 4 * q + 3 : 0] : ((4 * q + 3 == K) ? diag : 0u);
+        *reinterpret_cast<uint4 *>(ck + q * (GL * 4)) = v;
+    }
+}
+
+// word w (0..K) of lane t's checkpoint in block-relative layout
+template <int K>
+__device__ __forceinline__ uint32_t load_checkpoint_word(const uint32_t *blk, int t, int w)
+{
+    return blk[(w >> 2) * (GL * 4) + t * 4 + (w & 3)];
+}
+
+__device__ __forceinline__ int half_of(uint32_t w, int half)
+{
+    return half ? (int)(int16_t)(w >> 16) : (int)(int16_t)(w & 0xffffu);
+}
+
+}  // namespace swb

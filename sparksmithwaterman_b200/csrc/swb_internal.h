@@ -1,0 +1,98 @@
+// swb_internal.h -- shared declarations of libswb200 (host structs, kernel launch API).
+//
+// Geometry of the short-read path (reads up to 8*32 = 256 rows)
+//   * a GROUP of GL = 8 lanes owns one (read pair, reference) task; lane t owns the K
+//     consecutive read rows t*K+1 .. t*K+K and marches along the reference columns,
+//   * the 8 lanes form a skewed wavefront: at STEP s lane t computes column j = s - t + 1,
+//     the boundary row travels to lane t+1 with one __shfl_up_sync per step,
+//   * two reads are packed in the two s16 halves of every register (DPX s16x2 ops),
+//   * every CB steps the lanes' registers (K cells + the diagonal boundary) are written to
+//     HBM as a CHECKPOINT, together with the tile maximum of the last CB steps; the
+//     traceback kernels restart from a checkpoint and recompute only the blocks a path
+//     crosses, so no direction plane is ever written.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+#include <string>
+#include <vector>
+
+#include "../../include/swb200.h"
+
+namespace swb {
+
+constexpr int GL = 8;        // lanes per group
+constexpr int CB = 32;       // steps per checkpoint block (multiple of 16)
+constexpr int MAX_SHORT_ROWS = GL * 32;
+
+// rows-per-lane variants compiled for the short path
+constexpr int kNumK = 7;
+constexpr int kKList[kNumK] = {4, 8, 13, 16, 19, 25, 32};
+
+template <int K> struct Geo {
+    static constexpr int KW = ((K + 1 + 3) / 4) * 4;            // checkpoint words per lane (K cells + diag)
+    static constexpr int KP = ((K + 3) / 4) * 4;                // profile words per lane per code
+    static constexpr int KS = ((KP / 4) % 2 == 1) ? KP : KP + 4; // padded: odd number of 16B units -> conflict-free LDS.128
+    static constexpr int CSTRIDE = GL * KS;                     // words per reference code
+    static constexpr int PROF_WORDS = 4 * CSTRIDE;
+    static constexpr int RS = ((K + 1 + 1) / 2) * 2;            // traceback tile row stride (halfwords)
+    static constexpr int TILE_HALFWORDS = GL * (CB + 1) * RS;   // per group
+};
+
+constexpr int16_t S_PAD = -16384;   // profile score of a padding row (beyond the read's end)
+
+// key of one maximum cell: pair p (33 bits) | i (9 bits) | j (22 bits)
+constexpr int KEY_J_BITS = 22, KEY_I_BITS = 9;
+__host__ __device__ inline uint64_t make_key(uint64_t p, uint32_t i, uint32_t j)
+{ return (p << (KEY_J_BITS + KEY_I_BITS)) | ((uint64_t)i << KEY_J_BITS) | j; }
+__host__ __device__ inline uint64_t key_pair(uint64_t k) { return k >> (KEY_J_BITS + KEY_I_BITS); }
+__host__ __device__ inline uint32_t key_i(uint64_t k) { return (uint32_t)(k >> KEY_J_BITS) & ((1u << KEY_I_BITS) - 1); }
+__host__ __device__ inline uint32_t key_j(uint64_t k) { return (uint32_t)k & ((1u << KEY_J_BITS) - 1); }
+
+struct TileTask { uint32_t rp_half; uint32_t ref_sorted; uint32_t block; uint32_t lane_mask; };
+
+// Everything the short-path kernels need for one batch of read pairs of one K class.
+struct BatchParams {
+    // reference set (sorted by descending length)
+    const uint32_t *ref_words;      // 2-bit codes, 16 per word
+    const uint32_t *ref_word_off;   // [n_refs] first word of sorted ref
+    const int32_t  *ref_len;        // [n_refs]
+    const int32_t  *ref_orig;       // [n_refs] sorted -> original index
+    const int32_t  *ref_sorted_of;  // [n_refs] original -> sorted index
+    const int64_t  *ref_blk_off;    // [n_refs+1] prefix of checkpoint blocks per sorted ref
+    int32_t n_refs;
+    int64_t blocks_per_rp;          // ref_blk_off[n_refs]
+    // reads
+    const uint8_t *read_codes;      // 1 byte per base: 0..3, 0xFF = matches nothing
+    const int64_t *read_off;        // [n_reads+1]
+    const int32_t *rp_reads;        // [n_rp][2] read indices of the batch's pairs (-1 = none)
+    const int32_t *read_slot;       // [n_reads] rp_local*2+half for reads of this batch, else -1
+    int32_t n_rp;
+    int64_t n_reads;                // reads in the whole call (pair index stride)
+    // scores
+    int32_t match, mismatch, gap;
+    // outputs / workspace
+    int32_t  *scores;               // [n_refs_orig * n_reads]
+    uint32_t *ck;                   // checkpoints  [n_rp][blocks_per_rp][KW/4][GL][4]
+    uint32_t *tmx;                  // tile maxima  [n_rp][blocks_per_rp][GL]
+};
+
+struct LaunchStats { int launches = 0; };
+
+// swb_fill.cu
+cudaError_t launch_fill(int K, const BatchParams &P, int sm_count, cudaStream_t st);
+// swb_trace.cu
+cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, cudaStream_t st);
+cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, uint32_t n_tasks,
+                          uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st);
+cudaError_t launch_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells,
+                         int32_t *beginnings, int32_t *op_lens, uint32_t *ops, int ops_stride_words,
+                         int sm_count, cudaStream_t st);
+cudaError_t launch_cell_offsets(const uint64_t *keys, uint32_t n_cells, const int64_t *pair_ids, int64_t n_pairs,
+                                int64_t *offsets, cudaStream_t st);
+cudaError_t launch_ref_totals(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *totals, cudaStream_t st);
+cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, cudaStream_t st);
+cudaError_t sort_keys(uint64_t *keys_in, uint64_t *keys_out, uint32_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
+size_t      sort_keys_tmp_bytes(uint32_t n);
+
+}  // namespace swb
