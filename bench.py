@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""bench.py -- GCUPS (including traceback) of the Smith-Waterman hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--reads-per-step B] [--impl reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Workload = BASELINE.json configs[1]: 150 bp reads vs 10,000 RefSeq-shaped references
+(lognormal lengths, mean 2,160 / median 1,609 bp), default scores 5/-3/-4.  A STEP is one
+batch of B reads (a slice of the 100k-read job) aligned against ALL references resident in
+HBM: fill, every max cell, every traceback.  GCUPS = sum(m*n) / 1e9 / seconds.
+
+  value : reads already resident in HBM, results left in HBM (swb_align_resident)
+  e2e   : the reference-facing C-ABI call with HOST buffers (swb_align): H2D of the reads
+          and D2H of scores, max-cell lists and packed alignments inside the timed region
+  N > 1 : the reference set is sharded over the ranks (balanced by length), every rank
+          aligns the same reads against its shard, and the per-read best-hit records are
+          merged with one NCCL all_gather per step (weak scaling: 10k refs per GPU).
+
+`--impl reference` times the reference's CPU path instead: the C restatement of
+SmithWaterman.java under oracle/ (no JVM exists in this image) on all host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SCORES = (5, -3, -4)
+METRIC = "GCUPS incl. traceback (150 bp reads x 10k RefSeq-shaped refs per B200)"
+UNIT = "GCUPS"
+READ_LEN = 150
+N_REFS_PER_GPU = 10_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=4)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--reads-per-step", type=int, default=128)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workspace-gb", type=float, default=16.0)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), d.get("sm_max_mhz", 1965.0), "measured"
+    return 6650.0, 1965.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc = index, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for k, nm in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        # samples under load = upper half (the sampler also sees the idle edges)
+        load = sm[len(sm) // 2:] if sm else []
+        med = load[len(load) // 2] if load else None
+        return {"sm_mhz": med, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power) if power else None}
+
+
+def shard_refs(refs, rank: int, world: int):
+    """Balanced shard: sort by length, deal round-robin."""
+    order = sorted(range(len(refs)), key=lambda k: -len(refs[k]))
+    mine = sorted(order[rank::world])
+    return [refs[k] for k in mine], mine
+
+
+def cpu_baseline_leg(refs, reads, threads, target_cells=2.0e10):
+    """Oracle CPU harness (C restatement of the Java path) on a bounded sample."""
+    import oracle
+    n_refs = min(len(refs), 1000)
+    sub_refs = refs[:n_refs]
+    ref_bases = sum(len(r) for r in sub_refs)
+    n_reads = max(1, min(len(reads), int(target_cells / (ref_bases * READ_LEN))))
+    r = oracle.cpu_baseline(sub_refs, reads[:n_reads], *SCORES, threads=threads, mode=1)
+    return {"value": round(r["gcups"], 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "sample": f"{n_reads} x {READ_LEN} bp reads vs first {n_refs} refs of the workload "
+                      f"({r['cells']:.3g} cells, {r['seconds']:.1f} s), dynamic ref queue over {threads} threads, "
+                      "C restatement of SmithWaterman.java (no JVM in this image)",
+            "reads_per_s": round(n_reads / r["seconds"] * (n_refs / len(refs)), 4),
+            "seconds": round(r["seconds"], 3)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path, all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    from sparksmithwaterman_b200 import synth
+    oracle.build()
+    threads = os.cpu_count() or 1
+    refs = synth.make_refs(1000)
+    reads = synth.make_reads(max(8, args.reads_per_step // 16) * (args.steps + args.warmup), READ_LEN, refs)
+    per = max(1, len(reads) // (args.steps + args.warmup))
+    # size one step to ~5 s
+    ref_bases = sum(len(r) for r in refs)
+    probe = oracle.cpu_baseline(refs[:200], reads[:2], *SCORES, threads=threads, mode=1)
+    rate = probe["cells"] / probe["seconds"]
+    per = max(1, min(per, int(5.0 * rate / (ref_bases * READ_LEN))))
+    for w in range(args.warmup):
+        oracle.cpu_baseline(refs[:100], reads[:1], *SCORES, threads=threads, mode=1)
+    t0 = time.perf_counter()
+    cells = 0
+    for k in range(args.steps):
+        r = oracle.cpu_baseline(refs, reads[k * per:(k + 1) * per], *SCORES, threads=threads, mode=1)
+        cells += r["cells"]
+    dt = time.perf_counter() - t0
+    v = cells / 1e9 / dt
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": "cfg2 sample: 150 bp reads vs first 1,000 of the 10k RefSeq-shaped refs",
+                       "reads_per_step": per, "refs": len(refs)},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{per} reads x {len(refs)} refs per step, {args.steps} steps; "
+                                       "C restatement of SmithWaterman.java + MapRef loop (no JVM in this image), "
+                                       "dynamic ref queue over all host threads"},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    import sparksmithwaterman_b200 as swb
+    from sparksmithwaterman_b200 import synth
+    from sparksmithwaterman_b200.build import build_native
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if rank == 0:
+        build_native()
+    if dist:
+        dist.barrier()
+
+    B, K, W = args.reads_per_step, args.steps, args.warmup
+    # weak scaling: 10k refs per GPU; every rank generates the same global set and keeps its shard
+    all_refs = synth.make_refs(N_REFS_PER_GPU * world)
+    refs, my_ids = shard_refs(all_refs, rank, world)
+    reads_pool = synth.make_reads(B * (W + K), READ_LEN, all_refs)
+    step_reads = [reads_pool[k * B:(k + 1) * B] for k in range(W + K)]
+
+    eng = swb.Engine(local_rank, int(args.workspace_gb * (1 << 30)))
+    t0 = time.perf_counter()
+    rs = eng.load_refset(refs)
+    torch.cuda.synchronize()
+    refset_load_ms = (time.perf_counter() - t0) * 1e3
+    ref_bases = rs.total_bases
+    cells_per_step_local = ref_bases * READ_LEN * B
+    stream = torch.cuda.ExternalStream(eng.stream_ptr, device=torch.device("cuda", local_rank))
+    my_ids_t = torch.tensor(my_ids, dtype=torch.int32, device="cuda")
+
+    def step_resident(rd, fetch=False):
+        return rd.align(SCORES, scores_only=False, fetch=fetch)
+
+    def allgather_best(res):
+        if not dist:
+            return
+        best = torch.as_tensor(res.device_array(2, (res.n_reads, 4)), device="cuda").clone()
+        best[:, 1] = my_ids_t[best[:, 1].long().clamp(min=0)]          # shard-local -> global ref id
+        out = [torch.empty_like(best) for _ in range(world)]
+        dist.all_gather(out, best)
+        allb = torch.stack(out)                                         # [world, B, 4]
+        key = allb[:, :, 0].long() * (1 << 32) - allb[:, :, 1].long()  # max score, then lowest ref id
+        win = key.argmax(dim=0)
+        return allb[win, torch.arange(allb.shape[1], device="cuda")]
+
+    # resident read batches (inputs in HBM before the timed region)
+    resident = [rs.upload_reads(r) for r in step_reads]
+    for k in range(W):
+        res = step_resident(resident[k]); allgather_best(res); res.free()
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    agg = {"fill_ms": 0.0, "locate_ms": 0.0, "trace_ms": 0.0, "launches": 0.0, "checkpoint_bytes": 0.0,
+           "max_cells": 0.0, "batches": 0.0}
+    for k in range(W, W + K):
+        res = step_resident(resident[k])
+        st = res.stats
+        for key in agg:
+            agg[key] += st[key]
+        allgather_best(res)
+        res.free()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    if dist:
+        dist.barrier()
+    clocks = sampler.stop()
+    dev_ms = ev0.elapsed_time(ev1)
+    step_ms = max(dev_ms, t_wall * 1e3) / K          # events and wall agree unless the host lags
+    if dist:
+        t = torch.tensor([step_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        step_ms = float(t.item())
+        c = torch.tensor([float(cells_per_step_local)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(c, op=dist.ReduceOp.SUM)
+        cells_per_step = float(c.item())
+    else:
+        cells_per_step = float(cells_per_step_local)
+    value = cells_per_step / 1e9 / (step_ms * 1e-3)
+
+    # ---- e2e: host buffers through swb_align, H2D + D2H inside the timed region ----------
+    torch.cuda.synchronize()
+    if dist:
+        dist.barrier()
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    for k in range(W, W + K):
+        res = rs.align(step_reads[k], SCORES)                     # upload + compute + fetch
+        sc = res.scores                                            # results are on the host now
+        nc = res.total_cells
+        h2d = sum(len(r) for r in step_reads[k]) + 8 * (B + 1)
+        stride_guess = 22 * 4
+        d2h = sc.nbytes + 4 * len(refs) + 16 * B + nc * (8 + 4 + 4 + stride_guess)
+        allgather_best(res)
+        res.free()
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    if dist:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = cells_per_step / 1e9 / (e2e_ms * 1e-3)
+
+    if rank != 0:
+        if dist:
+            dist.destroy_process_group()
+        return
+
+    hbm_peak, sm_max, peak_kind = peaks()
+    sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+    # DPX roofline: 64 integer-pipe lane-ops/clk/SM (measured, profiles/dpx_microbench_r01.json),
+    # 2 lane-ops per cell at the s16x2 minimum
+    peak_gcups = sms * sm_max * 1e6 * 64 / 2 / 1e9
+    fill_gcups = cells_per_step_local * K / 1e9 / (agg["fill_ms"] * 1e-3) if agg["fill_ms"] > 0 else 0.0
+    run_clock = clocks.get("sm_mhz") or sm_max
+    roofline = {"bound": "int_dpx", "kernel": "fill_kernel<19>", "achieved": round(fill_gcups, 1),
+                "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4),
+                "peak_def": f"{sms} SMs x {sm_max:.0f} MHz ({peak_kind} sm_max_mhz) x 64 int lane-ops/clk/SM "
+                            "(measured: profiles/dpx_microbench_r01.json) / 2 ops per s16x2 cell",
+                "frac_at_run_clock": round(fill_gcups / (peak_gcups * run_clock / sm_max), 4),
+                "traffic": None,
+                "hbm": {"algorithmic_bytes_per_launch": agg["checkpoint_bytes"] / max(agg["batches"], 1),
+                        "achieved_gbs": round(agg["checkpoint_bytes"] / 1e9 / (agg["fill_ms"] * 1e-3), 1)
+                        if agg["fill_ms"] > 0 else 0.0,
+                        "peak_gbs": hbm_peak, "peak_kind": peak_kind,
+                        "note": "checkpoint + tile-max writes of the fill; HBM is the secondary bound"},
+                "fill_ms_per_step": round(agg["fill_ms"] / K, 3), "locate_ms_per_step": round(agg["locate_ms"] / K, 3),
+                "trace_ms_per_step": round(agg["trace_ms"] / K, 3)}
+    line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "s16x2", "data": "synthetic",
+            "config": {"workload": "cfg2: 150 bp reads vs 10,000 RefSeq-shaped refs per GPU, scores 5/-3/-4; "
+                                   f"step = {B} reads of the 100k-read job x all refs, fill + all max cells + traceback",
+                       "reads_per_step": B, "refs_per_gpu": len(refs), "ref_bases_per_gpu": int(ref_bases),
+                       "pairs_per_step": B * len(refs) * world,
+                       "l2": "per-step working set (checkpoints, GBs) exceeds the 126 MB L2; no explicit flush",
+                       "parallelism": f"refshard{world}" if world > 1 else "single"},
+            "reads_per_s": round(B / (step_ms * 1e-3), 1),
+            "refset_load_ms": round(refset_load_ms, 1),
+            "roofline": roofline, "clocks": clocks,
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
+                    "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": int(agg["launches"]), "max_cells_per_step": int(agg["max_cells"] / K)}
+    if not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_leg(all_refs, reads_pool, os.cpu_count() or 1)
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU numbers
+            line["cpu_baseline"] = {"error": repr(e)}
+    print(json.dumps(line), flush=True)
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -140,6 +140,10 @@ int swb_result_stats(const swb_result *res, double *out, int n);
  * host round trip): which = 0 scores, 1 ref_totals, 2 best_hits. */
 int swb_result_device_ptr(const swb_result *res, int which, void **ptr, int64_t *n_elems);
 
+/* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so a
+ * host can bracket calls with its own events on that stream. */
+int swb_get_stream(swb_ctx *ctx, void **stream);
+
 /* Integer / DPX issue-rate microbenchmark (roofline denominator). */
 int swb_microbench_json(int device, int iters, char *buf, int buflen);
 

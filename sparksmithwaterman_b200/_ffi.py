@@ -52,6 +52,7 @@ SIGNATURES = {
                                          C.c_char_p, C.c_char_p, C.c_int64]),
     "swb_result_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
     "swb_result_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P), _I64P]),
+    "swb_get_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "swb_microbench_json": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_int]),
 }
 

@@ -164,6 +164,13 @@ void swb_destroy(swb_ctx *c)
     delete c;
 }
 
+int swb_get_stream(swb_ctx *ctx, void **stream)
+{
+    if (!ctx || !stream) return fail(SWB_E_INVALID, "swb_get_stream: null");
+    *stream = (void *)ctx->stream;
+    return SWB_OK;
+}
+
 static int check_offsets(const char *who, int64_t n, const char *bytes, const int64_t *off)
 {
     if (n < 0) return fail(SWB_E_INVALID, std::string(who) + ": negative count");
@@ -358,6 +365,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     CU(res->d_best.alloc((size_t)n_reads * 4));
     CU(cudaMemsetAsync(res->d_scores.p, 0, std::max<size_t>(n_pairs, 1) * 4, st));
 
+    std::vector<int32_t> h_read_batch;
     double t_fill = 0, t_locate = 0, t_trace = 0, ck_bytes = 0;
     int launches = 1, n_batches = 0;
     auto tic = [&]() { return cudaEventRecord(ctx->ev[0], st); };
@@ -389,6 +397,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
         CU(d_slot.alloc((size_t)n_reads));
         CU(d_count.alloc(2));
         std::vector<int32_t> h_slot((size_t)n_reads);
+        h_read_batch.assign((size_t)n_reads, -1);
 
         for (int kc = 0; kc < kNumK; ++kc) {
             auto &idx = classes[(size_t)kc];
@@ -488,6 +497,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 ++launches;
                 CU(toc(t_trace));
                 res->stats[8] += n_cells;
+                for (int32_t v : h_rp) if (v >= 0) h_read_batch[(size_t)v] = (int32_t)res->batches.size();
                 res->batches.push_back(std::move(bo));
             }
         }
@@ -496,6 +506,22 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
     CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, st));
     launches += 2;
+    DevBuf<int32_t> d_read_batch;
+    DevBuf<const uint64_t *> d_bkeys;
+    DevBuf<uint32_t> d_bn;
+    if (!res->batches.empty() && n_reads > 0) {
+        std::vector<const uint64_t *> hk;
+        std::vector<uint32_t> hn;
+        for (auto &bo : res->batches) { hk.push_back(bo.keys.p); hn.push_back(bo.n_cells); }
+        CU(d_read_batch.alloc((size_t)n_reads));
+        CU(d_bkeys.alloc(hk.size()));
+        CU(d_bn.alloc(hn.size()));
+        CU(cudaMemcpyAsync(d_read_batch.p, h_read_batch.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_bkeys.p, hk.data(), hk.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_bn.p, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice, st));
+        CU(launch_best_cells(res->d_best.p, n_reads, d_read_batch.p, d_bkeys.p, d_bn.p, st));
+        ++launches;
+    }
     double t_misc = 0;
     CU(toc(t_misc));
 
@@ -600,16 +626,6 @@ int swb_result_fetch(swb_result *res)
         res->cell_off[(size_t)key_pair(e.key) + 1] += 1;
     }
     for (size_t p = 0; p < n_pairs; ++p) res->cell_off[p + 1] += res->cell_off[p];
-    for (int64_t q = 0; q < res->n_reads; ++q) {
-        const int32_t ref = res->best[(size_t)q * 4 + 1];
-        if (ref < 0) continue;
-        const size_t p = (size_t)ref * res->n_reads + q;
-        if (res->cell_off[p + 1] > res->cell_off[p]) {
-            res->best[(size_t)q * 4 + 2] = res->cells[2 * (size_t)res->cell_off[p]];
-            res->best[(size_t)q * 4 + 3] = res->cells[2 * (size_t)res->cell_off[p] + 1];
-        }
-    }
-    if (res->n_reads) CU(cudaMemcpy(res->d_best.p, res->best.data(), (size_t)res->n_reads * 16, cudaMemcpyHostToDevice));
     res->fetched = true;
     return SWB_OK;
 }

@@ -92,6 +92,8 @@ cudaError_t launch_cell_offsets(const uint64_t *keys, uint32_t n_cells, const in
                                 int64_t *offsets, cudaStream_t st);
 cudaError_t launch_ref_totals(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *totals, cudaStream_t st);
 cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, cudaStream_t st);
+cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, const int32_t *read_batch,
+                              const uint64_t *const *batch_keys, const uint32_t *batch_n, cudaStream_t st);
 cudaError_t sort_keys(uint64_t *keys_in, uint64_t *keys_out, uint32_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t      sort_keys_tmp_bytes(uint32_t n);
 

@@ -440,6 +440,36 @@ cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_re
     return cudaGetLastError();
 }
 
+// fill (i, j) of each read's best hit: first key of pair (best ref, read) in the read's batch
+__global__ void best_cells_kernel(int32_t *best, int64_t n_reads, const int32_t *read_batch,
+                                  const uint64_t *const *batch_keys, const uint32_t *batch_n)
+{
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n_reads) return;
+    const int b = read_batch[q];
+    const int ref = best[4 * q + 1];
+    if (b < 0 || ref < 0 || best[4 * q] <= 0) return;
+    const uint64_t *keys = batch_keys[b];
+    const uint64_t p = (uint64_t)ref * (uint64_t)n_reads + (uint64_t)q;
+    const uint64_t target = make_key(p, 0, 0);
+    uint32_t lo = 0, hi = batch_n[b];
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+    if (lo < batch_n[b] && key_pair(keys[lo]) == p) {
+        best[4 * q + 2] = (int32_t)key_i(keys[lo]);
+        best[4 * q + 3] = (int32_t)key_j(keys[lo]);
+    }
+}
+
+cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, const int32_t *read_batch,
+                              const uint64_t *const *batch_keys, const uint32_t *batch_n, cudaStream_t st)
+{
+    if (n_reads == 0) return cudaSuccess;
+    const int threads = 128;
+    best_cells_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(best, n_reads, read_batch,
+                                                                                        batch_keys, batch_n);
+    return cudaGetLastError();
+}
+
 size_t sort_keys_tmp_bytes(uint32_t n)
 {
     size_t bytes = 0;

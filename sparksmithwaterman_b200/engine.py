@@ -50,6 +50,13 @@ class Engine:
         except Exception:
             pass
 
+    @property
+    def stream_ptr(self) -> int:
+        """cudaStream_t the engine launches on (for external event timing)."""
+        p = C.c_void_p()
+        check(self.lib.swb_get_stream(self.h, C.byref(p)))
+        return int(p.value or 0)
+
     def load_refset(self, refs: Sequence) -> "RefSet":
         return RefSet(self, refs)
 
@@ -198,6 +205,20 @@ class AlignResult:
     @property
     def op_lens(self) -> np.ndarray:
         return self._arr(self.lib.swb_result_op_lens(self.h), self.total_cells, np.int32)
+
+    def device_array(self, which: int, shape, typestr: str = "<i4"):
+        """Zero-copy view of an HBM-resident output (0 scores, 1 ref_totals, 2 best_hits) as an
+        object with __cuda_array_interface__ (torch.as_tensor(..., device="cuda") wraps it)."""
+        ptr = C.c_void_p(); n = C.c_int64()
+        check(self.lib.swb_result_device_ptr(self.h, which, C.byref(ptr), C.byref(n)))
+
+        class _View:
+            pass
+        v = _View()
+        v.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr.value or 0), False),
+                                      "version": 2, "strides": None}
+        v._keepalive = self
+        return v
 
     def pair_index(self, ref: int, read: int) -> int:
         return ref * self.n_reads + read
