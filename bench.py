@@ -108,9 +108,9 @@ class ClockSampler:
 
 
 def shard_refs(refs, rank: int, world: int):
-    """Balanced shard: sort by length, deal round-robin."""
-    order = sorted(range(len(refs)), key=lambda k: -len(refs[k]))
-    mine = sorted(order[rank::world])
+    """Length-balanced shard of the reference set."""
+    from sparksmithwaterman_b200 import multigpu
+    mine = multigpu.shard_refs([len(r) for r in refs], rank, world)
     return [refs[k] for k in mine], mine
 
 

@@ -1,0 +1,104 @@
+"""CPU: the C-ABI library loads and exports every symbol include/swb200.h declares; the
+product fails loudly without a GPU; host-side logic (sharding, merge, reductions, synthetic
+data) behaves as the reference's callers do.  No compute call runs without a GPU."""
+import os
+import re
+
+import numpy as np
+import pytest
+
+import sparksmithwaterman_b200 as swb
+from sparksmithwaterman_b200 import _ffi, distribution, multigpu, synth
+from sparksmithwaterman_b200.build import build_native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build_native()
+    return _ffi.load()
+
+
+def test_header_symbols_all_exported(lib):
+    with open(os.path.join(ROOT, "include", "swb200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    declared = set(re.findall(r"\b(swb_[a-z0-9_]+)\s*\(", text))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in swb200.h but not exported"
+    assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
+    assert lib.swb_abi_version() == 1
+
+
+def test_product_does_not_touch_the_oracle():
+    pkg = os.path.join(ROOT, "sparksmithwaterman_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                with open(os.path.join(dirpath, fn)) as f:
+                    src = f.read()
+                assert "import oracle" not in src and "sw_oracle" not in src and "from oracle" not in src, fn
+
+
+def test_fails_loudly_without_gpu(lib):
+    if lib.swb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(swb.SwbError) as ei:
+        swb.Engine(0)
+    assert "no CUDA device" in str(ei.value)
+
+
+def test_synth_shape_and_determinism():
+    L = synth.ref_lengths(20000)
+    assert 50 <= L.min() and L.max() <= 200000
+    assert abs(np.median(L) - 1609) < 60 and abs(L.mean() - 2160) < 90        # README.md:39-40 of the reference
+    a, b = synth.make_refs(50), synth.make_refs(50)
+    assert a == b and all(set(r) <= set(b"ACGT") for r in a)
+    r1 = synth.make_reads(40, 150, a)
+    assert r1 == synth.make_reads(40, 150, a) and all(len(q) == 150 for q in r1)
+
+
+def test_shard_refs_partition_and_balance():
+    L = synth.ref_lengths(1000)
+    for world in (1, 2, 4, 8):
+        shards = [multigpu.shard_refs(L, r, world) for r in range(world)]
+        assert sorted(sum(shards, [])) == list(range(1000))
+        tot = [int(L[s].sum()) for s in shards]
+        assert max(tot) - min(tot) <= 0.05 * max(tot)
+
+
+def test_merge_best_hits_is_shard_invariant():
+    rng = np.random.default_rng(0)
+    n_refs, n_reads = 64, 33
+    scores = rng.integers(0, 40, size=(n_refs, n_reads))
+    cells = rng.integers(1, 100, size=(n_refs, n_reads, 2))
+    L = rng.integers(50, 500, size=n_refs)
+
+    def best_of(ids):
+        out = np.zeros((n_reads, 4), np.int32)
+        for q in range(n_reads):
+            k = max(range(len(ids)), key=lambda x: (scores[ids[x], q], -x))      # first max wins
+            out[q] = (scores[ids[k], q], k, *cells[ids[k], q])
+        return out
+    single = multigpu.localize(best_of(list(range(n_refs))), list(range(n_refs)))
+    for world in (2, 4, 8):
+        recs = []
+        for r in range(world):
+            ids = multigpu.shard_refs(L, r, world)
+            recs.append(multigpu.localize(best_of(ids), ids))
+        assert (multigpu.merge_best_hits(np.stack(recs)) == single).all()
+
+
+def test_reductions_mirror_the_reference():
+    a = (10, (["b-meta", "ACGT"], [(3, ["A", "A"])]))
+    b = (12, (["a-meta", "ACGA"], []))
+    c = (12, (["0-meta", "ACGC"], []))
+    best, opt = distribution.NoDistribution.reduce([a, b, c])
+    assert best == 12 and [v[0][0] for v in opt] == ["0-meta", "a-meta"]
+    # the driver as written keys on the FIRST element of each file (Distribution.java:342)
+    best, opt = distribution.DistributeReference.reduce([[a, b, c]])
+    assert best == 10 and [v[0][0] for v in opt] == ["b-meta"]
+    sites = [(5, ["x", "1"]), (2, ["y", "2"]), (5, ["z", "3"]), (2, ["w", "4"])]
+    assert [s[1][1] for s in distribution.match_site_sort(sites)] == ["2", "4", "1", "3"]     # stable
+    assert distribution.wrap32(2**31 - 1 + 5) == -(2**31) + 4
