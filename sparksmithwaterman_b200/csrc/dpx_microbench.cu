@@ -150,7 +150,7 @@ extern "C" int swb_microbench_json(int device, int iters, char *buf, int buflen)
     run_all<0>(iters, p.multiProcessorCount, clock_khz, dout, dcyc, r, ms, mhz);
     cudaFree(dout); cudaFree(dcyc);
     std::string s = "{";
-    char tmp[256];
+    char tmp[768];
     snprintf(tmp, sizeof tmp, "\"gpu\": \"%s\", \"sms\": %d, \"clock_mhz_nominal\": %.1f, \"iters\": %d, \"mixes\": {",
              p.name, p.multiProcessorCount, clock_khz / 1000.0, iters);
     s += tmp;

@@ -28,23 +28,28 @@ int cuda_fail(cudaError_t e, const char *what)
         if (e_ != cudaSuccess) return cuda_fail(e_, #x);                       \
     } while (0)
 
+// Device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are
+// ordered on the engine's stream and reuse pool memory, so the align loop never hits the
+// synchronising cudaMalloc/cudaFree.
 template <class T> struct DevBuf {
-    T *p = nullptr; size_t n = 0;
+    T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
-    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFree(p); p = nullptr; n = 0; }
-    cudaError_t alloc(size_t count)
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count, cudaStream_t stream)
     {
         release();
         if (count == 0) count = 1;
-        cudaError_t e = cudaMalloc(&p, count * sizeof(T));
-        if (e == cudaSuccess) n = count;
+        st = stream;
+        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), stream);
+        if (e == cudaSuccess) n = count; else p = nullptr;
         return e;
     }
+    cudaError_t reserve(size_t count, cudaStream_t stream) { return n >= count && p ? cudaSuccess : alloc(count + count / 8, stream); }
 };
 
 inline int upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
@@ -58,6 +63,25 @@ struct swb_ctx {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::recursive_mutex mu;
+    // grow-only scratch reused by every align call on this context
+    DevBuf<uint32_t> ck, tmx, counters;
+    DevBuf<int32_t> rp, slot;
+    DevBuf<TileTask> tasks;
+    DevBuf<uint64_t> keys_tmp;
+    DevBuf<uint8_t> sort_tmp;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaError_t next_event(cudaEvent_t *e)
+    {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t n;
+            cudaError_t rc = cudaEventCreate(&n);
+            if (rc != cudaSuccess) return rc;
+            ev_pool.push_back(n);
+        }
+        *e = ev_pool[ev_used++];
+        return cudaSuccess;
+    }
 };
 
 struct swb_refset {
@@ -89,6 +113,7 @@ struct BatchOut {
     DevBuf<uint64_t> keys;
     DevBuf<int32_t> beg, oplen;
     DevBuf<uint32_t> ops;
+    std::vector<int32_t> slot_read;              // read slot of this batch -> read index of the call
     // host copies (after fetch)
     std::vector<uint64_t> h_keys;
     std::vector<uint32_t> h_ops;
@@ -150,6 +175,10 @@ int swb_create(int device, int64_t workspace_bytes, swb_ctx **out)
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaEventCreate(&c->ev[0]));
     CU(cudaEventCreate(&c->ev[1]));
+    cudaMemPool_t pool;
+    CU(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = UINT64_MAX;                                    // keep freed blocks in the pool
+    CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     *out = c;
     return SWB_OK;
 }
@@ -158,6 +187,11 @@ void swb_destroy(swb_ctx *c)
 {
     if (!c) return;
     cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
+    c->tasks.release(); c->keys_tmp.release(); c->sort_tmp.release();
+    for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -251,12 +285,13 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         const int32_t n = len_sorted[(size_t)s];
         for (int32_t c = 0; c < n; ++c) w[c >> 4] |= (uint32_t)rs->code_of[upper(p[c])] << (2 * (c & 15));
     }
-    CU(rs->words.alloc(words.size()));
-    CU(rs->word_off.alloc((size_t)n_refs));
-    CU(rs->len.alloc((size_t)n_refs));
-    CU(rs->orig.alloc((size_t)n_refs));
-    CU(rs->sorted_of.alloc((size_t)n_refs));
-    CU(rs->blk_off.alloc((size_t)n_refs + 1));
+    CU(rs->words.alloc(words.size(), ctx->stream));
+    CU(rs->word_off.alloc((size_t)n_refs, ctx->stream));
+    CU(rs->len.alloc((size_t)n_refs, ctx->stream));
+    CU(rs->orig.alloc((size_t)n_refs, ctx->stream));
+    CU(rs->sorted_of.alloc((size_t)n_refs, ctx->stream));
+    CU(rs->blk_off.alloc((size_t)n_refs + 1, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
     CU(cudaMemcpy(rs->words.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
     if (n_refs) {
         CU(cudaMemcpy(rs->word_off.p, word_off.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
@@ -311,8 +346,8 @@ int swb_reads_upload(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const 
             c[x] = rs->code_of[upper(p[x])];
         }
     }
-    CU(rd->codes.alloc(codes.size()));
-    CU(rd->off.alloc(off.size()));
+    CU(rd->codes.alloc(codes.size(), ctx->stream));
+    CU(rd->off.alloc(off.size(), ctx->stream));
     CU(cudaMemcpyAsync(rd->codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaMemcpyAsync(rd->off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
@@ -360,25 +395,29 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     res->ctx = ctx; res->n_refs = n_refs; res->n_reads = n_reads; res->flags = flags;
     res->ref_len = rs->len_orig; res->read_len = rd->len;
     const size_t n_pairs = (size_t)(n_refs * n_reads);
-    CU(res->d_scores.alloc(n_pairs));
-    CU(res->d_totals.alloc((size_t)n_refs));
-    CU(res->d_best.alloc((size_t)n_reads * 4));
+    CU(res->d_scores.alloc(n_pairs, st));
+    CU(res->d_totals.alloc((size_t)n_refs, st));
+    CU(res->d_best.alloc((size_t)n_reads * 4, st));
     CU(cudaMemsetAsync(res->d_scores.p, 0, std::max<size_t>(n_pairs, 1) * 4, st));
 
-    std::vector<int32_t> h_read_batch;
-    double t_fill = 0, t_locate = 0, t_trace = 0, ck_bytes = 0;
-    int launches = 1, n_batches = 0;
-    auto tic = [&]() { return cudaEventRecord(ctx->ev[0], st); };
-    auto toc = [&](double &acc) -> cudaError_t {
-        cudaError_t e = cudaEventRecord(ctx->ev[1], st);
-        if (e != cudaSuccess) return e;
-        e = cudaEventSynchronize(ctx->ev[1]);
-        if (e != cudaSuccess) return e;
-        float ms = 0;
-        e = cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
-        acc += ms;
+    // phase timing: event pairs are only recorded inside the loop and read after the last sync
+    ctx->ev_used = 0;
+    struct Span { cudaEvent_t a, b; int phase; };
+    std::vector<Span> spans;
+    auto tic = [&](int phase) -> cudaError_t {
+        Span sp; sp.phase = phase;
+        cudaError_t e = ctx->next_event(&sp.a);
+        if (e == cudaSuccess) e = ctx->next_event(&sp.b);
+        if (e == cudaSuccess) e = cudaEventRecord(sp.a, st);
+        if (e == cudaSuccess) spans.push_back(sp);
         return e;
     };
+    auto toc = [&]() -> cudaError_t { return cudaEventRecord(spans.back().b, st); };
+
+    std::vector<int32_t> h_read_batch, h_read_slot_all;
+    double ck_bytes = 0;
+    int launches = 1, n_batches = 0;
+    CU(ctx->counters.reserve(8, st));
 
     if (n_refs > 0 && n_reads > 0) {
         // group reads by rows-per-lane class, longest first inside a class
@@ -389,15 +428,10 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
             const int K = pick_k(m);
             for (int k = 0; k < kNumK; ++k) if (kKList[k] == K) classes[(size_t)k].push_back((int32_t)q);
         }
-        DevBuf<int32_t> d_rp, d_slot;
-        DevBuf<uint32_t> d_ck, d_tmx, d_count;
-        DevBuf<TileTask> d_tasks;
-        DevBuf<uint64_t> d_keys_tmp;
-        DevBuf<uint8_t> d_sort_tmp;
-        CU(d_slot.alloc((size_t)n_reads));
-        CU(d_count.alloc(2));
+        CU(ctx->slot.reserve((size_t)n_reads, st));
         std::vector<int32_t> h_slot((size_t)n_reads);
         h_read_batch.assign((size_t)n_reads, -1);
+        h_read_slot_all.assign((size_t)n_reads, -1);
 
         for (int kc = 0; kc < kNumK; ++kc) {
             auto &idx = classes[(size_t)kc];
@@ -410,7 +444,10 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
             const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)KW * GL * 4 + GL * 4);
             int64_t rp_per_batch = std::max<int64_t>(1, ctx->ws_bytes / std::max<int64_t>(bytes_per_rp, 1));
             rp_per_batch = std::min<int64_t>(rp_per_batch, 1 << 16);
-            if (rp_per_batch * rs->n_refs * 2 >= ((int64_t)1 << 31)) rp_per_batch = std::max<int64_t>(1, (((int64_t)1 << 31) - 1) / (rs->n_refs * 2));
+            if (rp_per_batch * rs->n_refs * 2 >= ((int64_t)1 << 30)) rp_per_batch = std::max<int64_t>(1, (((int64_t)1 << 30) - 1) / (rs->n_refs * 2));
+            // equal-sized batches (no small straggler batch at the end)
+            const int64_t nb = (n_rp_total + rp_per_batch - 1) / rp_per_batch;
+            rp_per_batch = (n_rp_total + nb - 1) / nb;
             for (int64_t rp0 = 0; rp0 < n_rp_total; rp0 += rp_per_batch) {
                 const int n_rp = (int)std::min<int64_t>(rp_per_batch, n_rp_total - rp0);
                 ++n_batches;
@@ -426,109 +463,124 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                             m_max = std::max(m_max, rd->len[(size_t)idx[(size_t)k]]);
                         }
                     }
-                CU(d_rp.alloc(h_rp.size()));
-                CU(cudaMemcpyAsync(d_rp.p, h_rp.data(), h_rp.size() * 4, cudaMemcpyHostToDevice, st));
-                CU(cudaMemcpyAsync(d_slot.p, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
+                CU(ctx->rp.reserve(h_rp.size(), st));
+                CU(cudaMemcpyAsync(ctx->rp.p, h_rp.data(), h_rp.size() * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(ctx->slot.p, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
                 const size_t ck_words = (size_t)n_rp * rs->blocks_per_rp * KW * GL;
                 const size_t tmx_words = (size_t)n_rp * rs->blocks_per_rp * GL;
-                if (d_ck.n < ck_words) CU(d_ck.alloc(ck_words));
-                if (d_tmx.n < tmx_words) CU(d_tmx.alloc(tmx_words));
+                CU(ctx->ck.reserve(ck_words, st));
+                CU(ctx->tmx.reserve(tmx_words, st));
                 ck_bytes += (double)(ck_words + tmx_words) * 4;
 
                 BatchParams P;
                 P.ref_words = rs->words.p; P.ref_word_off = rs->word_off.p; P.ref_len = rs->len.p;
                 P.ref_orig = rs->orig.p; P.ref_sorted_of = rs->sorted_of.p; P.ref_blk_off = rs->blk_off.p;
                 P.n_refs = (int32_t)n_refs; P.blocks_per_rp = rs->blocks_per_rp;
-                P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = d_rp.p; P.read_slot = d_slot.p;
+                P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = ctx->rp.p; P.read_slot = ctx->slot.p;
                 P.n_rp = n_rp; P.n_reads = n_reads;
                 P.match = match; P.mismatch = mismatch; P.gap = gap;
-                P.scores = res->d_scores.p; P.ck = d_ck.p; P.tmx = d_tmx.p;
+                P.scores = res->d_scores.p; P.ck = ctx->ck.p; P.tmx = ctx->tmx.p;
+                uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_work = ctx->counters.p + 2;
 
-                CU(tic());
-                CU(launch_fill(K, P, ctx->sm_count, st));
+                CU(tic(1));
+                CU(launch_fill(K, P, d_work, ctx->sm_count, st));
                 ++launches;
-                CU(toc(t_fill));
-                if (flags & SWB_F_SCORES_ONLY) continue;
-
-                // ---- flagged tiles -> max cells -> sorted keys ---------------------------
-                CU(tic());
-                uint32_t n_tasks = 0, cap_tasks = (uint32_t)std::min<int64_t>((int64_t)n_rp * 2 * n_refs * 2 + 1024, (int64_t)1 << 31);
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    if (d_tasks.n < cap_tasks) CU(d_tasks.alloc(cap_tasks));
-                    CU(cudaMemsetAsync(d_count.p, 0, 8, st));
-                    CU(launch_flag_tiles(P, d_tasks.p, cap_tasks, d_count.p, st));
-                    ++launches;
-                    CU(cudaMemcpyAsync(&n_tasks, d_count.p, 4, cudaMemcpyDeviceToHost, st));
-                    CU(cudaStreamSynchronize(st));
-                    if (n_tasks <= cap_tasks) break;
-                    cap_tasks = n_tasks;
+                CU(toc());
+                if (flags & SWB_F_SCORES_ONLY) {
+                    CU(cudaStreamSynchronize(st));     // h_rp / h_slot are reused by the next batch
+                    continue;
                 }
+
+                // ---- flagged tiles -> max cells -> sorted keys (one host sync: the two counts) ----
+                CU(tic(2));
+                const int64_t pairs_b = (int64_t)n_rp * 2 * n_refs;
+                uint32_t cap_tasks = (uint32_t)std::min<int64_t>(pairs_b * 2 + 1024, (int64_t)1 << 31);
+                uint32_t cap_cells = (uint32_t)std::min<int64_t>(pairs_b * 2 + 4096, (int64_t)1 << 31);
+                uint32_t h_counts[2] = {0, 0};
+                for (int attempt = 0; attempt < 3; ++attempt) {
+                    CU(ctx->tasks.reserve(cap_tasks, st));
+                    CU(ctx->keys_tmp.reserve(cap_cells, st));
+                    CU(cudaMemsetAsync(ctx->counters.p, 0, 8, st));
+                    CU(launch_flag_tiles(P, ctx->tasks.p, cap_tasks, d_ntasks, st));
+                    CU(launch_locate(K, P, ctx->tasks.p, d_ntasks, cap_tasks, ctx->keys_tmp.p, cap_cells, d_ncells,
+                                     ctx->sm_count, st));
+                    launches += 2;
+                    CU(cudaMemcpyAsync(h_counts, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
+                    CU(cudaStreamSynchronize(st));
+                    if (h_counts[0] <= cap_tasks && h_counts[1] <= cap_cells) break;
+                    if (attempt == 2) return fail(SWB_E_NOMEM, "swb_align: max-cell list did not fit after two retries");
+                    cap_tasks = std::max(cap_tasks, h_counts[0]);
+                    cap_cells = std::max<uint32_t>(cap_cells, (uint32_t)std::min<uint64_t>((uint64_t)h_counts[1] * 2, 1ull << 31));
+                }
+                const uint32_t n_cells = h_counts[1];
                 BatchOut bo;
                 bo.K = K;
-                uint32_t n_cells = 0, cap_cells = (uint32_t)std::min<int64_t>((int64_t)n_tasks * 2 + 4096, (int64_t)1 << 31);
-                for (int attempt = 0; attempt < 2; ++attempt) {
-                    if (d_keys_tmp.n < cap_cells) CU(d_keys_tmp.alloc(cap_cells));
-                    CU(cudaMemsetAsync(d_count.p + 1, 0, 4, st));
-                    CU(launch_locate(K, P, d_tasks.p, n_tasks, d_keys_tmp.p, cap_cells, d_count.p + 1, ctx->sm_count, st));
-                    ++launches;
-                    CU(cudaMemcpyAsync(&n_cells, d_count.p + 1, 4, cudaMemcpyDeviceToHost, st));
-                    CU(cudaStreamSynchronize(st));
-                    if (n_cells <= cap_cells) break;
-                    cap_cells = n_cells;
-                }
                 bo.n_cells = n_cells;
-                CU(bo.keys.alloc(n_cells));
+                CU(bo.keys.alloc(n_cells, st));
                 const size_t tmp_bytes = sort_keys_tmp_bytes(n_cells);
-                if (d_sort_tmp.n < tmp_bytes) CU(d_sort_tmp.alloc(tmp_bytes));
-                CU(sort_keys(d_keys_tmp.p, bo.keys.p, n_cells, d_sort_tmp.p, tmp_bytes, st));
+                CU(ctx->sort_tmp.reserve(tmp_bytes, st));
+                CU(sort_keys(ctx->keys_tmp.p, bo.keys.p, n_cells, ctx->sort_tmp.p, tmp_bytes, st));
                 launches += 4;
-                CU(toc(t_locate));
+                CU(toc());
 
                 // ---- traceback ----------------------------------------------------------
-                CU(tic());
+                CU(tic(3));
                 const int64_t big = std::max({match, mismatch, 0});
                 int64_t lmax = (int64_t)m_max + (big * m_max - 1) / (-(int64_t)gap) + 1;
                 lmax = std::min<int64_t>(lmax, (int64_t)m_max + rs->max_len);
                 bo.ops_stride = (int)((lmax + 15) / 16);
-                CU(bo.beg.alloc(n_cells));
-                CU(bo.oplen.alloc(n_cells));
-                CU(bo.ops.alloc((size_t)n_cells * bo.ops_stride));
+                CU(bo.beg.alloc(n_cells, st));
+                CU(bo.oplen.alloc(n_cells, st));
+                CU(bo.ops.alloc((size_t)n_cells * bo.ops_stride, st));
                 CU(launch_trace(K, P, bo.keys.p, n_cells, bo.beg.p, bo.oplen.p, bo.ops.p, bo.ops_stride, ctx->sm_count, st));
                 ++launches;
-                CU(toc(t_trace));
+                CU(toc());
                 res->stats[8] += n_cells;
-                for (int32_t v : h_rp) if (v >= 0) h_read_batch[(size_t)v] = (int32_t)res->batches.size();
+                for (size_t sl = 0; sl < h_rp.size(); ++sl)
+                    if (h_rp[sl] >= 0) {
+                        h_read_batch[(size_t)h_rp[sl]] = (int32_t)res->batches.size();
+                        h_read_slot_all[(size_t)h_rp[sl]] = (int32_t)sl;
+                    }
+                bo.slot_read = h_rp;
                 res->batches.push_back(std::move(bo));
             }
         }
     }
-    CU(tic());
+    CU(tic(4));
     CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
     CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, st));
     launches += 2;
-    DevBuf<int32_t> d_read_batch;
+    DevBuf<int32_t> d_read_batch, d_read_slot_all;
     DevBuf<const uint64_t *> d_bkeys;
     DevBuf<uint32_t> d_bn;
+    std::vector<const uint64_t *> hk;
+    std::vector<uint32_t> hn;
     if (!res->batches.empty() && n_reads > 0) {
-        std::vector<const uint64_t *> hk;
-        std::vector<uint32_t> hn;
         for (auto &bo : res->batches) { hk.push_back(bo.keys.p); hn.push_back(bo.n_cells); }
-        CU(d_read_batch.alloc((size_t)n_reads));
-        CU(d_bkeys.alloc(hk.size()));
-        CU(d_bn.alloc(hn.size()));
+        CU(d_read_batch.alloc((size_t)n_reads, st));
+        CU(d_read_slot_all.alloc((size_t)n_reads, st));
+        CU(d_bkeys.alloc(hk.size(), st));
+        CU(d_bn.alloc(hn.size(), st));
         CU(cudaMemcpyAsync(d_read_batch.p, h_read_batch.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_read_slot_all.p, h_read_slot_all.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_bkeys.p, hk.data(), hk.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(d_bn.p, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice, st));
-        CU(launch_best_cells(res->d_best.p, n_reads, d_read_batch.p, d_bkeys.p, d_bn.p, st));
+        CU(launch_best_cells(res->d_best.p, n_reads, n_refs, d_read_batch.p, d_read_slot_all.p, d_bkeys.p, d_bn.p, st));
         ++launches;
     }
-    double t_misc = 0;
-    CU(toc(t_misc));
+    CU(toc());
+    CU(cudaStreamSynchronize(st));
+    double t_phase[5] = {0, 0, 0, 0, 0};
+    for (const Span &sp : spans) {
+        float ms = 0;
+        CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
+        t_phase[sp.phase] += ms;
+    }
 
     int64_t read_bases = 0;
     for (int32_t m : rd->len) read_bases += m;
-    res->stats[1] = t_fill; res->stats[2] = t_locate; res->stats[3] = t_trace;
-    res->stats[5] = t_fill + t_locate + t_trace + t_misc;
+    res->stats[1] = t_phase[1]; res->stats[2] = t_phase[2]; res->stats[3] = t_phase[3];
+    res->stats[5] = t_phase[1] + t_phase[2] + t_phase[3] + t_phase[4];
     res->stats[6] = (double)rs->total_bases * (double)read_bases;
     res->stats[7] = (double)n_refs * (double)n_reads;
     res->stats[9] = launches; res->stats[10] = ck_bytes; res->stats[11] = n_batches;
@@ -602,30 +654,38 @@ int swb_result_fetch(swb_result *res)
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     res->stats[4] = ms;
 
-    // merge the batches (each already sorted by key) into pair-major order
-    struct Ent { uint64_t key; uint32_t b, k; };
-    std::vector<Ent> ents;
-    ents.reserve(total_cells);
-    for (size_t b = 0; b < res->batches.size(); ++b)
-        for (uint32_t k = 0; k < res->batches[b].n_cells; ++k) ents.push_back(Ent{res->batches[b].h_keys[k], (uint32_t)b, k});
-    if (res->batches.size() > 1)
-        std::sort(ents.begin(), ents.end(), [](const Ent &x, const Ent &y) { return x.key < y.key; });
+    // batches hold disjoint reads and are sorted (read slot, ref, i, j): counting-sort the cells
+    // into the ABI's pair order p = ref * n_reads + read; the (i, j) order inside a pair is kept
     res->cells.resize(total_cells * 2);
     res->beginnings.resize(total_cells);
     res->op_lens.resize(total_cells);
     res->cell_batch.resize(total_cells);
     res->cell_local.resize(total_cells);
     res->cell_off.assign(n_pairs + 1, 0);
-    for (size_t c = 0; c < total_cells; ++c) {
-        const Ent &e = ents[c];
-        res->cells[2 * c] = (int32_t)key_i(e.key);
-        res->cells[2 * c + 1] = (int32_t)key_j(e.key);
-        res->beginnings[c] = h_beg[e.b][e.k];
-        res->op_lens[c] = h_len[e.b][e.k];
-        res->cell_batch[c] = e.b; res->cell_local[c] = e.k;
-        res->cell_off[(size_t)key_pair(e.key) + 1] += 1;
-    }
+    const uint64_t nr = (uint64_t)std::max<int64_t>(res->n_refs, 1);
+    auto pair_of = [&](const BatchOut &bo, uint64_t key) -> size_t {
+        const uint64_t pk = key_pair(key);
+        const uint64_t slot = pk / nr, ref = pk - slot * nr;
+        return (size_t)(ref * (uint64_t)res->n_reads + (uint64_t)bo.slot_read[(size_t)slot]);
+    };
+    for (const BatchOut &bo : res->batches)
+        for (uint32_t k = 0; k < bo.n_cells; ++k) res->cell_off[pair_of(bo, bo.h_keys[k]) + 1] += 1;
     for (size_t p = 0; p < n_pairs; ++p) res->cell_off[p + 1] += res->cell_off[p];
+    {
+        std::vector<int64_t> cursor(res->cell_off.begin(), res->cell_off.end() - 1);
+        for (size_t b = 0; b < res->batches.size(); ++b) {
+            const BatchOut &bo = res->batches[b];
+            for (uint32_t k = 0; k < bo.n_cells; ++k) {
+                const uint64_t key = bo.h_keys[k];
+                const size_t c = (size_t)cursor[pair_of(bo, key)]++;
+                res->cells[2 * c] = (int32_t)key_i(key);
+                res->cells[2 * c + 1] = (int32_t)key_j(key);
+                res->beginnings[c] = h_beg[b][k];
+                res->op_lens[c] = h_len[b][k];
+                res->cell_batch[c] = (uint32_t)b; res->cell_local[c] = k;
+            }
+        }
+    }
     res->fetched = true;
     return SWB_OK;
 }

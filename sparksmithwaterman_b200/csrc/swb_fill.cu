@@ -16,46 +16,62 @@
 #include "swb_internal.h"
 #include "swb_device.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace swb {
 
 template <int K>
-__global__ void __launch_bounds__(256, 2) fill_kernel(const BatchParams P, int quads_per_cta)
+__global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t *work_counter, uint32_t zero)
 {
     using G = Geo<K>;
-    extern __shared__ __align__(16) uint32_t prof[];            // [4 codes][GL lanes][KS]
+    extern __shared__ __align__(16) uint32_t prof_all[];        // per warp: [4 codes][GL lanes][KS]
 
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
-    const int rp = blockIdx.x % P.n_rp;                           // longest references first
-    const int chunk = blockIdx.x / P.n_rp;
-
-    // ---- query profile of this CTA's read pair -------------------------------------
-    const int ra = P.rp_reads[2 * rp], rb = P.rp_reads[2 * rp + 1];
-    const int64_t offa = P.read_off[ra];
-    const int ma = (int)(P.read_off[ra + 1] - offa);
-    const int64_t offb = rb >= 0 ? P.read_off[rb] : 0;
-    const int mb = rb >= 0 ? (int)(P.read_off[rb + 1] - offb) : 0;
-    for (int idx = threadIdx.x; idx < 4 * GL * K; idx += blockDim.x) {
-        const int c = idx / (GL * K), rem = idx - c * GL * K;
-        const int tt = rem / K, r = rem - tt * K;
-        const int row = tt * K + r;
-        int lo = S_PAD, hi = S_PAD;
-        if (row < ma) lo = (P.read_codes[offa + row] == c) ? P.match : P.mismatch;
-        if (row < mb) hi = (P.read_codes[offb + row] == c) ? P.match : P.mismatch;
-        prof[c * G::CSTRIDE + tt * G::KS + r] = pack2(lo, hi);
-    }
-    __syncthreads();
+    uint32_t *prof = prof_all + warp * G::PROF_WORDS;
+    const int n_quads = (P.n_refs + 3) >> 2;
+    const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
     const uint32_t g2 = pack2(P.gap, P.gap);
-    uint32_t zero = 0;
-    asm volatile("" : "+r"(zero));                                // a register zero: keeps PRMT out of the loop
+    // `zero` is a kernel argument (always 0): ptxas cannot fold it, so the RELU ops take it from a
+    // register instead of re-materialising a packed zero with one PRMT per cell
     const uint32_t lmask = t ? 0xffffffffu : 0u;
-    const int n_quads = (P.n_refs + 3) >> 2;
-    const int q_begin = chunk * quads_per_cta;
-    const int q_end = min(n_quads, q_begin + quads_per_cta);
     const int my_prof = t * G::KS;
+    int cur_rp = -1, ra = 0, rb = -1;
 
-    for (int q = q_begin + warp; q < q_end; q += nwarps) {
+    // persistent warps: items (quad, read pair) are handed out quad-major, i.e. longest
+    // references first, through one global counter -> no tail, no per-CTA imbalance
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int q = (int)(item / (uint32_t)P.n_rp);
+        const int rp = (int)(item - (uint32_t)q * (uint32_t)P.n_rp);
+        if (rp != cur_rp) {
+            // ---- query profile of this warp's read pair ------------------------------------
+            cur_rp = rp;
+            ra = P.rp_reads[2 * rp]; rb = P.rp_reads[2 * rp + 1];
+            const int64_t offa = P.read_off[ra];
+            const int ma = (int)(P.read_off[ra + 1] - offa);
+            const int64_t offb = rb >= 0 ? P.read_off[rb] : 0;
+            const int mb = rb >= 0 ? (int)(P.read_off[rb + 1] - offb) : 0;
+            __syncwarp();
+            for (int idx = lane; idx < GL * K; idx += 32) {
+                const int tt = idx / K, r = idx - tt * K;
+                const int row = tt * K + r;
+                const int qa = row < ma ? (int)P.read_codes[offa + row] : -1;
+                const int qb = row < mb ? (int)P.read_codes[offb + row] : -1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int lo = qa < 0 ? (int)S_PAD : (qa == c ? P.match : P.mismatch);
+                    const int hi = qb < 0 ? (int)S_PAD : (qb == c ? P.match : P.mismatch);
+                    prof[c * G::CSTRIDE + tt * G::KS + r] = pack2(lo, hi);
+                }
+            }
+            __syncwarp();
+        }
         const int ref = 4 * q + g;                                // sorted reference index of this group
         const bool has_ref = ref < P.n_refs;
         const int n_g = has_ref ? P.ref_len[ref] : 0;
@@ -161,31 +177,39 @@ __global__ void __launch_bounds__(256, 2) fill_kernel(const BatchParams P, int q
 }
 
 template <int K>
-static cudaError_t launch_fill_k(const BatchParams &P, int sm_count, cudaStream_t st)
+static cudaError_t launch_fill_k(const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st)
 {
     using G = Geo<K>;
     const int n_quads = (P.n_refs + 3) / 4;
-    // enough CTAs to fill the machine several times over, at least one quad per warp
-    const int warps = 8;
-    int quads_per_cta = warps * 4;
-    while (quads_per_cta > warps && (int64_t)P.n_rp * ((n_quads + quads_per_cta - 1) / quads_per_cta) < 4LL * sm_count)
-        quads_per_cta -= warps;
-    const int chunks = (n_quads + quads_per_cta - 1) / quads_per_cta;
-    const size_t smem = G::PROF_WORDS * sizeof(uint32_t);
-    fill_kernel<K><<<dim3((unsigned)(chunks * P.n_rp)), dim3(warps * 32), smem, st>>>(P, quads_per_cta);
+    static const int env_warps = getenv("SWB_FILL_WARPS") ? atoi(getenv("SWB_FILL_WARPS")) : 0;
+    static const int env_ctas = getenv("SWB_FILL_CTAS_PER_SM") ? atoi(getenv("SWB_FILL_CTAS_PER_SM")) : 0;
+    const int warps = env_warps > 0 ? env_warps : 12;
+    const int ctas_per_sm = env_ctas > 0 ? env_ctas : 1;   // one CTA per SM: measured 54 ms vs 69 ms for two (warp starvation)
+    const int64_t items = (int64_t)n_quads * P.n_rp;
+    // persistent CTAs, never more than there is work
+    const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count * ctas_per_sm);
+    const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    fill_kernel<K><<<dim3((unsigned)ctas), dim3(warps * 32), smem, st>>>(P, work_counter, 0u);
     return cudaGetLastError();
 }
 
-cudaError_t launch_fill(int K, const BatchParams &P, int sm_count, cudaStream_t st)
+cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st)
 {
     switch (K) {
-        case 4:  return launch_fill_k<4>(P, sm_count, st);
-        case 8:  return launch_fill_k<8>(P, sm_count, st);
-        case 13: return launch_fill_k<13>(P, sm_count, st);
-        case 16: return launch_fill_k<16>(P, sm_count, st);
-        case 19: return launch_fill_k<19>(P, sm_count, st);
-        case 25: return launch_fill_k<25>(P, sm_count, st);
-        case 32: return launch_fill_k<32>(P, sm_count, st);
+        case 4:  return launch_fill_k<4>(P, work_counter, sm_count, st);
+        case 8:  return launch_fill_k<8>(P, work_counter, sm_count, st);
+        case 13: return launch_fill_k<13>(P, work_counter, sm_count, st);
+        case 16: return launch_fill_k<16>(P, work_counter, sm_count, st);
+        case 19: return launch_fill_k<19>(P, work_counter, sm_count, st);
+        case 25: return launch_fill_k<25>(P, work_counter, sm_count, st);
+        case 32: return launch_fill_k<32>(P, work_counter, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }

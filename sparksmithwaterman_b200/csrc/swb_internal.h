@@ -22,7 +22,7 @@
 namespace swb {
 
 constexpr int GL = 8;        // lanes per group
-constexpr int CB = 32;       // steps per checkpoint block (multiple of 16)
+constexpr int CB = 16;       // steps per checkpoint block (multiple of 16; the trace kernel's code window needs 16)
 constexpr int MAX_SHORT_ROWS = GL * 32;
 
 // rows-per-lane variants compiled for the short path
@@ -41,7 +41,8 @@ template <int K> struct Geo {
 
 constexpr int16_t S_PAD = -16384;   // profile score of a padding row (beyond the read's end)
 
-// key of one maximum cell: pair p (33 bits) | i (9 bits) | j (22 bits)
+// key of one maximum cell: pair key = read slot * n_refs + ref (33 bits) | i (9 bits) | j (22 bits);
+// sorting the keys gives, per (read, ref) pair, the reference's row-major max-cell order
 constexpr int KEY_J_BITS = 22, KEY_I_BITS = 9;
 __host__ __device__ inline uint64_t make_key(uint64_t p, uint32_t i, uint32_t j)
 { return (p << (KEY_J_BITS + KEY_I_BITS)) | ((uint64_t)i << KEY_J_BITS) | j; }
@@ -80,11 +81,12 @@ struct BatchParams {
 struct LaunchStats { int launches = 0; };
 
 // swb_fill.cu
-cudaError_t launch_fill(int K, const BatchParams &P, int sm_count, cudaStream_t st);
+cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st);
 // swb_trace.cu
 cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, cudaStream_t st);
-cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, uint32_t n_tasks,
-                          uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st);
+cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
+                          uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
+                          cudaStream_t st);
 cudaError_t launch_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells,
                          int32_t *beginnings, int32_t *op_lens, uint32_t *ops, int ops_stride_words,
                          int sm_count, cudaStream_t st);
@@ -92,8 +94,9 @@ cudaError_t launch_cell_offsets(const uint64_t *keys, uint32_t n_cells, const in
                                 int64_t *offsets, cudaStream_t st);
 cudaError_t launch_ref_totals(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *totals, cudaStream_t st);
 cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, cudaStream_t st);
-cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, const int32_t *read_batch,
-                              const uint64_t *const *batch_keys, const uint32_t *batch_n, cudaStream_t st);
+cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, int64_t n_refs, const int32_t *read_batch,
+                              const int32_t *read_slot, const uint64_t *const *batch_keys, const uint32_t *batch_n,
+                              cudaStream_t st);
 cudaError_t sort_keys(uint64_t *keys_in, uint64_t *keys_out, uint32_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t      sort_keys_tmp_bytes(uint32_t n);
 

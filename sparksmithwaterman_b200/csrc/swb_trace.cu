@@ -147,9 +147,11 @@ __device__ __forceinline__ void init_group(const BatchParams &P, int rp, int hal
 
 // ---------------------------------------------------------------------------------------
 template <int K>
-__global__ void __launch_bounds__(128) locate_kernel(const BatchParams P, const TileTask *tasks, uint32_t n_tasks,
+__global__ void __launch_bounds__(128) locate_kernel(const BatchParams P, const TileTask *tasks,
+                                                      const uint32_t *n_tasks_ptr, uint32_t cap_tasks,
                                                       uint64_t *keys, uint32_t cap, uint32_t *count)
 {
+    const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);        // written by flag_tiles on the same stream
     const int lane = threadIdx.x & 31, t = lane & (GL - 1), g = lane >> 3;
     const unsigned gmask = 0xffu << (8 * g);
     const uint32_t n_groups = gridDim.x * (blockDim.x >> 3);
@@ -164,10 +166,12 @@ __global__ void __launch_bounds__(128) locate_kernel(const BatchParams P, const 
         int64_t blk0 = 0, pair = 0; int read_idx = 0;
         int H[K], diag = 0;
         int S = 0;
+        uint64_t pkey = 0;
         if (live) {
             init_group<K>(P, (int)(T.rp_half >> 1), (int)(T.rp_half & 1), (int)T.ref_sorted, t, C, blk0, pair, read_idx);
             load_state<K>(P, blk0, (int)T.block, (int)(T.rp_half & 1), t, H, diag);
             S = P.scores[pair];
+            pkey = (uint64_t)T.rp_half * (uint64_t)P.n_refs + (uint64_t)P.ref_orig[T.ref_sorted];
         } else {
             C.n = 0; C.m = 0; C.ref_words = P.ref_words; C.match = C.mismatch = C.gap = 0;
 #pragma unroll
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(128) locate_kernel(const BatchParams P, const 
                              const int i = t * K + r + 1;
                              if (Hc[r] == S && i <= C.m) {
                                  const uint32_t k = atomicAdd(count, 1u);
-                                 if (k < cap) keys[k] = make_key((uint64_t)pair, (uint32_t)i, (uint32_t)j);
+                                 if (k < cap) keys[k] = make_key(pkey, (uint32_t)i, (uint32_t)j);
                              }
                          }
                      });
@@ -190,149 +194,293 @@ __global__ void __launch_bounds__(128) locate_kernel(const BatchParams P, const 
 }
 
 template <int K>
-static cudaError_t launch_locate_k(const BatchParams &P, const TileTask *tasks, uint32_t n_tasks, uint64_t *keys,
-                                   uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st)
+static cudaError_t launch_locate_k(const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
+                                   uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
+                                   cudaStream_t st)
 {
-    if (n_tasks == 0) return cudaSuccess;
-    const int threads = 128;                      // 16 groups per CTA
-    int64_t ctas = ((int64_t)n_tasks + 15) / 16;
-    ctas = std::min<int64_t>(ctas, (int64_t)sm_count * 16);
-    locate_kernel<K><<<(unsigned)ctas, threads, 0, st>>>(P, tasks, n_tasks, keys, cap, count);
+    const int threads = 128;                      // 16 groups per CTA; the task count is read on the device
+    int64_t ctas = std::min<int64_t>(((int64_t)cap_tasks + 15) / 16, (int64_t)sm_count * 16);
+    locate_kernel<K><<<(unsigned)std::max<int64_t>(ctas, 1), threads, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count);
     return cudaGetLastError();
 }
 
-cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, uint32_t n_tasks, uint64_t *keys,
-                          uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st)
+cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
+                          uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
+                          cudaStream_t st)
 {
     switch (K) {
-        case 4:  return launch_locate_k<4>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
-        case 8:  return launch_locate_k<8>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
-        case 13: return launch_locate_k<13>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
-        case 16: return launch_locate_k<16>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
-        case 19: return launch_locate_k<19>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
-        case 25: return launch_locate_k<25>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
-        case 32: return launch_locate_k<32>(P, tasks, n_tasks, keys, cap, count, sm_count, st);
+        case 4:  return launch_locate_k<4>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 8:  return launch_locate_k<8>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 13: return launch_locate_k<13>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 16: return launch_locate_k<16>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 19: return launch_locate_k<19>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 25: return launch_locate_k<25>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 32: return launch_locate_k<32>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }
 
+template <int K> struct TraceGeo {
+    // lanes of a half's tile: a walk of CB steps climbs at most CB rows (plus rare insertion runs,
+    // which simply end the block early), i.e. ceil(CB / K) lanes above the current one
+    static constexpr int NLW = ((CB + K - 1) / K + 1) < GL ? ((CB + K - 1) / K + 1) : GL;
+};
+
+// one tile column (KW words) of this lane into the windows it belongs to (either may be null)
+template <int KW>
+__device__ __forceinline__ void store_column(uint32_t *ta, uint32_t *tb, int c, const uint32_t (&v)[KW])
+{
+    if (ta) {
+        uint4 *col = reinterpret_cast<uint4 *>(ta + c * KW);
+#pragma unroll
+        for (int q = 0; q < KW / 4; ++q) col[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+    if (tb) {
+        uint4 *col = reinterpret_cast<uint4 *>(tb + c * KW);
+#pragma unroll
+        for (int q = 0; q < KW / 4; ++q) col[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    }
+}
+
 // ---------------------------------------------------------------------------------------
-// Traceback.  Tile of one group in shared memory (int16):
-//   tile[t][c][r], c = 0..CB, r = 0..K.   c = 0 is the checkpointed column of lane t,
-//   c >= 1 the column computed at step u = c-1; r = 0 is the boundary row received from
-//   lane t-1 (row t*K of the matrix), r >= 1 the lane's own rows.  With that halo every
-//   neighbour (W, N, NW) of a cell with c >= 1, r >= 1 lies in the same lane's tile.
+// Traceback, packed: one 8-lane group walks TWO max cells at once, one per s16 half.
+// Keys are sorted (read slot, ref, i, j), so a run of cells shares its read: the two halves
+// align the same read rows against two (usually different) references, and the score
+// profile depends on the read only:
+//     prof2[cA*5 + cB][lane][row] = pack(s(read[row], cA), s(read[row], cB)),  code 4 = "no column"
+// (S_PAD: a column left of the matrix stays all-zero, one right of it is never read).
+// Each half restarts from ITS block's checkpoint (own ref, own block index); the group then
+// runs the same three-op cell as the fill for CB steps, storing every column:
+//     tile[lane][c][w]   c = 0..CB (c = 0: the checkpointed column), w = 0: boundary row
+//                        received from lane-1 (matrix row lane*K), w = 1..K: the lane's rows
+// so W, N and NW of a cell with c >= 1 lie in the same lane's tile.  Lane h of the group
+// walks half h (GetAlignment.call, SmithWaterman.java:380-409) until the path leaves the
+// block, then the block that holds the current cell is recomputed -- exact, because every
+// block starts from the fill's own registers.
 template <int K>
 __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const uint64_t *keys, uint32_t n_cells,
-                                                     int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
-                                                     int ops_stride, int groups_per_cta)
+                                                     int chunk, int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
+                                                     int ops_stride, uint32_t zero)
 {
     using G = Geo<K>;
-    extern __shared__ __align__(16) int16_t tiles[];
-    const int lane = threadIdx.x & 31, t = lane & (GL - 1), g = lane >> 3;
-    const int warp = threadIdx.x >> 5;
+    constexpr int KW = G::KW;
+    constexpr int NLW = TraceGeo<K>::NLW;                           // lanes kept per half: a CB-step walk climbs <= CB rows
+    constexpr int HALF_WORDS = NLW * (CB + 1) * KW;
+    constexpr int TILE_WORDS = 2 * HALF_WORDS;
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t seg_next;
+    uint32_t *prof2 = smem;                                         // [25][GL][KS]
+    const int lane = threadIdx.x & 31, t = lane & (GL - 1), g = lane >> 3, warp = threadIdx.x >> 5;
     const unsigned gmask = 0xffu << (8 * g);
-    const int gl = warp * 4 + g;                                   // group within CTA
-    int16_t *tile = tiles + (size_t)gl * G::TILE_HALFWORDS;
-    int16_t *mytile = tile + (size_t)t * (CB + 1) * G::RS;
-    const uint32_t n_groups = gridDim.x * groups_per_cta;
-    const uint32_t gid = blockIdx.x * groups_per_cta + gl;
-
-    // per-group state (identical in all 8 lanes; lane 0 walks and broadcasts)
-    bool busy = false;
-    uint32_t cell = 0, next_cell = gid;
-    int ci = 0, cj = 0, hcur = 0, beginning = 0, oplen = 0, half = 0, b = 0;
-    uint32_t opword = 0;
-    GroupCtx<K> C;
-    int64_t blk0 = 0, pair = 0; int read_idx = 0;
-    C.n = 0; C.m = 0; C.ref_words = P.ref_words; C.match = C.mismatch = C.gap = 0;
-#pragma unroll
-    for (int r = 0; r < K; ++r) C.rc[r] = 0xFE;
-
-    for (;;) {
-        if (!busy && next_cell < n_cells) {
-            cell = next_cell; next_cell += n_groups;
-            const uint64_t key = keys[cell];
-            pair = (int64_t)key_pair(key);
-            ci = (int)key_i(key); cj = (int)key_j(key);
-            const int64_t ro = pair / P.n_reads;
-            const int rd = (int)(pair - ro * P.n_reads);
-            const int slot = P.read_slot[rd];
-            const int ref = P.ref_sorted_of[ro];
-            half = slot & 1;
-            init_group<K>(P, slot >> 1, half, ref, t, C, blk0, pair, read_idx);
-            hcur = P.scores[pair];
-            beginning = 0; oplen = 0; opword = 0;
-            busy = true;
-        }
-        if (!__any_sync(0xffffffffu, busy)) break;
-
-        // ---- recompute the block that holds the current cell ---------------------------
+    uint32_t *tile = smem + 25 * G::CSTRIDE + (size_t)(warp * 4 + g) * TILE_WORDS;
+    const uint32_t g2 = pack2(P.gap, P.gap);
+    const uint32_t c_lo = blockIdx.x * (uint32_t)chunk;
+    const uint32_t c_hi = min(n_cells, c_lo + (uint32_t)chunk);
+    uint32_t seg_lo = c_lo;
+    while (seg_lo < c_hi) {
+        // ---- segment = run of cells of one read (slot) -----------------------------------
+        const uint32_t slot = (uint32_t)(key_pair(keys[seg_lo]) / (uint64_t)P.n_refs);
+        uint32_t seg_hi;
         {
-            const int tc = (ci - 1) / K;
-            b = busy ? (cj - 1 + tc) / CB : 0;
+            const uint64_t target = make_key((uint64_t)(slot + 1) * (uint64_t)P.n_refs, 0, 0);
+            uint32_t lo = seg_lo, hi = c_hi;
+            while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+            seg_hi = lo;
         }
-        int H[K], diag;
-        if (busy) load_state<K>(P, blk0, b, half, t, H, diag);
-        else {
-#pragma unroll
-            for (int r = 0; r < K; ++r) H[r] = 0;
-            diag = 0;
+        const int read_idx = P.rp_reads[slot];
+        const int rh = (int)(slot & 1u);                             // the read's half in the fill's checkpoints
+        const int64_t roff = P.read_off[read_idx];
+        const int m = (int)(P.read_off[read_idx + 1] - roff);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 25 * GL * K; idx += blockDim.x) {
+            const int cc = idx / (GL * K), rem = idx - cc * GL * K;
+            const int tt = rem / K, r = rem - tt * K;
+            const int row = tt * K + r;
+            const int ca = cc / 5, cb = cc - ca * 5;
+            int lo = S_PAD, hi = S_PAD;
+            if (row < m) {
+                const int q = P.read_codes[roff + row];
+                if (ca < 4) lo = (q == ca) ? P.match : P.mismatch;
+                if (cb < 4) hi = (q == cb) ? P.match : P.mismatch;
+            }
+            prof2[cc * G::CSTRIDE + tt * G::KS + r] = pack2(lo, hi);
         }
-        // halo column c = 0
-        {
-            mytile[0] = (int16_t)diag;
-#pragma unroll
-            for (int r = 0; r < K; ++r) mytile[r + 1] = (int16_t)H[r];
-        }
-        run_block<K>(C, b, t, gmask, H, diag,
-                     [&](int u, int top, const int (&Hc)[K], bool, int) {
-                         int16_t *col = mytile + (u + 1) * G::RS;
-                         col[0] = (int16_t)top;
-#pragma unroll
-                         for (int r = 0; r < K; ++r) col[r + 1] = (int16_t)Hc[r];
-                     });
-        __syncwarp();
+        if (threadIdx.x == 0) seg_next = seg_lo;
+        __syncthreads();
 
-        // ---- walk inside the tile (lane 0 of the group) --------------------------------
-        int done = 0;
-        if (busy && t == 0) {
-            uint32_t *myops = ops + (size_t)cell * ops_stride;
-            while (hcur > 0) {
-                const int tc = (ci - 1) / K;
-                const int r = ci - tc * K;                          // 1..K
-                const int c = cj - (b * CB - tc);                   // column index in lane tc's tile
-                if (c < 1 || c > CB) break;                         // the cell belongs to an earlier block
-                const int16_t *lt = tile + ((size_t)tc * (CB + 1) + c) * G::RS + r;
-                const int hw = lt[-G::RS];                          // W  = tile[tc][c-1][r]
-                const int hn = lt[-1];                              // N  = tile[tc][c][r-1]
-                const int hnw = lt[-G::RS - 1];                     // NW = tile[tc][c-1][r-1]
-                const int col = cj - 1;
-                const int rc = (int)((__ldg(C.ref_words + (col >> 4)) >> (2 * (col & 15))) & 3u);
-                const int qc = (int)P.read_codes[P.read_off[read_idx] + ci - 1];
-                const int sc = (qc == rc) ? C.match : C.mismatch;
-                beginning = cj;
-                uint32_t op;
-                if (hnw + sc == hcur)        { op = 1; --ci; --cj; hcur = hnw; }   // alignment
-                else if (hn + C.gap == hcur) { op = 2; --ci;       hcur = hn;  }   // insertion
-                else                         { op = 3;       --cj; hcur = hw;  }   // deletion
-                opword |= op << (2 * (oplen & 15));
-                ++oplen;
-                if ((oplen & 15) == 0) { myops[(oplen >> 4) - 1] = opword; opword = 0; }
+        // ---- per-half state, replicated in the 8 lanes of the group ----------------------
+        bool busy0 = false, busy1 = false;
+        int ci0 = 0, cj0 = 0, ci1 = 0, cj1 = 0, n0 = 0, n1 = 0;
+        const uint32_t *rw0 = P.ref_words, *rw1 = P.ref_words;
+        int64_t bk0 = 0, bk1 = 0;
+        // walker state (lane 0 -> half 0, lane 1 -> half 1)
+        uint32_t w_cell = 0, w_opword = 0;
+        int w_h = 0, w_beg = 0, w_len = 0;
+
+        for (;;) {
+            // fetch a new cell for every idle half
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const bool idle = h ? !busy1 : !busy0;
+                uint32_t e = 0xffffffffu;
+                if (idle && t == h) e = atomicAdd(&seg_next, 1u);
+                e = __shfl_sync(gmask, e, h, GL);
+                if (idle && e < seg_hi) {
+                    const uint64_t key = keys[e];
+                    const int ro = (int)(key_pair(key) - (uint64_t)slot * (uint64_t)P.n_refs);
+                    const int ref = P.ref_sorted_of[ro];
+                    const int ii = (int)key_i(key), jj = (int)key_j(key);
+                    if (h == 0) { busy0 = true; ci0 = ii; cj0 = jj; n0 = P.ref_len[ref]; rw0 = P.ref_words + P.ref_word_off[ref];
+                                  bk0 = (int64_t)(slot >> 1) * P.blocks_per_rp + P.ref_blk_off[ref]; }
+                    else        { busy1 = true; ci1 = ii; cj1 = jj; n1 = P.ref_len[ref]; rw1 = P.ref_words + P.ref_word_off[ref];
+                                  bk1 = (int64_t)(slot >> 1) * P.blocks_per_rp + P.ref_blk_off[ref]; }
+                    if (t == h) {
+                        w_cell = e; w_opword = 0; w_beg = 0; w_len = 0;
+                        w_h = P.scores[(int64_t)ro * P.n_reads + read_idx];
+                    }
+                }
             }
-            if (hcur <= 0) {
-                if (oplen & 15) myops[oplen >> 4] = opword;
-                beginnings[cell] = beginning;
-                op_lens[cell] = oplen;
-                done = 1;
+            if (!__any_sync(0xffffffffu, busy0 || busy1)) break;
+
+            // ---- block of each half, checkpoint -> registers ---------------------------------
+            const int b0 = busy0 ? (cj0 - 1 + (ci0 - 1) / K) / CB : 0;
+            const int b1 = busy1 ? (cj1 - 1 + (ci1 - 1) / K) / CB : 0;
+            // window of lanes whose columns the walk of each half may read: [tc - NLW + 1, tc]
+            const int tca = (ci0 - 1) / K, tcb = (ci1 - 1) / K;
+            const int sa = busy0 ? t - (tca - NLW + 1) : -1;          // this lane's slot in half 0's tile, if any
+            const int sb = busy1 ? t - (tcb - NLW + 1) : -1;
+            uint32_t *tileA = (sa >= 0 && sa < NLW) ? tile + (size_t)sa * (CB + 1) * KW : nullptr;
+            uint32_t *tileB = (sb >= 0 && sb < NLW) ? tile + HALF_WORDS + (size_t)sb * (CB + 1) * KW : nullptr;
+            uint32_t H[K], diag = 0;
+            {
+                const uint4 *ckA = reinterpret_cast<const uint4 *>(P.ck + (bk0 + b0) * (int64_t)(KW * GL)) + t;
+                const uint4 *ckB = reinterpret_cast<const uint4 *>(P.ck + (bk1 + b1) * (int64_t)(KW * GL)) + t;
+                const bool la = busy0 && b0 > 0, lb = busy1 && b1 > 0;
+                const uint32_t sel = rh ? 0x7632u : 0x5410u;        // (A.half rh) | (B.half rh) << 16
+                const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int q = 0; q < KW / 4; ++q) {
+                    const uint4 a = la ? __ldg(ckA + q * GL) : z;
+                    const uint4 bq = lb ? __ldg(ckB + q * GL) : z;
+                    const uint32_t v[4] = {__byte_perm(a.x, bq.x, sel), __byte_perm(a.y, bq.y, sel),
+                                           __byte_perm(a.z, bq.z, sel), __byte_perm(a.w, bq.w, sel)};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int w = 4 * q + e;
+                        if (w < K) H[w < K ? w : 0] = v[e];
+                        else if (w == K) diag = v[e];
+                    }
+                }
             }
+            // reference-code windows of this lane for the block: 0-based columns j0 .. j0+15
+            uint32_t win0, win1; int ulo0, uhi0, ulo1, uhi1;
+            {
+                const int j0 = b0 * CB - t, j1 = b1 * CB - t;
+                const int wi0 = j0 >> 4, wi1 = j1 >> 4;                   // floor (j may be negative in block 0)
+                const uint32_t a0 = (busy0 && wi0 >= 0 && wi0 * 16 < n0) ? __ldg(rw0 + wi0) : 0u;
+                const uint32_t a1 = (busy0 && wi0 + 1 >= 0 && (wi0 + 1) * 16 < n0) ? __ldg(rw0 + wi0 + 1) : 0u;
+                const uint32_t c0 = (busy1 && wi1 >= 0 && wi1 * 16 < n1) ? __ldg(rw1 + wi1) : 0u;
+                const uint32_t c1 = (busy1 && wi1 + 1 >= 0 && (wi1 + 1) * 16 < n1) ? __ldg(rw1 + wi1 + 1) : 0u;
+                win0 = __funnelshift_r(a0, a1, 2 * (j0 & 15));
+                win1 = __funnelshift_r(c0, c1, 2 * (j1 & 15));
+                // step u computes 0-based column j0 + u: valid iff 0 <= j0 + u < n
+                ulo0 = -j0; uhi0 = busy0 ? n0 - j0 - 1 : -1;
+                ulo1 = -j1; uhi1 = busy1 ? n1 - j1 - 1 : -1;
+            }
+            // halo column c = 0
+            {
+                uint32_t v[KW];
+                v[0] = diag;
+#pragma unroll
+                for (int r = 0; r < K; ++r) v[r + 1] = H[r];
+#pragma unroll
+                for (int r = K + 1; r < KW; ++r) v[r] = 0;
+                store_column<KW>(tileA, tileB, 0, v);
+            }
+#pragma unroll 2
+            for (int u = 0; u < CB; ++u) {
+                uint32_t top = __shfl_up_sync(gmask, H[K - 1], 1, GL);
+                if (t == 0) top = 0;
+                const int ca = (u >= ulo0 && u <= uhi0) ? (int)((win0 >> (2 * u)) & 3u) : 4;
+                const int cb = (u >= ulo1 && u <= uhi1) ? (int)((win1 >> (2 * u)) & 3u) : 4;
+                uint32_t sv[G::KP];
+                load_profile<G::KP>(prof2 + (ca * 5 + cb) * G::CSTRIDE + t * G::KS, sv);
+                uint32_t nw = diag, nn = top;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const uint32_t x = viaddmax_relu(nw, sv[r], zero);
+                    const uint32_t pre = viaddmax(H[r], g2, x);
+                    nw = H[r];
+                    H[r] = viaddmax(nn, g2, pre);
+                    nn = H[r];
+                }
+                diag = top;
+                uint32_t v[KW];
+                v[0] = top;
+#pragma unroll
+                for (int r = 0; r < K; ++r) v[r + 1] = H[r];
+#pragma unroll
+                for (int r = K + 1; r < KW; ++r) v[r] = 0;
+                store_column<KW>(tileA, tileB, u + 1, v);
+            }
+            __syncwarp();
+
+            // ---- walk: lane 0 walks half 0, lane 1 walks half 1 -------------------------------
+            int done = 0, wi = 0, wj = 0;
+            if (t < 2 && (t ? busy1 : busy0)) {
+                const int h = t;
+                int ci = h ? ci1 : ci0, cj = h ? cj1 : cj0;
+                const int b = h ? b1 : b0;
+                const int lane_lo = (h ? tcb : tca) - NLW + 1;              // first lane held in this half's tile
+                const uint32_t *rw = h ? rw1 : rw0;
+                const uint32_t *th = tile + h * HALF_WORDS;
+                uint32_t *myops = ops + (size_t)w_cell * ops_stride;
+                const uint8_t *rcodes = P.read_codes + roff;
+                while (w_h > 0) {
+                    const int tc = (ci - 1) / K;
+                    const int r = ci - tc * K;                              // 1..K
+                    const int c = cj - (b * CB - tc);                       // column index in lane tc's tile
+                    const int sl = tc - lane_lo;
+                    if (c < 1 || c > CB || sl < 0) break;                   // outside what this block holds
+                    const uint32_t *lt = th + ((size_t)sl * (CB + 1) + c) * KW + r;
+                    const int hw = half_of(lt[-KW], h);                     // W
+                    const int hn = half_of(lt[-1], h);                      // N
+                    const int hnw = half_of(lt[-KW - 1], h);                // NW
+                    const int col = cj - 1;
+                    const int rc = (int)((__ldg(rw + (col >> 4)) >> (2 * (col & 15))) & 3u);
+                    const int sc = ((int)rcodes[ci - 1] == rc) ? P.match : P.mismatch;
+                    // type of a positive cell = first of (alignment, insertion, deletion) whose candidate
+                    // equals H: the ">=" cascade of GetCellScore.call.  Branch-free: both walkers of a
+                    // warp's groups stay converged.
+                    const bool is_a = (hnw + sc == w_h);
+                    const bool is_i = !is_a && (hn + P.gap == w_h);
+                    const uint32_t op = is_a ? 1u : (is_i ? 2u : 3u);
+                    w_beg = cj;
+                    w_h = is_a ? hnw : (is_i ? hn : hw);
+                    ci -= (op != 3u);
+                    cj -= (op != 2u);
+                    w_opword |= op << (2 * (w_len & 15));
+                    ++w_len;
+                    if ((w_len & 15) == 0) { myops[(w_len >> 4) - 1] = w_opword; w_opword = 0; }
+                }
+                if (w_h <= 0) {
+                    if (w_len & 15) myops[w_len >> 4] = w_opword;
+                    beginnings[w_cell] = w_beg;
+                    op_lens[w_cell] = w_len;
+                    done = 1;
+                }
+                wi = ci; wj = cj;
+            }
+            {
+                const int d0 = __shfl_sync(gmask, done, 0, GL), d1 = __shfl_sync(gmask, done, 1, GL);
+                const int i0 = __shfl_sync(gmask, wi, 0, GL), j0 = __shfl_sync(gmask, wj, 0, GL);
+                const int i1 = __shfl_sync(gmask, wi, 1, GL), j1 = __shfl_sync(gmask, wj, 1, GL);
+                if (busy0) { ci0 = i0; cj0 = j0; if (d0) busy0 = false; }
+                if (busy1) { ci1 = i1; cj1 = j1; if (d1) busy1 = false; }
+            }
+            __syncwarp();
         }
-        // broadcast the walker's state to the group
-        done = __shfl_sync(gmask, done, 0, GL);
-        ci = __shfl_sync(gmask, ci, 0, GL);
-        cj = __shfl_sync(gmask, cj, 0, GL);
-        if (done) busy = false;
-        __syncwarp();
+        seg_lo = seg_hi;
     }
 }
 
@@ -342,20 +490,21 @@ static cudaError_t launch_trace_k(const BatchParams &P, const uint64_t *keys, ui
 {
     using G = Geo<K>;
     if (n_cells == 0) return cudaSuccess;
-    const size_t per_group = (size_t)G::TILE_HALFWORDS * sizeof(int16_t);
+    const size_t per_group = (size_t)2 * TraceGeo<K>::NLW * (CB + 1) * G::KW * sizeof(uint32_t);
+    const size_t prof_bytes = (size_t)25 * G::CSTRIDE * sizeof(uint32_t);
     int warps = 4;
-    while (warps > 1 && per_group * 4 * warps > 200 * 1024) --warps;
-    const size_t smem = per_group * 4 * warps;
+    while (warps > 1 && prof_bytes + per_group * 4 * warps > 110 * 1024) --warps;   // two CTAs per SM
+    const size_t smem = prof_bytes + per_group * 4 * warps;
     static bool attr_set[64] = {false};
     if (!attr_set[K]) {
         cudaError_t e = cudaFuncSetAttribute(trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set[K] = true;
     }
-    const int gpc = warps * 4;
-    int64_t ctas = ((int64_t)n_cells + gpc - 1) / gpc;
-    ctas = std::min<int64_t>(ctas, (int64_t)sm_count * 2);
-    trace_kernel<K><<<(unsigned)ctas, warps * 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, gpc);
+    // chunks of the sorted cell list: several per SM for balance, each long enough to amortise its profile
+    int chunk = (int)std::max<int64_t>(256, ((int64_t)n_cells + sm_count * 4 - 1) / (sm_count * 4));
+    const int64_t ctas = ((int64_t)n_cells + chunk - 1) / chunk;
+    trace_kernel<K><<<(unsigned)ctas, warps * 32, smem, st>>>(P, keys, n_cells, chunk, beginnings, op_lens, ops, ops_stride, 0u);
     return cudaGetLastError();
 }
 
@@ -441,8 +590,8 @@ cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_re
 }
 
 // fill (i, j) of each read's best hit: first key of pair (best ref, read) in the read's batch
-__global__ void best_cells_kernel(int32_t *best, int64_t n_reads, const int32_t *read_batch,
-                                  const uint64_t *const *batch_keys, const uint32_t *batch_n)
+__global__ void best_cells_kernel(int32_t *best, int64_t n_reads, int64_t n_refs, const int32_t *read_batch,
+                                  const int32_t *read_slot, const uint64_t *const *batch_keys, const uint32_t *batch_n)
 {
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n_reads) return;
@@ -450,7 +599,7 @@ __global__ void best_cells_kernel(int32_t *best, int64_t n_reads, const int32_t 
     const int ref = best[4 * q + 1];
     if (b < 0 || ref < 0 || best[4 * q] <= 0) return;
     const uint64_t *keys = batch_keys[b];
-    const uint64_t p = (uint64_t)ref * (uint64_t)n_reads + (uint64_t)q;
+    const uint64_t p = (uint64_t)read_slot[q] * (uint64_t)n_refs + (uint64_t)ref;   // key order: (read slot, ref)
     const uint64_t target = make_key(p, 0, 0);
     uint32_t lo = 0, hi = batch_n[b];
     while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < target) lo = mid + 1; else hi = mid; }
@@ -460,13 +609,14 @@ __global__ void best_cells_kernel(int32_t *best, int64_t n_reads, const int32_t 
     }
 }
 
-cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, const int32_t *read_batch,
-                              const uint64_t *const *batch_keys, const uint32_t *batch_n, cudaStream_t st)
+cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, int64_t n_refs, const int32_t *read_batch,
+                              const int32_t *read_slot, const uint64_t *const *batch_keys, const uint32_t *batch_n,
+                              cudaStream_t st)
 {
     if (n_reads == 0) return cudaSuccess;
     const int threads = 128;
-    best_cells_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(best, n_reads, read_batch,
-                                                                                        batch_keys, batch_n);
+    best_cells_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(best, n_reads, n_refs, read_batch,
+                                                                                        read_slot, batch_keys, batch_n);
     return cudaGetLastError();
 }
 
