@@ -1,146 +1,22 @@
 // swb_api.cu -- the C ABI (include/swb200.h): contexts, HBM-resident reference sets and
 // read batches, the align driver (batching, kernel sequencing, timing) and result access.
 // No CPU fallback: every compute entry needs a CUDA device and fails loudly without one.
-#include "swb_internal.h"
+#include "swb_host.h"
 
-#include <algorithm>
-#include <cstdio>
-#include <cstring>
-#include <memory>
-#include <mutex>
-#include <numeric>
+using namespace swbh;
 
-using namespace swb;
-
-namespace {
-
-thread_local std::string g_err;
-
-int fail(int code, const std::string &msg) { g_err = msg; return code; }
-int cuda_fail(cudaError_t e, const char *what)
+namespace swbh {
+std::string &last_error()
 {
-    g_err = std::string(what) + ": " + cudaGetErrorString(e);
-    return SWB_E_CUDA;
+    thread_local std::string e;
+    return e;
 }
-#define CU(x)                                                                  \
-    do {                                                                       \
-        cudaError_t e_ = (x);                                                  \
-        if (e_ != cudaSuccess) return cuda_fail(e_, #x);                       \
-    } while (0)
-
-// Device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are
-// ordered on the engine's stream and reuse pool memory, so the align loop never hits the
-// synchronising cudaMalloc/cudaFree.
-template <class T> struct DevBuf {
-    T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
-    DevBuf() = default;
-    DevBuf(const DevBuf &) = delete;
-    DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
-    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
-    ~DevBuf() { release(); }
-    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
-    cudaError_t alloc(size_t count, cudaStream_t stream)
-    {
-        release();
-        if (count == 0) count = 1;
-        st = stream;
-        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), stream);
-        if (e == cudaSuccess) n = count; else p = nullptr;
-        return e;
-    }
-    cudaError_t reserve(size_t count, cudaStream_t stream) { return n >= count && p ? cudaSuccess : alloc(count + count / 8, stream); }
-};
-
-inline int upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
-
-}  // namespace
-
-struct swb_ctx {
-    int device = 0;
-    int sm_count = 0;
-    int64_t ws_bytes = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[2] = {nullptr, nullptr};
-    std::recursive_mutex mu;
-    // grow-only scratch reused by every align call on this context
-    DevBuf<uint32_t> ck, tmx, counters;
-    DevBuf<int32_t> rp, slot;
-    DevBuf<TileTask> tasks;
-    DevBuf<uint64_t> keys_tmp;
-    DevBuf<uint8_t> sort_tmp;
-    std::vector<cudaEvent_t> ev_pool;
-    size_t ev_used = 0;
-    cudaError_t next_event(cudaEvent_t *e)
-    {
-        if (ev_used == ev_pool.size()) {
-            cudaEvent_t n;
-            cudaError_t rc = cudaEventCreate(&n);
-            if (rc != cudaSuccess) return rc;
-            ev_pool.push_back(n);
-        }
-        *e = ev_pool[ev_used++];
-        return cudaSuccess;
-    }
-};
-
-struct swb_refset {
-    swb_ctx *ctx = nullptr;
-    int64_t n_refs = 0, total_bases = 0, blocks_per_rp = 0;
-    int32_t max_len = 0;
-    int n_symbols = 0;
-    uint8_t code_of[128];                       // upper-cased ASCII byte -> code, 0xFF = not in the set
-    std::vector<int32_t> len_orig;
-    DevBuf<uint32_t> words, word_off;
-    DevBuf<int32_t> len, orig, sorted_of;
-    DevBuf<int64_t> blk_off;
-};
-
-struct swb_reads {
-    swb_ctx *ctx = nullptr;
-    const swb_refset *rs = nullptr;
-    int64_t n_reads = 0;
-    std::vector<int32_t> len;
-    DevBuf<uint8_t> codes;
-    DevBuf<int64_t> off;
-};
-
-namespace {
-struct BatchOut {
-    int K = 0;
-    uint32_t n_cells = 0;
-    int ops_stride = 0;
-    DevBuf<uint64_t> keys;
-    DevBuf<int32_t> beg, oplen;
-    DevBuf<uint32_t> ops;
-    std::vector<int32_t> slot_read;              // read slot of this batch -> read index of the call
-    // host copies (after fetch)
-    std::vector<uint64_t> h_keys;
-    std::vector<uint32_t> h_ops;
-};
-}  // namespace
-
-struct swb_result {
-    swb_ctx *ctx = nullptr;
-    int64_t n_refs = 0, n_reads = 0;
-    uint32_t flags = 0;
-    bool fetched = false;
-    std::vector<int32_t> ref_len, read_len;
-    DevBuf<int32_t> d_scores, d_totals, d_best;
-    std::vector<BatchOut> batches;
-    // host
-    std::vector<int32_t> scores, totals, best;
-    std::vector<int64_t> cell_off;
-    std::vector<int32_t> cells, beginnings, op_lens;
-    std::vector<uint32_t> cell_batch;            // per global cell: batch index
-    std::vector<uint32_t> cell_local;            // per global cell: index inside the batch
-    double stats[12] = {0};
-};
+}  // namespace swbh
 
 extern "C" {
 
 int swb_abi_version(void) { return SWB_ABI_VERSION; }
-const char *swb_last_error(void) { return g_err.c_str(); }
+const char *swb_last_error(void) { return last_error().c_str(); }
 
 int swb_device_count(void)
 {
@@ -190,6 +66,9 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
     c->tasks.release(); c->keys_tmp.release(); c->sort_tmp.release();
+    c->w_brow.release(); c->w_ck.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
+    c->w_pair_read.release(); c->w_band_off.release(); c->w_blk_off.release(); c->w_brow_off.release();
+    c->w_items.release(); c->w_tasks.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
     cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
@@ -246,13 +125,8 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
     }
     memset(rs->code_of, 0xFF, sizeof rs->code_of);
     for (int c = 0; c < 128; ++c)
-        if (present[c]) {
-            if (rs->n_symbols == 4)
-                return fail(SWB_E_UNSUPPORTED,
-                            "swb_refset_load: more than 4 distinct (case-folded) symbols in the reference set; "
-                            "the 2-bit path cannot hold it");
-            rs->code_of[c] = (uint8_t)rs->n_symbols++;
-        }
+        if (present[c]) rs->code_of[c] = (uint8_t)rs->n_symbols++;
+    rs->two_bit_ok = rs->n_symbols <= 4;       // otherwise only the 8-bit int32 path can hold the set
 
     // length buckets: descending length, stable
     std::vector<int32_t> order((size_t)n_refs);
@@ -283,7 +157,25 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         const unsigned char *p = (const unsigned char *)bytes + offsets[o];
         uint32_t *w = words.data() + word_off[(size_t)s];
         const int32_t n = len_sorted[(size_t)s];
-        for (int32_t c = 0; c < n; ++c) w[c >> 4] |= (uint32_t)rs->code_of[upper(p[c])] << (2 * (c & 15));
+        if (rs->two_bit_ok)
+            for (int32_t c = 0; c < n; ++c) w[c >> 4] |= (uint32_t)rs->code_of[upper(p[c])] << (2 * (c & 15));
+    }
+    // 8-bit codes in the caller's order for the wide path
+    {
+        std::vector<uint8_t> c8((size_t)rs->total_bases + 1);
+        std::vector<int64_t> o8((size_t)n_refs + 1);
+        int64_t pos = 0;
+        for (int64_t k = 0; k < n_refs; ++k) {
+            o8[(size_t)k] = pos;
+            const unsigned char *p = (const unsigned char *)bytes + offsets[k];
+            for (int32_t c = 0; c < rs->len_orig[(size_t)k]; ++c) c8[(size_t)pos++] = rs->code_of[upper(p[c])];
+        }
+        o8[(size_t)n_refs] = pos;
+        CU(rs->codes8.alloc(c8.size(), ctx->stream));
+        CU(rs->off8.alloc(o8.size(), ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+        CU(cudaMemcpy(rs->codes8.p, c8.data(), c8.size(), cudaMemcpyHostToDevice));
+        CU(cudaMemcpy(rs->off8.p, o8.data(), o8.size() * 8, cudaMemcpyHostToDevice));
     }
     CU(rs->words.alloc(words.size(), ctx->stream));
     CU(rs->word_off.alloc((size_t)n_refs, ctx->stream));
@@ -331,8 +223,8 @@ int swb_reads_upload(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const 
     for (int64_t k = 0; k < n_reads; ++k) {
         off[(size_t)k] = total;
         const int64_t m = offsets[k + 1] - offsets[k];
-        if (m > MAX_SHORT_ROWS)
-            return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: read longer than 256 bases (long-pair path not built yet)");
+        if (m >= (1 << 21))
+            return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: read longer than 2,097,151 bases");
         rd->len[(size_t)k] = (int32_t)m;
         total += m;
     }
@@ -381,12 +273,20 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     if (n_refs * n_reads >= ((int64_t)1 << 33)) return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^33 pairs per call");
     int32_t max_m = 0;
     for (int32_t m : rd->len) max_m = std::max(max_m, m);
-    // domain of the s16x2 kernels (the int32 long-pair path is not built yet)
-    if (gap >= 0) return fail(SWB_E_UNSUPPORTED, "swb_align: gap score must be negative on the s16x2 path");
-    if (std::abs((int64_t)match) > 8000 || std::abs((int64_t)mismatch) > 8000 || std::abs((int64_t)gap) > 8000)
-        return fail(SWB_E_UNSUPPORTED, "swb_align: |score| > 8000 not supported on the s16x2 path");
-    if ((int64_t)std::max(match, 0) * std::min<int64_t>(max_m, rs->max_len) > 16000)
-        return fail(SWB_E_UNSUPPORTED, "swb_align: match * min(m, n) exceeds the s16 range");
+    // Java int arithmetic wraps; this engine refuses inputs whose scores could leave int32 instead
+    {
+        const int64_t big = std::max({std::abs((int64_t)match), std::abs((int64_t)mismatch), std::abs((int64_t)gap)});
+        if (big * ((int64_t)max_m + rs->max_len + 2) >= ((int64_t)1 << 30))
+            return fail(SWB_E_UNSUPPORTED, "swb_align: |score| * (m + n) could overflow int32");
+    }
+    // s16x2 short-read kernels: gap < 0 (padding stays below the maximum), small scores, 2-bit alphabet;
+    // everything else goes through the int32 wide path (swb_wide.cu)
+    const bool short_scores_ok = rs->two_bit_ok && gap < 0 && std::abs((int64_t)match) <= 8000 &&
+                                 std::abs((int64_t)mismatch) <= 8000 && std::abs((int64_t)gap) <= 8000;
+    auto read_is_short = [&](int32_t m) {
+        return short_scores_ok && m <= MAX_SHORT_ROWS &&
+               (int64_t)std::max(match, 0) * std::min<int64_t>(m, rs->max_len) <= 16000;
+    };
 
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
@@ -413,8 +313,9 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
         return e;
     };
     auto toc = [&]() -> cudaError_t { return cudaEventRecord(spans.back().b, st); };
+    (void)max_m;
 
-    std::vector<int32_t> h_read_batch, h_read_slot_all;
+    std::vector<int32_t> h_read_batch, h_read_slot_all, wide_reads_all;
     double ck_bytes = 0;
     int launches = 1, n_batches = 0;
     CU(ctx->counters.reserve(8, st));
@@ -422,12 +323,15 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     if (n_refs > 0 && n_reads > 0) {
         // group reads by rows-per-lane class, longest first inside a class
         std::vector<std::vector<int32_t>> classes(kNumK);
+        std::vector<int32_t> wide_reads;
         for (int64_t q = 0; q < n_reads; ++q) {
             const int m = rd->len[(size_t)q];
             if (m == 0) continue;                                  // score 0, no cells
+            if (!read_is_short(m)) { wide_reads.push_back((int32_t)q); continue; }
             const int K = pick_k(m);
             for (int k = 0; k < kNumK; ++k) if (kKList[k] == K) classes[(size_t)k].push_back((int32_t)q);
         }
+        wide_reads_all = wide_reads;
         CU(ctx->slot.reserve((size_t)n_reads, st));
         std::vector<int32_t> h_slot((size_t)n_reads);
         h_read_batch.assign((size_t)n_reads, -1);
@@ -545,6 +449,11 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 res->batches.push_back(std::move(bo));
             }
         }
+    }
+    if (n_refs > 0 && !wide_reads_all.empty()) {
+        int rc = run_wide_path(ctx, rs, rd, wide_reads_all, match, mismatch, gap, flags, res.get(), &launches, &n_batches,
+                               &ck_bytes, tic, toc);
+        if (rc) return rc;
     }
     CU(tic(4));
     CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
@@ -664,6 +573,7 @@ int swb_result_fetch(swb_result *res)
     res->cell_off.assign(n_pairs + 1, 0);
     const uint64_t nr = (uint64_t)std::max<int64_t>(res->n_refs, 1);
     auto pair_of = [&](const BatchOut &bo, uint64_t key) -> size_t {
+        if (bo.wide) return (size_t)bo.wide_pair_p[(size_t)wide::wide_key_pair(key)];
         const uint64_t pk = key_pair(key);
         const uint64_t slot = pk / nr, ref = pk - slot * nr;
         return (size_t)(ref * (uint64_t)res->n_reads + (uint64_t)bo.slot_read[(size_t)slot]);
@@ -678,13 +588,30 @@ int swb_result_fetch(swb_result *res)
             for (uint32_t k = 0; k < bo.n_cells; ++k) {
                 const uint64_t key = bo.h_keys[k];
                 const size_t c = (size_t)cursor[pair_of(bo, key)]++;
-                res->cells[2 * c] = (int32_t)key_i(key);
-                res->cells[2 * c + 1] = (int32_t)key_j(key);
+                res->cells[2 * c] = (int32_t)(bo.wide ? wide::wide_key_i(key) : key_i(key));
+                res->cells[2 * c + 1] = (int32_t)(bo.wide ? wide::wide_key_j(key) : key_j(key));
                 res->beginnings[c] = h_beg[b][k];
                 res->op_lens[c] = h_len[b][k];
                 res->cell_batch[c] = (uint32_t)b; res->cell_local[c] = k;
             }
         }
+    }
+    // best-hit cells of reads that went through the wide path are filled here (the device kernel
+    // only knows the short path's key layout)
+    {
+        bool patched = false;
+        for (int64_t q = 0; q < res->n_reads; ++q) {
+            int32_t *b = res->best.data() + 4 * q;
+            if (b[0] > 0 && b[1] >= 0 && b[2] == 0) {
+                const size_t p = (size_t)b[1] * (size_t)res->n_reads + (size_t)q;
+                if (res->cell_off[p + 1] > res->cell_off[p]) {
+                    b[2] = res->cells[2 * (size_t)res->cell_off[p]];
+                    b[3] = res->cells[2 * (size_t)res->cell_off[p] + 1];
+                    patched = true;
+                }
+            }
+        }
+        if (patched) CU(cudaMemcpy(res->d_best.p, res->best.data(), (size_t)res->n_reads * 16, cudaMemcpyHostToDevice));
     }
     res->fetched = true;
     return SWB_OK;
@@ -748,7 +675,7 @@ int swb_result_ops(const swb_result *r, int64_t cell, uint8_t *outp, int64_t cap
     const int32_t len = r->op_lens[(size_t)cell];
     if (cap < len) return fail(SWB_E_RANGE, "swb_result_ops: buffer too small");
     const BatchOut &bo = r->batches[r->cell_batch[(size_t)cell]];
-    const uint32_t *w = bo.h_ops.data() + (size_t)r->cell_local[(size_t)cell] * bo.ops_stride;
+    const uint32_t *w = bo.h_ops.data() + (size_t)r->cell_local[(size_t)cell] * (size_t)bo.ops_stride;
     // the device stores the walk order (end -> start); hand out start -> end
     for (int32_t k = 0; k < len; ++k) {
         const int32_t src = len - 1 - k;

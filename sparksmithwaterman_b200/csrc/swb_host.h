@@ -1,0 +1,155 @@
+// swb_host.h -- host-side structures of libswb200 shared by swb_api.cu and swb_wide_host.cu.
+#pragma once
+#include "swb_internal.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <numeric>
+
+namespace swbh {
+using namespace swb;
+
+std::string &last_error();
+inline int fail(int code, const std::string &msg) { last_error() = msg; return code; }
+inline int cuda_fail(cudaError_t e, const char *what)
+{
+    last_error() = std::string(what) + ": " + cudaGetErrorString(e);
+    return SWB_E_CUDA;
+}
+#define CU(x)                                                                  \
+    do {                                                                       \
+        cudaError_t e_ = (x);                                                  \
+        if (e_ != cudaSuccess) return swbh::cuda_fail(e_, #x);                 \
+    } while (0)
+
+// Device buffer from the stream-ordered pool (cudaMallocAsync): allocation and release are
+// ordered on the engine's stream and reuse pool memory, so the align loop never hits the
+// synchronising cudaMalloc/cudaFree.
+template <class T> struct DevBuf {
+    T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
+    ~DevBuf() { release(); }
+    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
+    cudaError_t alloc(size_t count, cudaStream_t stream)
+    {
+        release();
+        if (count == 0) count = 1;
+        st = stream;
+        cudaError_t e = cudaMallocAsync(&p, count * sizeof(T), stream);
+        if (e == cudaSuccess) n = count; else p = nullptr;
+        return e;
+    }
+    cudaError_t reserve(size_t count, cudaStream_t stream) { return n >= count && p ? cudaSuccess : alloc(count + count / 8, stream); }
+};
+
+inline int upper(int c) { return (c >= 'a' && c <= 'z') ? c - 32 : c; }
+
+}  // namespace swbh
+
+using swbh::DevBuf;
+using swb::TileTask;
+using swb::WideTask;
+
+struct swb_ctx {
+    int device = 0;
+    int sm_count = 0;
+    int64_t ws_bytes = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    std::recursive_mutex mu;
+    // grow-only scratch reused by every align call on this context
+    DevBuf<uint32_t> ck, tmx, counters;
+    DevBuf<int32_t> rp, slot;
+    DevBuf<TileTask> tasks;
+    DevBuf<uint64_t> keys_tmp;
+    DevBuf<uint8_t> sort_tmp;
+    // wide (int32, long-pair) path scratch
+    DevBuf<int32_t> w_brow, w_ck, w_tmx, w_prog, w_pair_ref, w_pair_read;
+    DevBuf<int64_t> w_band_off, w_blk_off, w_brow_off;
+    DevBuf<int2> w_items;
+    DevBuf<WideTask> w_tasks;
+    std::vector<cudaEvent_t> ev_pool;
+    size_t ev_used = 0;
+    cudaError_t next_event(cudaEvent_t *e)
+    {
+        if (ev_used == ev_pool.size()) {
+            cudaEvent_t n;
+            cudaError_t rc = cudaEventCreate(&n);
+            if (rc != cudaSuccess) return rc;
+            ev_pool.push_back(n);
+        }
+        *e = ev_pool[ev_used++];
+        return cudaSuccess;
+    }
+};
+
+struct swb_refset {
+    swb_ctx *ctx = nullptr;
+    int64_t n_refs = 0, total_bases = 0, blocks_per_rp = 0;
+    int32_t max_len = 0;
+    int n_symbols = 0;
+    uint8_t code_of[128];                       // upper-cased ASCII byte -> code (rank among the set's symbols), 0xFF = absent
+    bool two_bit_ok = false;                    // <= 4 symbols: the 2-bit packed short-read path is available
+    DevBuf<uint8_t> codes8;                     // 1 byte per base, original order (wide path)
+    DevBuf<int64_t> off8;                       // [n_refs + 1]
+    std::vector<int32_t> len_orig;
+    DevBuf<uint32_t> words, word_off;
+    DevBuf<int32_t> len, orig, sorted_of;
+    DevBuf<int64_t> blk_off;
+};
+
+struct swb_reads {
+    swb_ctx *ctx = nullptr;
+    const swb_refset *rs = nullptr;
+    int64_t n_reads = 0;
+    std::vector<int32_t> len;
+    DevBuf<uint8_t> codes;
+    DevBuf<int64_t> off;
+};
+
+struct BatchOut {
+    int K = 0;
+    bool wide = false;                           // produced by the int32 long-pair path (different key layout)
+    std::vector<int64_t> wide_pair_p;            // wide: local pair -> ABI pair index p
+    uint32_t n_cells = 0;
+    int64_t ops_stride = 0;
+    DevBuf<uint64_t> keys;
+    DevBuf<int32_t> beg, oplen;
+    DevBuf<uint32_t> ops;
+    std::vector<int32_t> slot_read;              // read slot of this batch -> read index of the call
+    // host copies (after fetch)
+    std::vector<uint64_t> h_keys;
+    std::vector<uint32_t> h_ops;
+};
+
+struct swb_result {
+    swb_ctx *ctx = nullptr;
+    int64_t n_refs = 0, n_reads = 0;
+    uint32_t flags = 0;
+    bool fetched = false;
+    std::vector<int32_t> ref_len, read_len;
+    DevBuf<int32_t> d_scores, d_totals, d_best;
+    std::vector<BatchOut> batches;
+    // host
+    std::vector<int32_t> scores, totals, best;
+    std::vector<int64_t> cell_off;
+    std::vector<int32_t> cells, beginnings, op_lens;
+    std::vector<uint32_t> cell_batch;            // per global cell: batch index
+    std::vector<uint32_t> cell_local;            // per global cell: index inside the batch
+    double stats[12] = {0};
+};
+
+
+#include <functional>
+namespace swbh {
+int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const std::vector<int32_t> &reads,
+                  int match, int mismatch, int gap, uint32_t flags, swb_result *res, int *launches, int *n_batches,
+                  double *ck_bytes, const std::function<cudaError_t(int)> &tic, const std::function<cudaError_t()> &toc);
+}

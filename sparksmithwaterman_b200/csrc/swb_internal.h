@@ -78,7 +78,46 @@ struct BatchParams {
     uint32_t *tmx;                  // tile maxima  [n_rp][blocks_per_rp][GL]
 };
 
-struct LaunchStats { int launches = 0; };
+// ---- general ("wide") int32 path: bands of 32 lanes x KL rows, see swb_wide.cu ------------------
+namespace wide {
+constexpr int WL = 32;       // lanes per band (one warp)
+constexpr int KL = 8;        // rows per lane
+constexpr int BH = WL * KL;  // rows per band
+constexpr int WCB = 64;      // steps per checkpoint block
+// key: local pair (21 bits) | i (21 bits) | j (22 bits)
+__host__ __device__ inline uint64_t wide_key(uint64_t pair, uint32_t i, uint32_t j) { return (pair << 43) | ((uint64_t)i << 22) | j; }
+__host__ __device__ inline uint64_t wide_key_pair(uint64_t k) { return k >> 43; }
+__host__ __device__ inline uint32_t wide_key_i(uint64_t k) { return (uint32_t)(k >> 22) & ((1u << 21) - 1); }
+__host__ __device__ inline uint32_t wide_key_j(uint64_t k) { return (uint32_t)k & ((1u << 22) - 1); }
+}  // namespace wide
+
+struct WideTask { int32_t pair, band, block; uint32_t lane_mask; };
+
+struct WideParams {
+    int32_t n_pairs;
+    const int32_t *pair_ref;     // [n_pairs] reference index (original order)
+    const int32_t *pair_read;    // [n_pairs] read index
+    const uint8_t *ref_codes;    // 1 byte per base, original reference order
+    const int64_t *ref_off;      // [n_refs + 1]
+    const uint8_t *read_codes;
+    const int64_t *read_off;
+    int32_t match, mismatch, gap;
+    int64_t n_reads;
+    const int64_t *band_off;     // [n_pairs + 1] prefix of bands
+    const int64_t *blk_off;      // [n_pairs + 1] prefix of bands * blocks
+    const int64_t *brow_off;     // [n_pairs + 1] prefix of bands * (n + 1)
+    int32_t *brow, *ck, *tmx, *prog;
+    int32_t *scores;
+};
+
+cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count,
+                             cudaStream_t st);
+cudaError_t launch_wide_flag(const WideParams &P, int64_t total_blocks, WideTask *tasks, uint32_t cap, uint32_t *count,
+                             cudaStream_t st);
+cudaError_t launch_wide_locate(const WideParams &P, const WideTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
+                               uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st);
+cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+                              int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st);
 
 // swb_fill.cu
 cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st);

@@ -1,0 +1,145 @@
+// swb_wide_host.cu -- host driver of the int32 wide path (swb_wide.cu): pair batching by
+// workspace, band tickets, flag -> locate -> sort -> trace, results appended as BatchOut.
+#include "swb_host.h"
+
+#include <functional>
+
+namespace swbh {
+
+using namespace swb::wide;
+
+int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const std::vector<int32_t> &reads,
+                  int match, int mismatch, int gap, uint32_t flags, swb_result *res, int *launches, int *n_batches,
+                  double *ck_bytes, const std::function<cudaError_t(int)> &tic, const std::function<cudaError_t()> &toc)
+{
+    cudaStream_t st = ctx->stream;
+    const int64_t n_refs = rs->n_refs, n_reads = rd->n_reads;
+    // all (read, ref) pairs with a non-empty matrix, read-major
+    std::vector<int32_t> pr, pq;
+    for (int32_t q : reads)
+        for (int64_t r = 0; r < n_refs; ++r)
+            if (rs->len_orig[(size_t)r] > 0) { pr.push_back((int32_t)r); pq.push_back(q); }
+    const size_t total_pairs = pr.size();
+    auto pair_bytes = [&](size_t k) -> int64_t {
+        const int64_t n = rs->len_orig[(size_t)pr[k]], m = rd->len[(size_t)pq[k]];
+        const int64_t bands = (m + BH - 1) / BH, nb = std::max<int64_t>(1, (n + WL - 1 + WCB - 1) / WCB);
+        return bands * nb * ((KL + 1) * WL * 4 + WL * 4) + bands * (n + 1) * 4 + bands * 4;
+    };
+    size_t k0 = 0;
+    while (k0 < total_pairs) {
+        // ---- next batch: as many pairs as the workspace holds ---------------------------------
+        size_t k1 = k0;
+        int64_t bytes = 0;
+        while (k1 < total_pairs && k1 - k0 < (size_t)((1 << 21) - 1)) {
+            const int64_t b = pair_bytes(k1);
+            if (k1 > k0 && bytes + b > ctx->ws_bytes) break;
+            bytes += b; ++k1;
+        }
+        const int np = (int)(k1 - k0);
+        ++*n_batches;
+        *ck_bytes += (double)bytes;
+        std::vector<int64_t> band_off((size_t)np + 1), blk_off((size_t)np + 1), brow_off((size_t)np + 1);
+        std::vector<int2> items;
+        int64_t nbands = 0, nblk = 0, nbrow = 0;
+        int max_bands = 0, m_max = 0, n_max = 0;
+        for (int k = 0; k < np; ++k) {
+            const int64_t n = rs->len_orig[(size_t)pr[k0 + k]], m = rd->len[(size_t)pq[k0 + k]];
+            const int64_t bands = (m + BH - 1) / BH, nb = std::max<int64_t>(1, (n + WL - 1 + WCB - 1) / WCB);
+            band_off[(size_t)k] = nbands; blk_off[(size_t)k] = nblk; brow_off[(size_t)k] = nbrow;
+            nbands += bands; nblk += bands * nb; nbrow += bands * (n + 1);
+            max_bands = std::max<int>(max_bands, (int)bands);
+            m_max = std::max<int>(m_max, (int)m); n_max = std::max<int>(n_max, (int)n);
+        }
+        band_off[(size_t)np] = nbands; blk_off[(size_t)np] = nblk; brow_off[(size_t)np] = nbrow;
+        // tickets in (band, pair) order: a warp only ever waits for a lower ticket
+        items.reserve((size_t)nbands);
+        for (int b = 0; b < max_bands; ++b)
+            for (int k = 0; k < np; ++k)
+                if (b < band_off[(size_t)k + 1] - band_off[(size_t)k]) items.push_back(make_int2(k, b));
+
+        CU(ctx->w_pair_ref.reserve((size_t)np, st));
+        CU(ctx->w_pair_read.reserve((size_t)np, st));
+        CU(ctx->w_band_off.reserve((size_t)np + 1, st));
+        CU(ctx->w_blk_off.reserve((size_t)np + 1, st));
+        CU(ctx->w_brow_off.reserve((size_t)np + 1, st));
+        CU(ctx->w_items.reserve(items.size(), st));
+        CU(ctx->w_brow.reserve((size_t)nbrow, st));
+        CU(ctx->w_ck.reserve((size_t)nblk * (KL + 1) * WL, st));
+        CU(ctx->w_tmx.reserve((size_t)nblk * WL, st));
+        CU(ctx->w_prog.reserve((size_t)nbands, st));
+        CU(ctx->counters.reserve(8, st));
+        CU(cudaMemcpyAsync(ctx->w_pair_ref.p, pr.data() + k0, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->w_pair_read.p, pq.data() + k0, (size_t)np * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->w_band_off.p, band_off.data(), band_off.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->w_blk_off.p, blk_off.data(), blk_off.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->w_brow_off.p, brow_off.data(), brow_off.size() * 8, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(ctx->w_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+        CU(cudaMemsetAsync(ctx->w_prog.p, 0, (size_t)nbands * 4, st));
+
+        WideParams P;
+        P.n_pairs = np; P.pair_ref = ctx->w_pair_ref.p; P.pair_read = ctx->w_pair_read.p;
+        P.ref_codes = rs->codes8.p; P.ref_off = rs->off8.p; P.read_codes = rd->codes.p; P.read_off = rd->off.p;
+        P.match = match; P.mismatch = mismatch; P.gap = gap; P.n_reads = n_reads;
+        P.band_off = ctx->w_band_off.p; P.blk_off = ctx->w_blk_off.p; P.brow_off = ctx->w_brow_off.p;
+        P.brow = ctx->w_brow.p; P.ck = ctx->w_ck.p; P.tmx = ctx->w_tmx.p; P.prog = ctx->w_prog.p;
+        P.scores = res->d_scores.p;
+        uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_ticket = ctx->counters.p + 2;
+
+        CU(tic(1));
+        CU(launch_wide_fill(P, ctx->w_items.p, (int)items.size(), d_ticket, ctx->sm_count, st));
+        ++*launches;
+        CU(toc());
+        if (flags & SWB_F_SCORES_ONLY) { CU(cudaStreamSynchronize(st)); k0 = k1; continue; }
+
+        CU(tic(2));
+        uint32_t cap_tasks = (uint32_t)std::min<int64_t>((int64_t)np * 4 + 4096, (int64_t)1 << 30);
+        uint32_t cap_cells = cap_tasks;
+        uint32_t h_counts[2] = {0, 0};
+        for (int attempt = 0; attempt < 3; ++attempt) {
+            CU(ctx->w_tasks.reserve(cap_tasks, st));
+            CU(ctx->keys_tmp.reserve(cap_cells, st));
+            CU(cudaMemsetAsync(ctx->counters.p, 0, 8, st));
+            CU(launch_wide_flag(P, nblk, ctx->w_tasks.p, cap_tasks, d_ntasks, st));
+            CU(launch_wide_locate(P, ctx->w_tasks.p, d_ntasks, cap_tasks, ctx->keys_tmp.p, cap_cells, d_ncells,
+                                  ctx->sm_count, st));
+            *launches += 2;
+            CU(cudaMemcpyAsync(h_counts, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
+            CU(cudaStreamSynchronize(st));
+            if (h_counts[0] <= cap_tasks && h_counts[1] <= cap_cells) break;
+            if (attempt == 2) return fail(SWB_E_NOMEM, "swb_align: max-cell list did not fit after two retries");
+            cap_tasks = std::max(cap_tasks, h_counts[0]);
+            cap_cells = std::max(cap_cells, h_counts[1]);
+        }
+        const uint32_t n_cells = h_counts[1];
+        BatchOut bo;
+        bo.wide = true; bo.n_cells = n_cells;
+        bo.wide_pair_p.resize((size_t)np);
+        for (int k = 0; k < np; ++k) bo.wide_pair_p[(size_t)k] = (int64_t)pr[k0 + k] * n_reads + pq[k0 + k];
+        CU(bo.keys.alloc(n_cells, st));
+        const size_t tmp_bytes = sort_keys_tmp_bytes(n_cells);
+        CU(ctx->sort_tmp.reserve(tmp_bytes, st));
+        CU(sort_keys(ctx->keys_tmp.p, bo.keys.p, n_cells, ctx->sort_tmp.p, tmp_bytes, st));
+        *launches += 4;
+        CU(toc());
+
+        CU(tic(3));
+        // longest alignment of a positive-score path: m rows + the deletions its score can pay for
+        const int64_t big = std::max({match, mismatch, 0});
+        int64_t lmax = (int64_t)m_max + n_max;
+        if (gap < 0) lmax = std::min<int64_t>(lmax, (int64_t)m_max + (big * m_max) / (-(int64_t)gap) + 1);
+        bo.ops_stride = (lmax + 15) / 16 + 1;
+        CU(bo.beg.alloc(n_cells, st));
+        CU(bo.oplen.alloc(n_cells, st));
+        CU(bo.ops.alloc((size_t)n_cells * (size_t)bo.ops_stride, st));
+        CU(launch_wide_trace(P, bo.keys.p, n_cells, bo.beg.p, bo.oplen.p, bo.ops.p, bo.ops_stride, ctx->sm_count, st));
+        ++*launches;
+        CU(toc());
+        CU(cudaStreamSynchronize(st));      // the host tables of this batch are reused by the next one
+        res->stats[8] += n_cells;
+        res->batches.push_back(std::move(bo));
+        k0 = k1;
+    }
+    return SWB_OK;
+}
+
+}  // namespace swbh

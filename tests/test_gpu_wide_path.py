@@ -1,0 +1,74 @@
+"""GPU parity of the int32 wide path (swb_wide.cu): long reads / long pairs (bands coupled through
+HBM), scores outside the s16x2 domain (gap >= 0, non-negative mismatch, ...), alphabets with
+more than four symbols.  Bit-exact vs the oracle."""
+import random
+
+import pytest
+
+import oracle
+from tests.helpers import check_pairs
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rnd, n, alphabet="ACGT"):
+    return "".join(rnd.choice(alphabet) for _ in range(n))
+
+
+def _mutate(rnd, s, sub=0.05, indel=0.02):
+    out = []
+    for ch in s:
+        u = rnd.random()
+        if u < indel / 2:
+            continue
+        if u < indel:
+            out.append(rnd.choice("ACGT"))
+        out.append(rnd.choice("ACGT") if rnd.random() < sub else ch)
+    return "".join(out)
+
+
+def test_long_reads_multi_band(engine):
+    rnd = random.Random(21)
+    refs = [_rand(rnd, n) for n in (1, 31, 32, 33, 64, 65, 300, 1000, 2500)]
+    base = refs[-1]
+    reads = [_rand(rnd, m) for m in (257, 300, 511, 512, 513, 700)] + [_mutate(rnd, base[200:1100]), base[0:300]]
+    check_pairs(engine, refs, reads)
+
+
+@pytest.mark.parametrize("scores", [(5, -3, 0), (1, 0, 0), (2, 1, -1), (-1, -2, -3), (0, 0, 0), (1, -1, 1),
+                                    (9000, -3, -4), (5, -9000, -4)])
+def test_scores_outside_short_domain(engine, scores):
+    rnd = random.Random(31)
+    refs = [_rand(rnd, rnd.randint(5, 60)) for _ in range(4)] + ["ATATATAT", "AAAA"]
+    reads = [_rand(rnd, rnd.randint(3, 40)) for _ in range(4)] + ["ATAT", "CCCC", ""]
+    check_pairs(engine, refs, reads, scores, max_cells=400)
+
+
+def test_alphabet_larger_than_four(engine):
+    rnd = random.Random(41)
+    refs = [_rand(rnd, 200, "ACGTN"), _rand(rnd, 150, "ACGTNRYKM"), "acgtnNNNacgtRYKM", "ACGT-ACGT*ACGT"]
+    reads = [_rand(rnd, 40, "ACGTN"), "NNNN", "acgtn", "RYKM", "T-ACGT*A", _rand(rnd, 300, "ACGTNRY")]
+    check_pairs(engine, refs, reads)
+
+
+def test_mixed_short_and_long_reads_in_one_call(engine):
+    rnd = random.Random(51)
+    refs = [_rand(rnd, rnd.randint(100, 1500)) for _ in range(12)]
+    reads = [_rand(rnd, m) for m in (50, 150, 256, 257, 400, 100, 1000)]
+    reads.append(_mutate(rnd, refs[3][:600]))
+    check_pairs(engine, refs, reads)
+
+
+def test_long_pair_homologous(engine):
+    """cfg3 shape at reduced size: long homologous pair (90 % identity with indels) + a random pair."""
+    rnd = random.Random(61)
+    a = _rand(rnd, 6000)
+    b = _mutate(rnd, a, sub=0.07, indel=0.03)
+    c = _rand(rnd, 5000)
+    rs = engine.load_refset([a, c])
+    res = rs.align([b]).cache()
+    for r, ref in enumerate([a, c]):
+        exp = oracle.align(ref, b, lowmem=True)
+        got = res.pair(r, 0)
+        assert got[0] == exp.score and got[1] == exp.cells and got[2] == exp.sites
+    res.free(); rs.free()
