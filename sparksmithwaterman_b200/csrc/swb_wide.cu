@@ -70,9 +70,18 @@ __device__ __forceinline__ void load_rows(const WCtx &C, int band, int lane, int
 
 // One 32-step chunk of a band.  `tbuf` holds, in lane L, the top-boundary value of column
 // s0 + 1 + L (bottom row of the band above; 0 for band 0).  sink(u, top, H, valid, j).
+// Reference codes reach the lanes through registers, not per-step loads: lane L holds the code of
+// column s0 - 31 + L (cprev) and of column s0 + 1 + L (ccur); at step u lane t needs column
+// s0 + u - t + 1, i.e. ccur[u - t] if u >= t, else cprev[32 + u - t] -- one SEL + one SHFL.
+__device__ __forceinline__ int code_prefetch(const WCtx &C, int s0, int lane)
+{
+    const int j = s0 + 1 + lane;
+    return (j >= 1 && j <= C.n) ? (int)C.ref[j - 1] : 0x200;
+}
+
 template <class Sink>
-__device__ __forceinline__ void wide_chunk(const WCtx &C, int s0, int lane, int tbuf, const int (&rc)[KL],
-                                           int (&H)[KL], int &diag, Sink &&sink)
+__device__ __forceinline__ void wide_chunk(const WCtx &C, int s0, int lane, int tbuf, int cprev, int ccur,
+                                           const int (&rc)[KL], int (&H)[KL], int &diag, Sink &&sink)
 {
 #pragma unroll 1
     for (int u = 0; u < 32; ++u) {
@@ -80,10 +89,10 @@ __device__ __forceinline__ void wide_chunk(const WCtx &C, int s0, int lane, int 
         int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
         const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
         if (lane == 0) top = t0;
+        const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
         const int j = s - lane + 1;
         const bool valid = (j >= 1) && (j <= C.n);
         if (valid) {
-            const int c = C.ref[j - 1];
             int nw = diag, nn = top;
 #pragma unroll
             for (int r = 0; r < KL; ++r) {
@@ -145,7 +154,9 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
         const int32_t *prog_up = band > 0 ? P.prog + P.band_off[pair] + band - 1 : nullptr;
         int32_t *prog_me = P.prog + P.band_off[pair] + band;
         int seen = 0;                                             // columns of the band above known complete
+        int cprev = 0x200;
         for (int s0 = 0; s0 < nsteps; s0 += 32) {
+            const int ccur = code_prefetch(C, s0, lane);
             if (band > 0) {
                 const int need = min(C.n, s0 + 32);
                 if (seen < need) {
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                 }
             }
             const int tbuf = top_prefetch(C, band, s0, lane);
-            wide_chunk(C, s0, lane, tbuf, rc, H, diag,
+            wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
                        [&](int, int, const int (&Hc)[KL], bool valid, int j) {
                            if (!valid) return;
                            if (lane == WL - 1) my_brow[j] = Hc[KL - 1];
@@ -171,6 +182,7 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                                for (int r = 0; r < KL; ++r) if (rc[r] < 0x100) tmax = max(tmax, Hc[r]);
                            }
                        });
+            cprev = ccur;
             // publish: lane 31 has finished every column <= s0 + 1
             __threadfence();
             if (lane == WL - 1) *reinterpret_cast<volatile int32_t *>(prog_me) = min(C.n, max(0, s0 + 1));
@@ -245,10 +257,12 @@ __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, co
         load_wide_state(C, T.band, T.block, lane, H, diag);
         const int S = P.scores[(int64_t)P.pair_ref[T.pair] * P.n_reads + P.pair_read[T.pair]];
         const bool mine = (T.lane_mask >> lane) & 1u;
+        int cprev = code_prefetch(C, T.block * WCB - 32, lane);
         for (int u0 = 0; u0 < WCB; u0 += 32) {
             const int s0 = T.block * WCB + u0;
             const int tbuf = top_prefetch(C, T.band, s0, lane);
-            wide_chunk(C, s0, lane, tbuf, rc, H, diag,
+            const int ccur = code_prefetch(C, s0, lane);
+            wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
                        [&](int, int, const int (&Hc)[KL], bool valid, int j) {
                            if (!(valid && mine)) return;
 #pragma unroll
@@ -260,6 +274,7 @@ __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, co
                                }
                            }
                        });
+            cprev = ccur;
         }
     }
 }
@@ -298,16 +313,19 @@ __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, cons
 #pragma unroll
                 for (int r = 0; r < KL; ++r) col[r + 1] = H[r];
             }
+            int cprev = code_prefetch(C, blk * WCB - 32, lane);
             for (int u0 = 0; u0 < WCB; u0 += 32) {
                 const int s0 = blk * WCB + u0;
                 const int tbuf = top_prefetch(C, band, s0, lane);
-                wide_chunk(C, s0, lane, tbuf, rc, H, diag,
+                const int ccur = code_prefetch(C, s0, lane);
+                wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
                            [&](int u, int top, const int (&Hc)[KL], bool, int) {
                                int32_t *col = wtile + (u0 + u + 1) * CW + lane * (KL + 1);
                                col[0] = top;
 #pragma unroll
                                for (int r = 0; r < KL; ++r) col[r + 1] = Hc[r];
                            });
+                cprev = ccur;
             }
             __syncwarp();
             if (lane == 0) {
