@@ -70,6 +70,7 @@ void swb_destroy(swb_ctx *c)
     c->w_pair_read.release(); c->w_band_off.release(); c->w_blk_off.release(); c->w_brow_off.release();
     c->w_items.release(); c->w_tasks.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
+    for (auto &b : c->pin_free) cudaFreeHost(b.p);
     cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
@@ -446,6 +447,8 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                         h_read_slot_all[(size_t)h_rp[sl]] = (int32_t)sl;
                     }
                 bo.slot_read = h_rp;
+                CU(bo.d_slot_read.alloc(h_rp.size(), st));
+                CU(cudaMemcpyAsync(bo.d_slot_read.p, bo.slot_read.data(), h_rp.size() * 4, cudaMemcpyHostToDevice, st));
                 res->batches.push_back(std::move(bo));
             }
         }
@@ -459,26 +462,60 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
     CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, st));
     launches += 2;
-    DevBuf<int32_t> d_read_batch, d_read_slot_all;
-    DevBuf<const uint64_t *> d_bkeys;
-    DevBuf<uint32_t> d_bn;
-    std::vector<const uint64_t *> hk;
-    std::vector<uint32_t> hn;
-    if (!res->batches.empty() && n_reads > 0) {
-        for (auto &bo : res->batches) { hk.push_back(bo.keys.p); hn.push_back(bo.n_cells); }
-        CU(d_read_batch.alloc((size_t)n_reads, st));
-        CU(d_read_slot_all.alloc((size_t)n_reads, st));
-        CU(d_bkeys.alloc(hk.size(), st));
-        CU(d_bn.alloc(hn.size(), st));
-        CU(cudaMemcpyAsync(d_read_batch.p, h_read_batch.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_read_slot_all.p, h_read_slot_all.data(), (size_t)n_reads * 4, cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_bkeys.p, hk.data(), hk.size() * sizeof(void *), cudaMemcpyHostToDevice, st));
-        CU(cudaMemcpyAsync(d_bn.p, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice, st));
-        CU(launch_best_cells(res->d_best.p, n_reads, n_refs, d_read_batch.p, d_read_slot_all.p, d_bkeys.p, d_bn.p, st));
-        ++launches;
+    // ---- assemble the final, ABI-ordered result on the device (swb_assemble.cu) ----------------
+    if (!(flags & SWB_F_SCORES_ONLY)) {
+        std::vector<BatchDesc> descs;
+        uint64_t n_total = 0;
+        for (auto &bo : res->batches) {
+            BatchDesc d;
+            d.keys = bo.keys.p; d.beg = bo.beg.p; d.oplen = bo.oplen.p; d.ops = bo.ops.p;
+            d.slot_read = bo.d_slot_read.p; d.pair_map = bo.d_pair_map.p;
+            d.ops_stride = bo.ops_stride; d.base = (uint32_t)n_total; d.n_cells = bo.n_cells; d.wide = bo.wide ? 1 : 0;
+            if (bo.n_cells) descs.push_back(d);
+            n_total += bo.n_cells;
+        }
+        if (n_total >= ((uint64_t)1 << 31)) return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^31 max cells in one call");
+        const uint32_t N = (uint32_t)n_total;
+        res->total_cells = N;
+        CU(res->f_cell_off.alloc(n_pairs + 1, st));
+        CU(res->f_cells.alloc((size_t)N * 2, st));
+        CU(res->f_beg.alloc(N, st));
+        CU(res->f_len.alloc(N, st));
+        CU(res->f_ops_off.alloc((size_t)N + 1, st));
+        DevBuf<BatchDesc> d_desc;
+        DevBuf<uint64_t> d_pair_tmp, d_pair_sorted;
+        DevBuf<uint32_t> d_src_tmp, d_order;
+        DevBuf<int64_t> d_words;
+        DevBuf<uint8_t> d_tmp;
+        CU(d_desc.alloc(descs.size(), st));
+        CU(d_pair_tmp.alloc(N, st)); CU(d_pair_sorted.alloc(N, st));
+        CU(d_src_tmp.alloc(N, st)); CU(d_order.alloc(N, st));
+        CU(d_words.alloc((size_t)N + 1, st));
+        const size_t tmp_bytes = assemble_tmp_bytes(N);
+        CU(d_tmp.alloc(tmp_bytes, st));
+        if (!descs.empty()) CU(cudaMemcpyAsync(d_desc.p, descs.data(), descs.size() * sizeof(BatchDesc), cudaMemcpyHostToDevice, st));
+        int pair_bits = 1;
+        while (pair_bits < 64 && ((uint64_t)1 << pair_bits) < (uint64_t)std::max<size_t>(n_pairs, 1)) ++pair_bits;
+        CU(assemble_sort(d_desc.p, (int)descs.size(), N, n_refs, n_reads, d_pair_tmp.p, d_src_tmp.p, d_pair_sorted.p, d_order.p,
+                         d_tmp.p, tmp_bytes, pair_bits, st));
+        CU(cudaMemsetAsync(d_words.p + N, 0, 8, st));
+        CU(assemble_gather_cells(d_desc.p, (int)descs.size(), N, d_order.p, res->f_cells.p, res->f_beg.p, res->f_len.p,
+                                 d_words.p, res->f_ops_off.p, d_tmp.p, tmp_bytes, st));
+        int64_t total_words = 0;
+        CU(cudaMemcpyAsync(&total_words, res->f_ops_off.p + N, 8, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        res->total_words = total_words;
+        CU(res->f_ops.alloc((size_t)total_words, st));
+        CU(assemble_gather_ops(d_desc.p, (int)descs.size(), N, d_order.p, res->f_ops_off.p, res->f_ops.p, st));
+        CU(assemble_offsets(d_pair_sorted.p, N, (int64_t)n_pairs, res->f_cell_off.p, res->d_best.p, n_reads, res->f_cells.p, st));
+        launches += 8;
+        CU(toc());
+        CU(cudaStreamSynchronize(st));
+        res->batches.clear();                     // per-batch buffers go back to the pool
+    } else {
+        CU(toc());
+        CU(cudaStreamSynchronize(st));
     }
-    CU(toc());
-    CU(cudaStreamSynchronize(st));
     double t_phase[5] = {0, 0, 0, 0, 0};
     for (const Span &sp : spans) {
         float ms = 0;
@@ -536,83 +573,34 @@ int swb_result_fetch(swb_result *res)
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev[0], st));
     const size_t n_pairs = (size_t)(res->n_refs * res->n_reads);
-    res->scores.resize(n_pairs);
-    res->totals.resize((size_t)res->n_refs);
-    res->best.resize((size_t)res->n_reads * 4);
-    if (n_pairs) CU(cudaMemcpyAsync(res->scores.data(), res->d_scores.p, n_pairs * 4, cudaMemcpyDeviceToHost, st));
-    if (res->n_refs) CU(cudaMemcpyAsync(res->totals.data(), res->d_totals.p, (size_t)res->n_refs * 4, cudaMemcpyDeviceToHost, st));
-    if (res->n_reads) CU(cudaMemcpyAsync(res->best.data(), res->d_best.p, (size_t)res->n_reads * 16, cudaMemcpyDeviceToHost, st));
-    size_t total_cells = 0;
-    std::vector<std::vector<int32_t>> h_beg(res->batches.size()), h_len(res->batches.size());
-    for (size_t b = 0; b < res->batches.size(); ++b) {
-        BatchOut &bo = res->batches[b];
-        bo.h_keys.resize(bo.n_cells);
-        bo.h_ops.resize((size_t)bo.n_cells * bo.ops_stride);
-        h_beg[b].resize(bo.n_cells); h_len[b].resize(bo.n_cells);
-        if (bo.n_cells) {
-            CU(cudaMemcpyAsync(bo.h_keys.data(), bo.keys.p, (size_t)bo.n_cells * 8, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h_beg[b].data(), bo.beg.p, (size_t)bo.n_cells * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(h_len[b].data(), bo.oplen.p, (size_t)bo.n_cells * 4, cudaMemcpyDeviceToHost, st));
-            CU(cudaMemcpyAsync(bo.h_ops.data(), bo.ops.p, bo.h_ops.size() * 4, cudaMemcpyDeviceToHost, st));
-        }
-        total_cells += bo.n_cells;
+    const size_t N = res->total_cells;
+    const bool full = !(res->flags & SWB_F_SCORES_ONLY);
+    // one pinned buffer per array, recycled through the context
+    auto pull = [&](const void *dev, size_t bytes, const void **host) -> int {
+        swb_ctx::PinBuf b = ctx->pin_get(std::max<size_t>(bytes, 16));
+        if (!b.p) return fail(SWB_E_NOMEM, "swb_result_fetch: pinned host allocation failed");
+        res->pins.push_back(b);
+        *host = b.p;
+        if (bytes) CU(cudaMemcpyAsync(b.p, dev, bytes, cudaMemcpyDeviceToHost, st));
+        return SWB_OK;
+    };
+    int rc;
+    if ((rc = pull(res->d_scores.p, n_pairs * 4, (const void **)&res->scores))) return rc;
+    if ((rc = pull(res->d_totals.p, (size_t)res->n_refs * 4, (const void **)&res->totals))) return rc;
+    if ((rc = pull(res->d_best.p, (size_t)res->n_reads * 16, (const void **)&res->best))) return rc;
+    if (full) {
+        if ((rc = pull(res->f_cell_off.p, (n_pairs + 1) * 8, (const void **)&res->cell_off))) return rc;
+        if ((rc = pull(res->f_cells.p, N * 8, (const void **)&res->cells))) return rc;
+        if ((rc = pull(res->f_beg.p, N * 4, (const void **)&res->beginnings))) return rc;
+        if ((rc = pull(res->f_len.p, N * 4, (const void **)&res->op_lens))) return rc;
+        if ((rc = pull(res->f_ops_off.p, (N + 1) * 8, (const void **)&res->ops_off))) return rc;
+        if ((rc = pull(res->f_ops.p, (size_t)res->total_words * 4, (const void **)&res->ops))) return rc;
     }
     CU(cudaEventRecord(ctx->ev[1], st));
     CU(cudaStreamSynchronize(st));
     float ms = 0;
     cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
     res->stats[4] = ms;
-
-    // batches hold disjoint reads and are sorted (read slot, ref, i, j): counting-sort the cells
-    // into the ABI's pair order p = ref * n_reads + read; the (i, j) order inside a pair is kept
-    res->cells.resize(total_cells * 2);
-    res->beginnings.resize(total_cells);
-    res->op_lens.resize(total_cells);
-    res->cell_batch.resize(total_cells);
-    res->cell_local.resize(total_cells);
-    res->cell_off.assign(n_pairs + 1, 0);
-    const uint64_t nr = (uint64_t)std::max<int64_t>(res->n_refs, 1);
-    auto pair_of = [&](const BatchOut &bo, uint64_t key) -> size_t {
-        if (bo.wide) return (size_t)bo.wide_pair_p[(size_t)wide::wide_key_pair(key)];
-        const uint64_t pk = key_pair(key);
-        const uint64_t slot = pk / nr, ref = pk - slot * nr;
-        return (size_t)(ref * (uint64_t)res->n_reads + (uint64_t)bo.slot_read[(size_t)slot]);
-    };
-    for (const BatchOut &bo : res->batches)
-        for (uint32_t k = 0; k < bo.n_cells; ++k) res->cell_off[pair_of(bo, bo.h_keys[k]) + 1] += 1;
-    for (size_t p = 0; p < n_pairs; ++p) res->cell_off[p + 1] += res->cell_off[p];
-    {
-        std::vector<int64_t> cursor(res->cell_off.begin(), res->cell_off.end() - 1);
-        for (size_t b = 0; b < res->batches.size(); ++b) {
-            const BatchOut &bo = res->batches[b];
-            for (uint32_t k = 0; k < bo.n_cells; ++k) {
-                const uint64_t key = bo.h_keys[k];
-                const size_t c = (size_t)cursor[pair_of(bo, key)]++;
-                res->cells[2 * c] = (int32_t)(bo.wide ? wide::wide_key_i(key) : key_i(key));
-                res->cells[2 * c + 1] = (int32_t)(bo.wide ? wide::wide_key_j(key) : key_j(key));
-                res->beginnings[c] = h_beg[b][k];
-                res->op_lens[c] = h_len[b][k];
-                res->cell_batch[c] = (uint32_t)b; res->cell_local[c] = k;
-            }
-        }
-    }
-    // best-hit cells of reads that went through the wide path are filled here (the device kernel
-    // only knows the short path's key layout)
-    {
-        bool patched = false;
-        for (int64_t q = 0; q < res->n_reads; ++q) {
-            int32_t *b = res->best.data() + 4 * q;
-            if (b[0] > 0 && b[1] >= 0 && b[2] == 0) {
-                const size_t p = (size_t)b[1] * (size_t)res->n_reads + (size_t)q;
-                if (res->cell_off[p + 1] > res->cell_off[p]) {
-                    b[2] = res->cells[2 * (size_t)res->cell_off[p]];
-                    b[3] = res->cells[2 * (size_t)res->cell_off[p] + 1];
-                    patched = true;
-                }
-            }
-        }
-        if (patched) CU(cudaMemcpy(res->d_best.p, res->best.data(), (size_t)res->n_reads * 16, cudaMemcpyHostToDevice));
-    }
     res->fetched = true;
     return SWB_OK;
 }
@@ -621,19 +609,23 @@ void swb_result_free(swb_result *res)
 {
     if (!res) return;
     cudaSetDevice(res->ctx->device);
+    {
+        std::lock_guard<std::recursive_mutex> lk(res->ctx->mu);
+        for (auto &b : res->pins) res->ctx->pin_put(b);
+    }
     delete res;
 }
 
 int64_t swb_result_n_refs(const swb_result *r) { return r ? r->n_refs : 0; }
 int64_t swb_result_n_reads(const swb_result *r) { return r ? r->n_reads : 0; }
-const int32_t *swb_result_scores(const swb_result *r) { return (r && r->fetched) ? r->scores.data() : nullptr; }
-const int32_t *swb_result_ref_totals(const swb_result *r) { return (r && r->fetched) ? r->totals.data() : nullptr; }
-const int32_t *swb_result_best_hits(const swb_result *r) { return (r && r->fetched) ? r->best.data() : nullptr; }
-const int64_t *swb_result_cell_offsets(const swb_result *r) { return (r && r->fetched) ? r->cell_off.data() : nullptr; }
-int64_t swb_result_total_cells(const swb_result *r) { return (r && r->fetched) ? (int64_t)r->beginnings.size() : 0; }
-const int32_t *swb_result_cells(const swb_result *r) { return (r && r->fetched) ? r->cells.data() : nullptr; }
-const int32_t *swb_result_beginnings(const swb_result *r) { return (r && r->fetched) ? r->beginnings.data() : nullptr; }
-const int32_t *swb_result_op_lens(const swb_result *r) { return (r && r->fetched) ? r->op_lens.data() : nullptr; }
+const int32_t *swb_result_scores(const swb_result *r) { return (r && r->fetched) ? r->scores : nullptr; }
+const int32_t *swb_result_ref_totals(const swb_result *r) { return (r && r->fetched) ? r->totals : nullptr; }
+const int32_t *swb_result_best_hits(const swb_result *r) { return (r && r->fetched) ? r->best : nullptr; }
+const int64_t *swb_result_cell_offsets(const swb_result *r) { return (r && r->fetched) ? r->cell_off : nullptr; }
+int64_t swb_result_total_cells(const swb_result *r) { return r ? (int64_t)r->total_cells : 0; }
+const int32_t *swb_result_cells(const swb_result *r) { return (r && r->fetched) ? r->cells : nullptr; }
+const int32_t *swb_result_beginnings(const swb_result *r) { return (r && r->fetched) ? r->beginnings : nullptr; }
+const int32_t *swb_result_op_lens(const swb_result *r) { return (r && r->fetched) ? r->op_lens : nullptr; }
 
 int64_t swb_result_pair_cell_count(const swb_result *r, int64_t pair)
 {
@@ -671,11 +663,10 @@ int swb_result_pair_cell(const swb_result *r, int64_t pair, int64_t k, int32_t *
 int swb_result_ops(const swb_result *r, int64_t cell, uint8_t *outp, int64_t cap)
 {
     if (!r || !r->fetched || !outp) return fail(SWB_E_INVALID, "swb_result_ops: null / not fetched");
-    if (cell < 0 || cell >= (int64_t)r->beginnings.size()) return fail(SWB_E_RANGE, "swb_result_ops: bad cell");
+    if (cell < 0 || cell >= (int64_t)r->total_cells || !r->ops) return fail(SWB_E_RANGE, "swb_result_ops: bad cell");
     const int32_t len = r->op_lens[(size_t)cell];
     if (cap < len) return fail(SWB_E_RANGE, "swb_result_ops: buffer too small");
-    const BatchOut &bo = r->batches[r->cell_batch[(size_t)cell]];
-    const uint32_t *w = bo.h_ops.data() + (size_t)r->cell_local[(size_t)cell] * (size_t)bo.ops_stride;
+    const uint32_t *w = r->ops + r->ops_off[(size_t)cell];
     // the device stores the walk order (end -> start); hand out start -> end
     for (int32_t k = 0; k < len; ++k) {
         const int32_t src = len - 1 - k;
@@ -688,7 +679,7 @@ int swb_result_materialize(const swb_result *r, int64_t cell, const char *ref, i
                            int64_t read_len, char *ref_aln, char *read_aln, int64_t cap)
 {
     if (!r || !r->fetched || !ref_aln || !read_aln) return fail(SWB_E_INVALID, "swb_result_materialize: null / not fetched");
-    if (cell < 0 || cell >= (int64_t)r->beginnings.size()) return fail(SWB_E_RANGE, "swb_result_materialize: bad cell");
+    if (cell < 0 || cell >= (int64_t)r->total_cells || !r->ops) return fail(SWB_E_RANGE, "swb_result_materialize: bad cell");
     const int32_t len = r->op_lens[(size_t)cell];
     if (cap < (int64_t)len + 1) return fail(SWB_E_RANGE, "swb_result_materialize: buffer too small");
     std::vector<uint8_t> ops((size_t)len + 1);

@@ -75,6 +75,21 @@ struct swb_ctx {
     DevBuf<int64_t> w_band_off, w_blk_off, w_brow_off;
     DevBuf<int2> w_items;
     DevBuf<WideTask> w_tasks;
+    // pinned host buffers, recycled between results (cudaHostAlloc is slow; D2H into pageable memory too)
+    struct PinBuf { void *p = nullptr; size_t bytes = 0; };
+    std::vector<PinBuf> pin_free;
+    PinBuf pin_get(size_t bytes)
+    {
+        size_t best = pin_free.size();
+        for (size_t k = 0; k < pin_free.size(); ++k)
+            if (pin_free[k].bytes >= bytes && (best == pin_free.size() || pin_free[k].bytes < pin_free[best].bytes)) best = k;
+        if (best != pin_free.size()) { PinBuf b = pin_free[best]; pin_free.erase(pin_free.begin() + best); return b; }
+        PinBuf b;
+        b.bytes = std::max<size_t>(bytes + bytes / 4, 4096);
+        if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; b.bytes = 0; }
+        return b;
+    }
+    void pin_put(PinBuf b) { if (b.p) pin_free.push_back(b); }
     std::vector<cudaEvent_t> ev_pool;
     size_t ev_used = 0;
     cudaError_t next_event(cudaEvent_t *e)
@@ -124,9 +139,8 @@ struct BatchOut {
     DevBuf<int32_t> beg, oplen;
     DevBuf<uint32_t> ops;
     std::vector<int32_t> slot_read;              // read slot of this batch -> read index of the call
-    // host copies (after fetch)
-    std::vector<uint64_t> h_keys;
-    std::vector<uint32_t> h_ops;
+    DevBuf<int32_t> d_slot_read;                 // the same on the device, for the assembly
+    DevBuf<int64_t> d_pair_map;                  // wide path: local pair -> p, on the device
 };
 
 struct swb_result {
@@ -136,13 +150,19 @@ struct swb_result {
     bool fetched = false;
     std::vector<int32_t> ref_len, read_len;
     DevBuf<int32_t> d_scores, d_totals, d_best;
-    std::vector<BatchOut> batches;
-    // host
-    std::vector<int32_t> scores, totals, best;
-    std::vector<int64_t> cell_off;
-    std::vector<int32_t> cells, beginnings, op_lens;
-    std::vector<uint32_t> cell_batch;            // per global cell: batch index
-    std::vector<uint32_t> cell_local;            // per global cell: index inside the batch
+    std::vector<BatchOut> batches;               // released once the result is assembled
+    // assembled on the device (swb_assemble.cu), ABI order
+    uint32_t total_cells = 0;
+    int64_t total_words = 0;
+    DevBuf<int32_t> f_cells, f_beg, f_len;
+    DevBuf<int64_t> f_ops_off, f_cell_off;
+    DevBuf<uint32_t> f_ops;
+    // host views into pinned buffers (after fetch)
+    std::vector<swb_ctx::PinBuf> pins;
+    const int32_t *scores = nullptr, *totals = nullptr, *best = nullptr;
+    const int64_t *cell_off = nullptr, *ops_off = nullptr;
+    const int32_t *cells = nullptr, *beginnings = nullptr, *op_lens = nullptr;
+    const uint32_t *ops = nullptr;
     double stats[12] = {0};
 };
 

@@ -110,6 +110,28 @@ struct WideParams {
     int32_t *scores;
 };
 
+// one batch of max cells as the assembly kernels see it (swb_assemble.cu)
+struct BatchDesc {
+    const uint64_t *keys; const int32_t *beg; const int32_t *oplen; const uint32_t *ops;
+    const int32_t *slot_read;   // short path: read slot -> read index
+    const int64_t *pair_map;    // wide path: local pair -> ABI pair index
+    int64_t ops_stride;
+    uint32_t base;              // index of the batch's first cell in the concatenation
+    uint32_t n_cells;
+    int32_t wide;
+};
+size_t      assemble_tmp_bytes(uint32_t n_cells);
+cudaError_t assemble_sort(const BatchDesc *batches, int nb, uint32_t n_cells, int64_t n_refs, int64_t n_reads,
+                          uint64_t *pair_tmp, uint32_t *src_tmp, uint64_t *pair_sorted, uint32_t *order, void *tmp,
+                          size_t tmp_bytes, int pair_bits, cudaStream_t st);
+cudaError_t assemble_gather_cells(const BatchDesc *batches, int nb, uint32_t n_cells, const uint32_t *order, int32_t *cells,
+                                  int32_t *beginnings, int32_t *op_lens, int64_t *words, int64_t *ops_off, void *tmp,
+                                  size_t tmp_bytes, cudaStream_t st);
+cudaError_t assemble_gather_ops(const BatchDesc *batches, int nb, uint32_t n_cells, const uint32_t *order,
+                                const int64_t *ops_off, uint32_t *ops_out, cudaStream_t st);
+cudaError_t assemble_offsets(const uint64_t *pair_sorted, uint32_t n_cells, int64_t n_pairs, int64_t *cell_off,
+                             int32_t *best, int64_t n_reads, const int32_t *cells, cudaStream_t st);
+
 cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count,
                              cudaStream_t st);
 cudaError_t launch_wide_flag(const WideParams &P, int64_t total_blocks, WideTask *tasks, uint32_t cap, uint32_t *count,

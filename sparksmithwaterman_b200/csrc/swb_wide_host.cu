@@ -115,6 +115,8 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         bo.wide = true; bo.n_cells = n_cells;
         bo.wide_pair_p.resize((size_t)np);
         for (int k = 0; k < np; ++k) bo.wide_pair_p[(size_t)k] = (int64_t)pr[k0 + k] * n_reads + pq[k0 + k];
+        CU(bo.d_pair_map.alloc((size_t)np, st));
+        CU(cudaMemcpyAsync(bo.d_pair_map.p, bo.wide_pair_p.data(), (size_t)np * 8, cudaMemcpyHostToDevice, st));
         CU(bo.keys.alloc(n_cells, st));
         const size_t tmp_bytes = sort_keys_tmp_bytes(n_cells);
         CU(ctx->sort_tmp.reserve(tmp_bytes, st));
