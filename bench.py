@@ -122,7 +122,13 @@ def cpu_baseline_leg(refs, reads, threads, target_cells=2.0e10):
     ref_bases = sum(len(r) for r in sub_refs)
     n_reads = max(1, min(len(reads), int(target_cells / (ref_bases * READ_LEN))))
     r = oracle.cpu_baseline(sub_refs, reads[:n_reads], *SCORES, threads=threads, mode=1)
+    # the same sample, sliced like ParallelCollectionRDD (contiguous ref slices, one thread each)
+    r0 = oracle.cpu_baseline(sub_refs, reads[:max(1, n_reads // 4)], *SCORES, threads=threads, mode=0)
     return {"value": round(r["gcups"], 4), "unit": UNIT, "cores": threads, "kind": "port",
+            "spark_local_shaped_gcups": round(r0["gcups"], 4),
+            "spark_local_as_written_gcups": round(r0["gcups"] / 2.0, 4),
+            "spark_local_note": "contiguous ref slices, one thread per slice; 'as written' halves it because the un-cached "
+                                "map is evaluated again by lookup() after first() (Distribution.java:341-352)",
             "sample": f"{n_reads} x {READ_LEN} bp reads vs first {n_refs} refs of the workload "
                       f"({r['cells']:.3g} cells, {r['seconds']:.1f} s), dynamic ref queue over {threads} threads, "
                       "C restatement of SmithWaterman.java (no JVM in this image)",
@@ -319,12 +325,23 @@ def main():
     peak_gcups = sms * sm_max * 1e6 * 64 / 2 / 1e9
     fill_gcups = cells_per_step_local * K / 1e9 / (agg["fill_ms"] * 1e-3) if agg["fill_ms"] > 0 else 0.0
     run_clock = clocks.get("sm_mhz") or sm_max
+    # DRAM bytes of the fill kernel per launch, scaled from the committed ncu --set full capture
+    # (profiles/ncu_fill_trace_r01.json: 14.307 GB read+written for a 17-read-pair launch of this refset)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_fill_trace_r01.json")) as f:
+            cap = json.load(f)[0]
+        gb = float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])
+        rp_per_launch = (B / 2.0) / max(agg["batches"] / K, 1)
+        traffic = round(gb * 1e9 / 17.0 * rp_per_launch)
+    except Exception:
+        traffic = None
     roofline = {"bound": "int_dpx", "kernel": "fill_kernel<19>", "achieved": round(fill_gcups, 1),
                 "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4),
                 "peak_def": f"{sms} SMs x {sm_max:.0f} MHz ({peak_kind} sm_max_mhz) x 64 int lane-ops/clk/SM "
                             "(measured: profiles/dpx_microbench_r01.json) / 2 ops per s16x2 cell",
                 "frac_at_run_clock": round(fill_gcups / (peak_gcups * run_clock / sm_max), 4),
-                "traffic": None,
+                "traffic": traffic,
                 "hbm": {"algorithmic_bytes_per_launch": agg["checkpoint_bytes"] / max(agg["batches"], 1),
                         "achieved_gbs": round(agg["checkpoint_bytes"] / 1e9 / (agg["fill_ms"] * 1e-3), 1)
                         if agg["fill_ms"] > 0 else 0.0,
