@@ -102,3 +102,21 @@ def test_reductions_mirror_the_reference():
     sites = [(5, ["x", "1"]), (2, ["y", "2"]), (5, ["z", "3"]), (2, ["w", "4"])]
     assert [s[1][1] for s in distribution.match_site_sort(sites)] == ["2", "4", "1", "3"]     # stable
     assert distribution.wrap32(2**31 - 1 + 5) == -(2**31) + 4
+
+
+def test_file_formats_mirror_inoutops(tmp_path):
+    from sparksmithwaterman_b200 import inout
+    rp = tmp_path / "refs.fa"
+    rp.write_text(">gi|1|a\nACGT \nac gt\n>gi|2|b\n>gi|3|c\nTTTT\r\nGG\n")
+    refs = inout.get_ref_seqs(str(rp))
+    assert refs == [[">gi|1|a", "ACGT ac gt"], [">gi|2|b", ""], [">gi|3|c", "TTTTGG"]]      # lines not trimmed
+    ip = tmp_path / "reads.txt"
+    ip.write_text(">gi header\n  ACGT \n\nTT\t\n")
+    assert inout.get_reads(str(ip)) == ["ACGT", "", "TT"]                                    # trimmed, empty kept
+    ip.write_text("ACGT\nGG")
+    assert inout.get_reads(str(ip)) == ["ACGT", "GG"]                                        # first line is a read
+    with pytest.raises(ValueError):
+        bad = tmp_path / "bad.fa"; bad.write_text("ACGT\n>gi|1\nAC\n"); inout.get_ref_seqs(str(bad))
+    txt = inout.get_output_str(["ACGT"], (2, 1), 20, 7, [([">gi|1|a", "ACGT"], [(1, ["ACGT", "ACGT"])])])
+    assert txt == ("Execution Time = 7 ms\n\n# Reference Sequences = 2\n# Reads = 1\n\nInput:\nACGT\n\n"
+                   "Maximum alignment score = 20\nReference:\n>gi|1|a\nACGT\n\n\tIndex = 1\n\tACGT\n\tACGT\n\n")

@@ -74,3 +74,43 @@ def test_unsupported_inputs_are_loud(engine):
     with pytest.raises(SwbError):
         engine.load_refset(["AC\xffT"])
     rs.free()
+
+
+def test_reference_file_round_trip(engine, tmp_path):
+    """N2: reference-format files in, the reference's result text out (both reductions)."""
+    from sparksmithwaterman_b200 import inout
+    rnd = random.Random(13)
+    refs = [[f">gi|{k}|syn|", "".join(rnd.choice("ACGT") for _ in range(rnd.randint(60, 300)))] for k in range(5)]
+    reads = [refs[2][1][10:50], "".join(rnd.choice("ACGT") for _ in range(30)), refs[4][1][0:25]]
+    rp = tmp_path / "ref1.fa"
+    rp.write_text("".join(f"{m}\n{s[:40]}\n{s[40:]}\n" for m, s in refs))
+    ip = tmp_path / "in1.txt"
+    ip.write_text(">gi reads\n" + "\n".join(reads) + "\n")
+    assert inout.get_ref_seqs(str(rp)) == refs and inout.get_reads(str(ip)) == reads
+    mapped = []
+    for meta, seq in refs:
+        total, sites = sw_twin.map_ref(seq, reads)
+        mapped.append((total, ([meta, seq], [(b, [ra, qa]) for (b, ra, qa) in sites])))
+    for as_written, reduce in ((True, lambda m: distribution.DistributeReference.reduce([m])),
+                               (False, distribution.NoDistribution.reduce)):
+        txt = inout.run_reference_files([str(rp)], str(ip), engine=engine, as_written=as_written)
+        best, opt = reduce(mapped)
+        exp = inout.get_output_str(reads, (5, 3), best, 0, opt)
+        strip = lambda t: t.split("\n", 1)[1]                    # drop the execution-time line
+        assert strip(txt) == strip(exp)
+
+
+def test_engineer_data_sweep_points(engine):
+    """N4: a few points of the reference's own sweeps, bit-exact."""
+    from sparksmithwaterman_b200 import datasets
+    from tests.helpers import check_pairs
+    pts = [next(datasets.change_read_len()), next(datasets.change_ref_len())]
+    it = datasets.change_read_len()
+    for _ in range(12):
+        p = next(it)
+    pts.append(p)                                                # 240 bp reads
+    for sweep, x, refs, reads in pts:
+        check_pairs(engine, refs[:3], reads[:2])
+    assert [p[1] for p in datasets.change_ref_num()][:10] == [1, 10, 30, 50, 100, 500, 1000, 1500, 2000, 4000]
+    assert len(list(datasets.change_ref_num())) == 28 and len(list(datasets.change_ref_len())) == 36   # runTest3/4 loop counts
+    assert len(list(datasets.change_read_num())) == 33 and len(list(datasets.change_read_len())) == 25
