@@ -388,7 +388,10 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_work = ctx->counters.p + 2;
 
                 CU(tic(1));
-                CU(launch_fill(K, P, d_work, ctx->sm_count, st));
+                if (fill_bias_ok(match, mismatch, gap, (int64_t)std::max(match, 0) * std::min<int64_t>(m_max, rs->max_len)))
+                    CU(launch_fill_bias(K, P, d_work, ctx->sm_count, st));
+                else
+                    CU(launch_fill(K, P, d_work, ctx->sm_count, st));
                 ++launches;
                 CU(toc());
                 if (flags & SWB_F_SCORES_ONLY) {

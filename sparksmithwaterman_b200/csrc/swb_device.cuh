@@ -25,6 +25,13 @@ __device__ __forceinline__ uint32_t viaddmax_relu(uint32_t a, uint32_t b, uint32
     asm("{.reg .b32 t; add.s16x2 t, %1, %2; max.s16x2.relu %0, t, %3;}" : "=r"(r) : "r"(a), "r"(b), "r"(c));
     return r;
 }
+// per-halfword a + b                     -> VIADD.16x2
+__device__ __forceinline__ uint32_t viadd2(uint32_t a, uint32_t b)
+{
+    uint32_t r;
+    asm("add.s16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
 // per-halfword max(a, b)                -> VIMNMX.S16x2
 __device__ __forceinline__ uint32_t vmax2(uint32_t a, uint32_t b)
 {

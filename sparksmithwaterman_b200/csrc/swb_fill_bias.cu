@@ -1,0 +1,254 @@
+// swb_fill_bias.cu -- the fill kernel with the horizontal gap folded into a column bias.
+//
+// Same job, geometry, scheduling, outputs and checkpoint format as swb_fill.cu, but every register
+// holds  H''(i,j) = H(i,j) + |gap| * (j - jref)  instead of H.  With that bias
+//     W + gap      ->  W''                       (the bias of column j-1 plus |gap| IS the bias of column j)
+//     N + gap      ->  N'' + gap                 (same column)
+//     NW + s       ->  NW'' + (s + |gap|)        (non-negative addend)
+//     0            ->  floor_j = |gap| * (j - jref)
+// so the cell costs ONE packed add with a non-negative addend -- done as IMAD on the FMA pipe, which
+// runs beside the ALU/DPX pipe (profiles/dpx_microbench_r01.json: VIADDMNMX + IMAD = 3.4 warp-instr/
+// clk/SM vs 2.0 for the ALU pipe alone) -- plus two ALU ops:
+//     t   = IMAD(NW'', 1, s'')              FMA pipe; carry-free: both halves are non-negative and small
+//     pre = VIMNMX3(t, W'', floor_j)        ALU
+//     H'' = VIADDMNMX(N'', gap, pre)        ALU, the only op on the row-to-row dependency chain
+// i.e. 2.5 ALU ops per cell pair (with the half VIMNMX3 of the tile maximum) instead of 3.5.
+// jref advances by CB at every checkpoint block (all registers -= CB*|gap|), so the bias stays in
+// [|gap|, 24*|gap|]; tile maxima and checkpoints are stored UNBIASED, the traceback kernels are unchanged.
+// Domain (checked by the host, else swb_fill.cu runs): gap < 0, match + |gap| >= 0, mismatch + |gap| >= 0,
+// max score + 32*|gap| within s16.  Padding rows score s = gap on the diagonal (s'' = 0): every padded
+// cell is then an earlier cell minus |gap|, i.e. strictly below the true maximum, as before.
+// Recurrence: reference SmithWaterman.java:217-252 (GetCellScore.call), :277-280, :309-318.
+#include "swb_internal.h"
+#include "swb_device.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace swb {
+
+__device__ __forceinline__ uint32_t imad_add(uint32_t a, uint32_t one, uint32_t b)
+{
+    // a * 1 + b with `one` opaque to ptxas: stays an IMAD (FMA pipe) instead of becoming IADD3 (ALU pipe)
+    return a * one + b;
+}
+
+template <int K>
+__global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uint32_t *work_counter, uint32_t one)
+{
+    using G = Geo<K>;
+    extern __shared__ __align__(16) uint32_t prof_all[];        // per warp: [4 codes][GL lanes][KS], entries s + |gap|
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int t = lane & (GL - 1), g = lane >> 3;
+    uint32_t *prof = prof_all + warp * G::PROF_WORDS;
+    const int n_quads = (P.n_refs + 3) >> 2;
+    const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
+
+    const int ag = -P.gap;                                        // |gap| > 0
+    const uint32_t g2 = pack2(P.gap, P.gap);
+    const uint32_t gpos = pack2(ag, ag);
+    const uint32_t base_bias = pack2(ag * (8 - t), ag * (8 - t)); // bias of this lane's stored column at a block start
+    const uint32_t renorm = (uint32_t)(-(int32_t)(pack2(ag * CB, ag * CB)));   // 32-bit add of -(CB*|gap|) in both halves (no borrow: bias >= CB*|gap| there)
+    const uint32_t unbias = (uint32_t)(-(int32_t)base_bias);      // for 32-bit IMAD subtraction (no borrow across halves)
+    const uint32_t negbase = pack2(-ag * (8 - t), -ag * (8 - t)); // per-half negation, for the packed s16x2 ops
+    const int my_prof = t * G::KS;
+    int cur_rp = -1, ra = 0, rb = -1;
+
+    for (;;) {
+        uint32_t item = 0;
+        if (lane == 0) item = atomicAdd(work_counter, 1u);
+        item = __shfl_sync(0xffffffffu, item, 0);
+        if (item >= n_items) break;
+        const int q = (int)(item / (uint32_t)P.n_rp);
+        const int rp = (int)(item - (uint32_t)q * (uint32_t)P.n_rp);
+        if (rp != cur_rp) {
+            cur_rp = rp;
+            ra = P.rp_reads[2 * rp]; rb = P.rp_reads[2 * rp + 1];
+            const int64_t offa = P.read_off[ra];
+            const int ma = (int)(P.read_off[ra + 1] - offa);
+            const int64_t offb = rb >= 0 ? P.read_off[rb] : 0;
+            const int mb = rb >= 0 ? (int)(P.read_off[rb + 1] - offb) : 0;
+            __syncwarp();
+            for (int idx = lane; idx < GL * K; idx += 32) {
+                const int tt = idx / K, r = idx - tt * K;
+                const int row = tt * K + r;
+                const int qa = row < ma ? (int)P.read_codes[offa + row] : -1;
+                const int qb = row < mb ? (int)P.read_codes[offb + row] : -1;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const int lo = qa < 0 ? 0 : (qa == c ? P.match : P.mismatch) + ag;
+                    const int hi = qb < 0 ? 0 : (qb == c ? P.match : P.mismatch) + ag;
+                    prof[c * G::CSTRIDE + tt * G::KS + r] = pack2(lo, hi);
+                }
+            }
+            __syncwarp();
+        }
+
+        const int ref = 4 * q + g;
+        const bool has_ref = ref < P.n_refs;
+        const int n_g = has_ref ? P.ref_len[ref] : 0;
+        const int nmax = P.ref_len[4 * q];
+        const int nmin = (4 * q + 3 < P.n_refs) ? P.ref_len[4 * q + 3] : 0;
+        const uint32_t *wp = P.ref_words + (has_ref ? P.ref_word_off[ref] : 0);
+        const int64_t blk0 = (int64_t)rp * P.blocks_per_rp + (has_ref ? P.ref_blk_off[ref] : 0);
+        const int my_steps = has_ref ? n_g + GL - 1 : 0;
+
+        // all-zero matrix left of column 1, biased: every register = the floor of its column
+        uint32_t H[K];
+#pragma unroll
+        for (int r = 0; r < K; ++r) H[r] = base_bias;
+        uint32_t diag = base_bias, floorv = base_bias, negfloor = negbase;
+        uint32_t tmax = 0, gmax = 0, wprev = 0;
+
+        const int nsteps = nmax + GL - 1;
+        for (int s0 = 0; s0 < nsteps; s0 += 16) {
+            const uint32_t wnew = (s0 < n_g) ? __ldg(wp + (s0 >> 4)) : 0u;
+            const uint32_t win = __funnelshift_rc(wprev, wnew, 32 - 2 * t);
+            wprev = wnew;
+            const bool fast = (s0 >= GL - 1) && (s0 + 16 <= nmin);
+
+            if (fast) {
+#pragma unroll
+                for (int u = 0; u < 16; ++u) {
+                    floorv = imad_add(floorv, one, gpos);                  // floor of the new column
+                    negfloor = viadd2(negfloor, g2);                        // its negative (packed)
+                    uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
+                    if (t == 0) top = floorv;                               // row 0 is all zero
+                    const uint32_t c = (win >> (2 * u)) & 3u;
+                    uint32_t sv[G::KP];
+                    load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
+                    uint32_t nw = diag, nn = top;
+#pragma unroll
+                    for (int r = 0; r < K; ++r) {
+                        const uint32_t tt = imad_add(nw, one, sv[r]);       // NW'' + s''          (FMA pipe)
+                        const uint32_t pre = vmax3(tt, H[r], floorv);       // max(t, W'', floor)  (ALU)
+                        nw = H[r];
+                        H[r] = viaddmax(nn, g2, pre);                       // max(N'' + gap, pre) (ALU)
+                        nn = H[r];
+                    }
+                    diag = top;
+                    tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
+                }
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < 16; ++u) {
+                    const int s = s0 + u;
+                    floorv = imad_add(floorv, one, gpos);
+                    negfloor = viadd2(negfloor, g2);
+                    uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
+                    if (t == 0) top = floorv;
+                    const uint32_t c = (win >> (2 * u)) & 3u;
+                    const bool valid = (s >= t) && (s < n_g + t);
+                    if (valid) {
+                        uint32_t sv[G::KP];
+                        load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
+                        uint32_t nw = diag, nn = top;
+#pragma unroll
+                        for (int r = 0; r < K; ++r) {
+                            const uint32_t tt = imad_add(nw, one, sv[r]);
+                            const uint32_t pre = vmax3(tt, H[r], floorv);
+                            nw = H[r];
+                            H[r] = viaddmax(nn, g2, pre);
+                            nn = H[r];
+                        }
+                        tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);
+                    } else {
+                        // outside the matrix: the column is all zero (left of it) or never read (right of it)
+#pragma unroll
+                        for (int r = 0; r < K; ++r) H[r] = floorv;
+                    }
+                    diag = top;
+                }
+            }
+
+            // ---- block boundary: move jref by CB columns, then (un-biased) tile max + checkpoint ----
+            const int s_next = s0 + 16;
+            if ((s_next % CB) == 0) {
+#pragma unroll
+                for (int r = 0; r < K; ++r) H[r] = imad_add(H[r], one, renorm);
+                diag = imad_add(diag, one, renorm);
+                floorv = base_bias;
+                negfloor = negbase;
+                const int b = s_next / CB;
+                if (s_next - CB < my_steps) {
+                    P.tmx[(blk0 + b - 1) * GL + t] = tmax;
+                    gmax = vmax2(gmax, tmax);
+                    tmax = 0;
+                }
+                if (s_next < my_steps) {
+                    uint32_t U[K];
+#pragma unroll
+                    for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
+                    uint32_t *ck = P.ck + (blk0 + b) * (int64_t)(G::KW * GL) + t * 4;
+                    store_checkpoint<K>(ck, U, imad_add(diag, one, unbias));
+                }
+            }
+        }
+        {
+            const int s_end = ((nsteps + 15) >> 4) << 4;
+            if ((s_end % CB) != 0) {
+                const int b_last = s_end / CB;
+                if (b_last * CB < my_steps) {
+                    P.tmx[(blk0 + b_last) * GL + t] = tmax;
+                    gmax = vmax2(gmax, tmax);
+                }
+            }
+        }
+        gmax = vmax2(gmax, __shfl_xor_sync(0xffffffffu, gmax, 1));
+        gmax = vmax2(gmax, __shfl_xor_sync(0xffffffffu, gmax, 2));
+        gmax = vmax2(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
+        if (t == 0 && has_ref) {
+            const int64_t ro = P.ref_orig[ref];
+            P.scores[ro * P.n_reads + ra] = (int)(int16_t)(gmax & 0xffffu);
+            if (rb >= 0) P.scores[ro * P.n_reads + rb] = (int)(int16_t)(gmax >> 16);
+        }
+    }
+}
+
+template <int K>
+static cudaError_t launch_fill_bias_k(const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st)
+{
+    using G = Geo<K>;
+    const int n_quads = (P.n_refs + 3) / 4;
+    static const int env_warps = getenv("SWB_FILL_WARPS") ? atoi(getenv("SWB_FILL_WARPS")) : 0;
+    const int warps = env_warps > 0 ? env_warps : 12;
+    const int64_t items = (int64_t)n_quads * P.n_rp;
+    const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count);   // one CTA per SM
+    const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
+    cudaError_t e = cudaSuccess;
+    if (smem > 48 * 1024) {
+        e = cudaFuncSetAttribute(fill_bias_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
+    e = cudaMemsetAsync(work_counter, 0, sizeof(uint32_t), st);
+    if (e != cudaSuccess) return e;
+    fill_bias_kernel<K><<<dim3((unsigned)ctas), dim3(warps * 32), smem, st>>>(P, work_counter, 1u);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fill_bias(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st)
+{
+    switch (K) {
+        case 4:  return launch_fill_bias_k<4>(P, work_counter, sm_count, st);
+        case 8:  return launch_fill_bias_k<8>(P, work_counter, sm_count, st);
+        case 13: return launch_fill_bias_k<13>(P, work_counter, sm_count, st);
+        case 16: return launch_fill_bias_k<16>(P, work_counter, sm_count, st);
+        case 19: return launch_fill_bias_k<19>(P, work_counter, sm_count, st);
+        case 25: return launch_fill_bias_k<25>(P, work_counter, sm_count, st);
+        case 32: return launch_fill_bias_k<32>(P, work_counter, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// host-side domain check of the biased kernel
+bool fill_bias_ok(int match, int mismatch, int gap, int64_t max_score)
+{
+    if (gap >= 0) return false;
+    const int ag = -gap;
+    static const bool disabled = getenv("SWB_NO_BIAS_FILL") != nullptr;
+    return !disabled && match + ag >= 0 && mismatch + ag >= 0 && match + ag <= 4000 &&
+           max_score + 32LL * ag <= 30000;
+}
+
+}  // namespace swb

@@ -143,6 +143,9 @@ cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_
 
 // swb_fill.cu
 cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st);
+// swb_fill_bias.cu: same contract, horizontal gap folded into a column bias (2.5 instead of 3.5 ALU ops / cell pair)
+cudaError_t launch_fill_bias(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st);
+bool fill_bias_ok(int match, int mismatch, int gap, int64_t max_score);
 // swb_trace.cu
 cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, cudaStream_t st);
 cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
