@@ -224,23 +224,37 @@ template <int K> struct TraceGeo {
     // lanes of a half's tile: a walk of CB steps climbs at most CB rows (plus rare insertion runs,
     // which simply end the block early), i.e. ceil(CB / K) lanes above the current one
     static constexpr int NLW = ((CB + K - 1) / K + 1) < GL ? ((CB + K - 1) / K + 1) : GL;
+    static constexpr int KH = ((Geo<K>::KW / 2 + 1 + 3) / 4) * 4;      // + 1: a spare halfword pair for the column code
 };
 
-// one tile column (KW words) of this lane into the windows it belongs to (either may be null)
-template <int KW>
-__device__ __forceinline__ void store_column(uint32_t *ta, uint32_t *tb, int c, const uint32_t (&v)[KW])
+// One tile column of this lane into the windows it belongs to (either may be null).  Each half's
+// tile keeps only ITS s16 half of the KW packed values: KW/2 words, padded to KH for STS.128.
+template <int KW, int KH>
+__device__ __forceinline__ void store_column(uint32_t *ta, uint32_t *tb, int c, const uint32_t (&v)[KW], uint32_t codes)
 {
+    static_assert(2 * KH > KW, "need a spare halfword per column for the reference code");
+    // codes = (code of half 0's column) | (code of half 1's column) << 16, kept in halfword KW of the column
     if (ta) {
-        uint4 *col = reinterpret_cast<uint4 *>(ta + c * KW);
+        uint32_t w[KH];
 #pragma unroll
-        for (int q = 0; q < KW / 4; ++q) col[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < KH; ++q) w[q] = (2 * q + 1 < KW) ? __byte_perm(v[2 * q], v[(2 * q + 1 < KW) ? 2 * q + 1 : 0], 0x5410)
+                                                             : (2 * q == KW ? (codes & 0xffffu) : 0u);
+        uint4 *col = reinterpret_cast<uint4 *>(ta + c * KH);
+#pragma unroll
+        for (int q = 0; q < KH / 4; ++q) col[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
     if (tb) {
-        uint4 *col = reinterpret_cast<uint4 *>(tb + c * KW);
+        uint32_t w[KH];
 #pragma unroll
-        for (int q = 0; q < KW / 4; ++q) col[q] = make_uint4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        for (int q = 0; q < KH; ++q) w[q] = (2 * q + 1 < KW) ? __byte_perm(v[2 * q], v[(2 * q + 1 < KW) ? 2 * q + 1 : 0], 0x7632)
+                                                             : (2 * q == KW ? (codes >> 16) : 0u);
+        uint4 *col = reinterpret_cast<uint4 *>(tb + c * KH);
+#pragma unroll
+        for (int q = 0; q < KH / 4; ++q) col[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
     }
 }
+
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------------
 // Traceback, packed: one 8-lane group walks TWO max cells at once, one per s16 half.
@@ -265,7 +279,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
     using G = Geo<K>;
     constexpr int KW = G::KW;
     constexpr int NLW = TraceGeo<K>::NLW;                           // lanes kept per half: a CB-step walk climbs <= CB rows
-    constexpr int HALF_WORDS = NLW * (CB + 1) * KW;
+    constexpr int KH = TraceGeo<K>::KH;                             // words per tile column: KW s16 values of ONE half
+    constexpr int HALF_WORDS = NLW * (CB + 1) * KH;
     constexpr int TILE_WORDS = 2 * HALF_WORDS;
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t seg_next;
@@ -273,6 +288,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
     const int lane = threadIdx.x & 31, t = lane & (GL - 1), g = lane >> 3, warp = threadIdx.x >> 5;
     const unsigned gmask = 0xffu << (8 * g);
     uint32_t *tile = smem + 25 * G::CSTRIDE + (size_t)(warp * 4 + g) * TILE_WORDS;
+    uint8_t *rcodes_s = reinterpret_cast<uint8_t *>(smem + 25 * G::CSTRIDE + (size_t)(blockDim.x >> 3) * TILE_WORDS);   // [GL*K]
     const uint32_t g2 = pack2(P.gap, P.gap);
     const uint32_t c_lo = blockIdx.x * (uint32_t)chunk;
     const uint32_t c_hi = min(n_cells, c_lo + (uint32_t)chunk);
@@ -305,6 +321,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
             }
             prof2[cc * G::CSTRIDE + tt * G::KS + r] = pack2(lo, hi);
         }
+        for (int idx = threadIdx.x; idx < GL * K; idx += blockDim.x)
+            rcodes_s[idx] = idx < m ? P.read_codes[roff + idx] : (uint8_t)0xFE;
         if (threadIdx.x == 0) seg_next = seg_lo;
         __syncthreads();
 
@@ -349,8 +367,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
             const int tca = (ci0 - 1) / K, tcb = (ci1 - 1) / K;
             const int sa = busy0 ? t - (tca - NLW + 1) : -1;          // this lane's slot in half 0's tile, if any
             const int sb = busy1 ? t - (tcb - NLW + 1) : -1;
-            uint32_t *tileA = (sa >= 0 && sa < NLW) ? tile + (size_t)sa * (CB + 1) * KW : nullptr;
-            uint32_t *tileB = (sb >= 0 && sb < NLW) ? tile + HALF_WORDS + (size_t)sb * (CB + 1) * KW : nullptr;
+            uint32_t *tileA = (sa >= 0 && sa < NLW) ? tile + (size_t)sa * (CB + 1) * KH : nullptr;
+            uint32_t *tileB = (sb >= 0 && sb < NLW) ? tile + HALF_WORDS + (size_t)sb * (CB + 1) * KH : nullptr;
             uint32_t H[K], diag = 0;
             {
                 const uint4 *ckA = reinterpret_cast<const uint4 *>(P.ck + (bk0 + b0) * (int64_t)(KW * GL)) + t;
@@ -371,6 +389,11 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                         else if (w == K) diag = v[e];
                     }
                 }
+            }
+            // the path almost always continues into the block to the left: pull its checkpoints towards L2
+            if (t < KW / 4) {
+                if (busy0 && b0 > 1) prefetch_l2(P.ck + (bk0 + b0 - 1) * (int64_t)(KW * GL) + t * (GL * 4));
+                if (busy1 && b1 > 1) prefetch_l2(P.ck + (bk1 + b1 - 1) * (int64_t)(KW * GL) + t * (GL * 4));
             }
             // reference-code windows of this lane for the block: 0-based columns j0 .. j0+15
             uint32_t win0, win1; int ulo0, uhi0, ulo1, uhi1;
@@ -395,7 +418,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 for (int r = 0; r < K; ++r) v[r + 1] = H[r];
 #pragma unroll
                 for (int r = K + 1; r < KW; ++r) v[r] = 0;
-                store_column<KW>(tileA, tileB, 0, v);
+                store_column<KW, KH>(tileA, tileB, 0, v, 0x00040004u);
             }
 #pragma unroll 2
             for (int u = 0; u < CB; ++u) {
@@ -421,7 +444,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 for (int r = 0; r < K; ++r) v[r + 1] = H[r];
 #pragma unroll
                 for (int r = K + 1; r < KW; ++r) v[r] = 0;
-                store_column<KW>(tileA, tileB, u + 1, v);
+                store_column<KW, KH>(tileA, tileB, u + 1, v, (uint32_t)ca | ((uint32_t)cb << 16));
             }
             __syncwarp();
 
@@ -432,23 +455,20 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 int ci = h ? ci1 : ci0, cj = h ? cj1 : cj0;
                 const int b = h ? b1 : b0;
                 const int lane_lo = (h ? tcb : tca) - NLW + 1;              // first lane held in this half's tile
-                const uint32_t *rw = h ? rw1 : rw0;
                 const uint32_t *th = tile + h * HALF_WORDS;
                 uint32_t *myops = ops + (size_t)w_cell * ops_stride;
-                const uint8_t *rcodes = P.read_codes + roff;
                 while (w_h > 0) {
                     const int tc = (ci - 1) / K;
                     const int r = ci - tc * K;                              // 1..K
                     const int c = cj - (b * CB - tc);                       // column index in lane tc's tile
                     const int sl = tc - lane_lo;
                     if (c < 1 || c > CB || sl < 0) break;                   // outside what this block holds
-                    const uint32_t *lt = th + ((size_t)sl * (CB + 1) + c) * KW + r;
-                    const int hw = half_of(lt[-KW], h);                     // W
-                    const int hn = half_of(lt[-1], h);                      // N
-                    const int hnw = half_of(lt[-KW - 1], h);                // NW
-                    const int col = cj - 1;
-                    const int rc = (int)((__ldg(rw + (col >> 4)) >> (2 * (col & 15))) & 3u);
-                    const int sc = ((int)rcodes[ci - 1] == rc) ? P.match : P.mismatch;
+                    const int16_t *lt = reinterpret_cast<const int16_t *>(th + ((size_t)sl * (CB + 1) + c) * KH) + r;
+                    const int hw = lt[-2 * KH];                             // W  = (c-1, r)
+                    const int hn = lt[-1];                                  // N  = (c, r-1)
+                    const int hnw = lt[-2 * KH - 1];                        // NW = (c-1, r-1)
+                    const int rc = lt[KW - r];                              // reference code of this column (halfword KW)
+                    const int sc = ((int)rcodes_s[ci - 1] == rc) ? P.match : P.mismatch;
                     // type of a positive cell = first of (alignment, insertion, deletion) whose candidate
                     // equals H: the ">=" cascade of GetCellScore.call.  Branch-free: both walkers of a
                     // warp's groups stay converged.
@@ -490,11 +510,11 @@ static cudaError_t launch_trace_k(const BatchParams &P, const uint64_t *keys, ui
 {
     using G = Geo<K>;
     if (n_cells == 0) return cudaSuccess;
-    const size_t per_group = (size_t)2 * TraceGeo<K>::NLW * (CB + 1) * G::KW * sizeof(uint32_t);
+    const size_t per_group = (size_t)2 * TraceGeo<K>::NLW * (CB + 1) * TraceGeo<K>::KH * sizeof(uint32_t);
     const size_t prof_bytes = (size_t)25 * G::CSTRIDE * sizeof(uint32_t);
     int warps = 4;
-    while (warps > 1 && prof_bytes + per_group * 4 * warps > 110 * 1024) --warps;   // two CTAs per SM
-    const size_t smem = prof_bytes + per_group * 4 * warps;
+    while (warps > 1 && prof_bytes + per_group * 4 * warps + 512 > 74 * 1024) --warps;   // three CTAs per SM
+    const size_t smem = prof_bytes + per_group * 4 * warps + (((size_t)GL * K + 15) / 16) * 16;
     static bool attr_set[64] = {false};
     if (!attr_set[K]) {
         cudaError_t e = cudaFuncSetAttribute(trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
