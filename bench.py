@@ -146,13 +146,13 @@ def run_reference(args):
     oracle.build()
     threads = os.cpu_count() or 1
     refs = synth.make_refs(1000)
-    reads = synth.make_reads(max(8, args.reads_per_step // 16) * (args.steps + args.warmup), READ_LEN, refs)
-    per = max(1, len(reads) // (args.steps + args.warmup))
-    # size one step to ~5 s
     ref_bases = sum(len(r) for r in refs)
-    probe = oracle.cpu_baseline(refs[:200], reads[:2], *SCORES, threads=threads, mode=1)
+    pool = synth.make_reads(64 * (args.steps + 1), READ_LEN, refs)
+    # size one step to ~8 s of host time from a 2-read probe over the same references
+    probe = oracle.cpu_baseline(refs, pool[:2], *SCORES, threads=threads, mode=1)
     rate = probe["cells"] / probe["seconds"]
-    per = max(1, min(per, int(5.0 * rate / (ref_bases * READ_LEN))))
+    per = max(1, min(64, int(8.0 * rate / (ref_bases * READ_LEN))))
+    reads = pool[2:]
     for w in range(args.warmup):
         oracle.cpu_baseline(refs[:100], reads[:1], *SCORES, threads=threads, mode=1)
     t0 = time.perf_counter()

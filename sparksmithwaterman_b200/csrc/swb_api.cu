@@ -66,6 +66,7 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
     c->tasks.release(); c->keys_tmp.release(); c->sort_tmp.release();
+    c->v_ref.release(); c->v_c0.release(); c->v_len.release(); c->v_skip.release(); c->v_end.release();
     c->w_brow.release(); c->w_ck.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
     c->w_pair_read.release(); c->w_band_off.release(); c->w_blk_off.release(); c->w_brow_off.release();
     c->w_items.release(); c->w_tasks.release();
@@ -150,6 +151,7 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         blocks += (n + GL - 1 + CB - 1) / CB > 0 ? (n + GL - 1 + CB - 1) / CB : 1;
     }
     blk_off[(size_t)n_refs] = blocks;
+    rs->len_sorted = len_sorted;
     rs->blocks_per_rp = blocks;
     if (words_total >= ((uint64_t)1 << 32)) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference set too large");
     std::vector<uint32_t> words((size_t)words_total + 1, 0u);
@@ -256,6 +258,45 @@ void swb_reads_free(swb_reads *rd)
 }
 int64_t swb_reads_count(const swb_reads *rd) { return rd ? rd->n_reads : 0; }
 
+// Work units of the fill: every reference is one segment unless it is very long.  A long reference
+// is cut into windows of SEG columns, each started W_al columns early from an all-zero boundary.
+// H(i,j) only depends on the columns (j - W, j], W = m + floor(max(match,mismatch,0)*m/|gap|) + 1 (a
+// positive-score path over i <= m rows can pay for at most that many deletions), so every cell
+// further than W from the window's left edge is exact; the segment OWNS (writes tile maxima and
+// checkpoints for) exactly the blocks of its own SEG columns.  This bounds the longest item (tail of
+// the persistent fill) and gives a single long reference enough items to fill the machine.
+namespace {
+struct Segments { std::vector<int32_t> ref, c0, len, skip, end; };
+void make_segments(const swb_refset *rs, int K, int match, int mismatch, int gap, int64_t n_rp, int sm_count, Segments &S)
+{
+    const int64_t m = (int64_t)GL * K;
+    const int64_t big = std::max({match, mismatch, 0});
+    const int64_t W = m + (big * m) / (-(int64_t)gap) + 1;
+    const int64_t W_al = ((W + 8 + 15) / 16) * 16;
+    int64_t SEG = 8192;
+    if (n_rp * ((rs->n_refs + 3) / 4) < (int64_t)sm_count * 24) SEG = 1024;     // few items: favour parallelism
+    SEG = std::max<int64_t>(SEG, ((2 * W_al + 15) / 16) * 16);
+    const int32_t BIG = 1 << 26;
+    struct One { int32_t ref, c0, len, skip, end; };
+    std::vector<One> v;
+    v.reserve((size_t)rs->n_refs + 64);
+    for (int64_t s = 0; s < rs->n_refs; ++s) {
+        const int64_t n = rs->len_sorted[(size_t)s];
+        if (n <= 2 * SEG) { v.push_back(One{(int32_t)s, 0, (int32_t)n, 0, BIG}); continue; }
+        const int64_t nseg = (n + SEG - 1) / SEG;
+        for (int64_t k = 0; k < nseg; ++k) {
+            const int64_t lo = k * SEG, hi = std::min<int64_t>(n, (k + 1) * SEG);
+            const int64_t c0 = std::max<int64_t>(0, lo - W_al);
+            v.push_back(One{(int32_t)s, (int32_t)c0, (int32_t)(hi - c0), (int32_t)((lo - c0) / CB),
+                            k == nseg - 1 ? BIG : (int32_t)((hi - c0) / CB)});
+        }
+    }
+    std::stable_sort(v.begin(), v.end(), [](const One &a, const One &b) { return a.len > b.len; });
+    S.ref.clear(); S.c0.clear(); S.len.clear(); S.skip.clear(); S.end.clear();
+    for (const One &o : v) { S.ref.push_back(o.ref); S.c0.push_back(o.c0); S.len.push_back(o.len); S.skip.push_back(o.skip); S.end.push_back(o.end); }
+}
+}  // namespace
+
 static int pick_k(int m)
 {
     for (int k = 0; k < kNumK; ++k)
@@ -346,6 +387,17 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
             std::stable_sort(idx.begin(), idx.end(),
                              [&](int32_t a, int32_t b) { return rd->len[(size_t)a] > rd->len[(size_t)b]; });
             const int64_t n_rp_total = ((int64_t)idx.size() + 1) / 2;
+            Segments segs;
+            make_segments(rs, K, match, mismatch, gap, n_rp_total, ctx->sm_count, segs);
+            const size_t nv = segs.ref.size();
+            CU(ctx->v_ref.reserve(nv, st)); CU(ctx->v_c0.reserve(nv, st)); CU(ctx->v_len.reserve(nv, st));
+            CU(ctx->v_skip.reserve(nv, st)); CU(ctx->v_end.reserve(nv, st));
+            CU(cudaMemcpyAsync(ctx->v_ref.p, segs.ref.data(), nv * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->v_c0.p, segs.c0.data(), nv * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->v_len.p, segs.len.data(), nv * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->v_skip.p, segs.skip.data(), nv * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaMemcpyAsync(ctx->v_end.p, segs.end.data(), nv * 4, cudaMemcpyHostToDevice, st));
+            CU(cudaStreamSynchronize(st));         // segs is a local
             const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)KW * GL * 4 + GL * 4);
             int64_t rp_per_batch = std::max<int64_t>(1, ctx->ws_bytes / std::max<int64_t>(bytes_per_rp, 1));
             rp_per_batch = std::min<int64_t>(rp_per_batch, 1 << 16);
@@ -381,6 +433,8 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 P.ref_words = rs->words.p; P.ref_word_off = rs->word_off.p; P.ref_len = rs->len.p;
                 P.ref_orig = rs->orig.p; P.ref_sorted_of = rs->sorted_of.p; P.ref_blk_off = rs->blk_off.p;
                 P.n_refs = (int32_t)n_refs; P.blocks_per_rp = rs->blocks_per_rp;
+                P.v_ref = ctx->v_ref.p; P.v_c0 = ctx->v_c0.p; P.v_len = ctx->v_len.p; P.v_skip = ctx->v_skip.p;
+                P.v_end = ctx->v_end.p; P.n_vrefs = (int32_t)nv;
                 P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = ctx->rp.p; P.read_slot = ctx->slot.p;
                 P.n_rp = n_rp; P.n_reads = n_reads;
                 P.match = match; P.mismatch = mismatch; P.gap = gap;

@@ -30,7 +30,7 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
     uint32_t *prof = prof_all + warp * G::PROF_WORDS;
-    const int n_quads = (P.n_refs + 3) >> 2;
+    const int n_quads = (P.n_vrefs + 3) >> 2;
     const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
     const uint32_t g2 = pack2(P.gap, P.gap);
@@ -72,14 +72,22 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
             }
             __syncwarp();
         }
-        const int ref = 4 * q + g;                                // sorted reference index of this group
-        const bool has_ref = ref < P.n_refs;
-        const int n_g = has_ref ? P.ref_len[ref] : 0;
-        const int nmax = P.ref_len[4 * q];                        // sorted descending
-        const int nmin = (4 * q + 3 < P.n_refs) ? P.ref_len[4 * q + 3] : 0;
-        const uint32_t *wp = P.ref_words + (has_ref ? P.ref_word_off[ref] : 0);
-        const int64_t blk0 = (int64_t)rp * P.blocks_per_rp + (has_ref ? P.ref_blk_off[ref] : 0);
-        const int my_steps = has_ref ? n_g + GL - 1 : 0;          // steps this group needs
+        // this group's SEGMENT: a window [c0, c0 + n_g) of a reference (the whole reference unless it is
+        // very long).  A segment owns the checkpoint blocks [skip, own_end) of its local step space; the
+        // blocks before `skip` only warm up the window (every owned cell is further than the longest
+        // possible alignment from the window's left edge, so it is exact), see make_segments().
+        const int v = 4 * q + g;
+        const bool has_ref = v < P.n_vrefs;
+        const int ref = has_ref ? P.v_ref[v] : 0;
+        const int c0 = has_ref ? P.v_c0[v] : 0;
+        const int n_g = has_ref ? P.v_len[v] : 0;
+        const int skip = has_ref ? P.v_skip[v] : 0;
+        const int own_end = has_ref ? P.v_end[v] : 0;
+        const int nmax = P.v_len[4 * q];                          // sorted descending
+        const int nmin = (4 * q + 3 < P.n_vrefs) ? P.v_len[4 * q + 3] : 0;
+        const uint32_t *wp = P.ref_words + (has_ref ? P.ref_word_off[ref] + (uint32_t)(c0 >> 4) : 0u);
+        const int64_t blk0 = (int64_t)rp * P.blocks_per_rp + (has_ref ? P.ref_blk_off[ref] + c0 / CB : 0);
+        const int my_steps = has_ref ? min(n_g + GL - 1, own_end * CB) : 0;   // steps whose blocks this group owns
 
         uint32_t H[K];
 #pragma unroll
@@ -142,12 +150,12 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
             const int s_next = s0 + 16;
             if ((s_next % CB) == 0) {
                 const int b = s_next / CB;                       // block that starts at s_next
-                if (s_next - CB < my_steps) {                     // block b-1 exists for this group
+                if (s_next - CB < my_steps && b - 1 >= skip) {    // block b-1 is owned by this group
                     P.tmx[(blk0 + b - 1) * GL + t] = tmax;
                     gmax = vmax2(gmax, tmax);
-                    tmax = 0;
                 }
-                if (s_next < my_steps) {                          // block b exists: checkpoint it
+                tmax = 0;
+                if (s_next < my_steps && b >= skip) {             // block b is owned: checkpoint it
                     uint32_t *ck = P.ck + (blk0 + b) * (int64_t)(G::KW * GL) + t * 4;
                     store_checkpoint<K>(ck, H, diag);
                 }
@@ -158,7 +166,7 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
             const int s_end = ((nsteps + 15) >> 4) << 4;          // first step not executed
             if ((s_end % CB) != 0) {
                 const int b_last = s_end / CB;
-                if (b_last * CB < my_steps) {
+                if (b_last * CB < my_steps && b_last >= skip) {
                     P.tmx[(blk0 + b_last) * GL + t] = tmax;
                     gmax = vmax2(gmax, tmax);
                 }
@@ -170,8 +178,9 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
         gmax = vmax2(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
         if (t == 0 && has_ref) {
             const int64_t ro = P.ref_orig[ref];
-            P.scores[ro * P.n_reads + ra] = (int)(int16_t)(gmax & 0xffffu);
-            if (rb >= 0) P.scores[ro * P.n_reads + rb] = (int)(int16_t)(gmax >> 16);
+            // several segments of one reference may contribute: scores are zero-initialised
+            atomicMax(P.scores + ro * P.n_reads + ra, (int)(int16_t)(gmax & 0xffffu));
+            if (rb >= 0) atomicMax(P.scores + ro * P.n_reads + rb, (int)(int16_t)(gmax >> 16));
         }
     }
 }
@@ -180,7 +189,7 @@ template <int K>
 static cudaError_t launch_fill_k(const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st)
 {
     using G = Geo<K>;
-    const int n_quads = (P.n_refs + 3) / 4;
+    const int n_quads = (P.n_vrefs + 3) / 4;
     static const int env_warps = getenv("SWB_FILL_WARPS") ? atoi(getenv("SWB_FILL_WARPS")) : 0;
     static const int env_ctas = getenv("SWB_FILL_CTAS_PER_SM") ? atoi(getenv("SWB_FILL_CTAS_PER_SM")) : 0;
     const int warps = env_warps > 0 ? env_warps : 12;

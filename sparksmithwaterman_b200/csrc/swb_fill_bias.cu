@@ -42,7 +42,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
     uint32_t *prof = prof_all + warp * G::PROF_WORDS;
-    const int n_quads = (P.n_refs + 3) >> 2;
+    const int n_quads = (P.n_vrefs + 3) >> 2;
     const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
     const int ag = -P.gap;                                        // |gap| > 0
@@ -85,14 +85,22 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
             __syncwarp();
         }
 
-        const int ref = 4 * q + g;
-        const bool has_ref = ref < P.n_refs;
-        const int n_g = has_ref ? P.ref_len[ref] : 0;
-        const int nmax = P.ref_len[4 * q];
-        const int nmin = (4 * q + 3 < P.n_refs) ? P.ref_len[4 * q + 3] : 0;
-        const uint32_t *wp = P.ref_words + (has_ref ? P.ref_word_off[ref] : 0);
-        const int64_t blk0 = (int64_t)rp * P.blocks_per_rp + (has_ref ? P.ref_blk_off[ref] : 0);
-        const int my_steps = has_ref ? n_g + GL - 1 : 0;
+        // this group's SEGMENT: a window [c0, c0 + n_g) of a reference (the whole reference unless it is
+        // very long).  A segment owns the checkpoint blocks [skip, own_end) of its local step space; the
+        // blocks before `skip` only warm up the window (every owned cell is further than the longest
+        // possible alignment from the window's left edge, so it is exact), see make_segments().
+        const int v = 4 * q + g;
+        const bool has_ref = v < P.n_vrefs;
+        const int ref = has_ref ? P.v_ref[v] : 0;
+        const int c0 = has_ref ? P.v_c0[v] : 0;
+        const int n_g = has_ref ? P.v_len[v] : 0;
+        const int skip = has_ref ? P.v_skip[v] : 0;
+        const int own_end = has_ref ? P.v_end[v] : 0;
+        const int nmax = P.v_len[4 * q];                          // sorted descending
+        const int nmin = (4 * q + 3 < P.n_vrefs) ? P.v_len[4 * q + 3] : 0;
+        const uint32_t *wp = P.ref_words + (has_ref ? P.ref_word_off[ref] + (uint32_t)(c0 >> 4) : 0u);
+        const int64_t blk0 = (int64_t)rp * P.blocks_per_rp + (has_ref ? P.ref_blk_off[ref] + c0 / CB : 0);
+        const int my_steps = has_ref ? min(n_g + GL - 1, own_end * CB) : 0;   // steps whose blocks this group owns
 
         // all-zero matrix left of column 1, biased: every register = the floor of its column
         uint32_t H[K];
@@ -171,12 +179,12 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                 floorv = base_bias;
                 negfloor = negbase;
                 const int b = s_next / CB;
-                if (s_next - CB < my_steps) {
+                if (s_next - CB < my_steps && b - 1 >= skip) {
                     P.tmx[(blk0 + b - 1) * GL + t] = tmax;
                     gmax = vmax2(gmax, tmax);
-                    tmax = 0;
                 }
-                if (s_next < my_steps) {
+                tmax = 0;
+                if (s_next < my_steps && b >= skip) {
                     uint32_t U[K];
 #pragma unroll
                     for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
@@ -189,7 +197,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
             const int s_end = ((nsteps + 15) >> 4) << 4;
             if ((s_end % CB) != 0) {
                 const int b_last = s_end / CB;
-                if (b_last * CB < my_steps) {
+                if (b_last * CB < my_steps && b_last >= skip) {
                     P.tmx[(blk0 + b_last) * GL + t] = tmax;
                     gmax = vmax2(gmax, tmax);
                 }
@@ -200,8 +208,9 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
         gmax = vmax2(gmax, __shfl_xor_sync(0xffffffffu, gmax, 4));
         if (t == 0 && has_ref) {
             const int64_t ro = P.ref_orig[ref];
-            P.scores[ro * P.n_reads + ra] = (int)(int16_t)(gmax & 0xffffu);
-            if (rb >= 0) P.scores[ro * P.n_reads + rb] = (int)(int16_t)(gmax >> 16);
+            // several segments of one reference may contribute: scores are zero-initialised
+            atomicMax(P.scores + ro * P.n_reads + ra, (int)(int16_t)(gmax & 0xffffu));
+            if (rb >= 0) atomicMax(P.scores + ro * P.n_reads + rb, (int)(int16_t)(gmax >> 16));
         }
     }
 }
@@ -210,7 +219,7 @@ template <int K>
 static cudaError_t launch_fill_bias_k(const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st)
 {
     using G = Geo<K>;
-    const int n_quads = (P.n_refs + 3) / 4;
+    const int n_quads = (P.n_vrefs + 3) / 4;
     static const int env_warps = getenv("SWB_FILL_WARPS") ? atoi(getenv("SWB_FILL_WARPS")) : 0;
     const int warps = env_warps > 0 ? env_warps : 12;
     const int64_t items = (int64_t)n_quads * P.n_rp;

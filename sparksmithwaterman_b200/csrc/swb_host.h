@@ -67,6 +67,7 @@ struct swb_ctx {
     // grow-only scratch reused by every align call on this context
     DevBuf<uint32_t> ck, tmx, counters;
     DevBuf<int32_t> rp, slot;
+    DevBuf<int32_t> v_ref, v_c0, v_len, v_skip, v_end;   // fill work units (reference segments) of the current class
     DevBuf<TileTask> tasks;
     DevBuf<uint64_t> keys_tmp;
     DevBuf<uint8_t> sort_tmp;
@@ -115,6 +116,7 @@ struct swb_refset {
     DevBuf<uint8_t> codes8;                     // 1 byte per base, original order (wide path)
     DevBuf<int64_t> off8;                       // [n_refs + 1]
     std::vector<int32_t> len_orig;
+    std::vector<int32_t> len_sorted;            // lengths in the device (descending-length) order
     DevBuf<uint32_t> words, word_off;
     DevBuf<int32_t> len, orig, sorted_of;
     DevBuf<int64_t> blk_off;

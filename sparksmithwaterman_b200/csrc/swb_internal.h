@@ -63,6 +63,9 @@ struct BatchParams {
     const int64_t  *ref_blk_off;    // [n_refs+1] prefix of checkpoint blocks per sorted ref
     int32_t n_refs;
     int64_t blocks_per_rp;          // ref_blk_off[n_refs]
+    // fill work units: segments of references, sorted by descending length (see make_segments)
+    const int32_t *v_ref, *v_c0, *v_len, *v_skip, *v_end;
+    int32_t n_vrefs;
     // reads
     const uint8_t *read_codes;      // 1 byte per base: 0..3, 0xFF = matches nothing
     const int64_t *read_off;        // [n_reads+1]

@@ -68,3 +68,16 @@ def test_cfg2_sample(engine):
     """BASELINE config 2 shape at reduced count: 150 bp reads vs RefSeq-shaped refs."""
     refs, reads = synth.workload(24, 150, 60)
     check_pairs(engine, [r.decode() for r in refs], [q.decode() for q in reads])
+
+
+def test_long_references_are_segmented_exactly(engine):
+    """References longer than two fill segments are cut into overlapping windows (swb_api.cu
+    make_segments); results must not depend on it: reads planted across segment boundaries,
+    a tie-heavy long repeat (max cells in every segment), scores with long gap runs."""
+    rnd = random.Random(77)
+    base = "".join(rnd.choice("ACGT") for _ in range(9000))
+    refs = [base, "AT" * 3000, "".join(rnd.choice("ACGT") for _ in range(2500)), base[:2049], base[100:4300]]
+    reads = [base[k - 70:k + 80] for k in (1024, 2048, 3072, 8192 - 40)]            # straddle 1024-column cuts
+    reads += [base[950:1010] + base[1030:1100], "AT" * 75, base[2000:2100] + "ACGTACGT" + base[2100:2140]]
+    check_pairs(engine, refs, reads)
+    check_pairs(engine, refs[:2], reads[:5], (2, -1, -1))                           # wide windows: W = m + 2m
