@@ -3,6 +3,8 @@
 // No CPU fallback: every compute entry needs a CUDA device and fails loudly without one.
 #include "swb_host.h"
 
+#include <chrono>
+
 using namespace swbh;
 
 namespace swbh {
@@ -49,6 +51,11 @@ int swb_create(int device, int64_t workspace_bytes, swb_ctx **out)
     ws = std::min<int64_t>(ws, (int64_t)(free_b / 2));
     c->ws_bytes = ws;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_fill, cudaStreamNonBlocking));
+    // Two-stream pipelining (fill of batch k+1 beside the traceback of batch k) is OFF by default: measured on
+    // B200 the persistent fill warps keep the integer pipe ~94 % busy and starve co-resident kernels (locate
+    // 0.55 -> 5.5 ms), so the overlap buys nothing (62.0 vs 61.1 ms per step).  SWB_PIPELINE=1 enables it.
+    c->pipeline = getenv("SWB_PIPELINE") != nullptr;
     CU(cudaEventCreate(&c->ev[0]));
     CU(cudaEventCreate(&c->ev[1]));
     cudaMemPool_t pool;
@@ -66,6 +73,8 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
     c->tasks.release(); c->keys_tmp.release(); c->sort_tmp.release();
+    for (int k = 0; k < 2; ++k) { c->ck2[k].release(); c->tmx2[k].release(); c->rp2[k].release(); }
+    cudaStreamSynchronize(c->stream_fill);
     c->v_ref.release(); c->v_c0.release(); c->v_len.release(); c->v_skip.release(); c->v_end.release();
     c->w_brow.release(); c->w_ck.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
     c->w_pair_read.release(); c->w_band_off.release(); c->w_blk_off.release(); c->w_brow_off.release();
@@ -75,6 +84,7 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->stream_fill) cudaStreamDestroy(c->stream_fill);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
 }
@@ -342,25 +352,36 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     CU(res->d_best.alloc((size_t)n_reads * 4, st));
     CU(cudaMemsetAsync(res->d_scores.p, 0, std::max<size_t>(n_pairs, 1) * 4, st));
 
+    const auto t_wall0 = std::chrono::steady_clock::now();
     // phase timing: event pairs are only recorded inside the loop and read after the last sync
     ctx->ev_used = 0;
     struct Span { cudaEvent_t a, b; int phase; };
     std::vector<Span> spans;
-    auto tic = [&](int phase) -> cudaError_t {
+    // spans may interleave (two streams): tic returns the span's index, toc closes that index
+    cudaError_t span_err = cudaSuccess;
+    auto tic = [&](int phase, cudaStream_t on) -> int {
         Span sp; sp.phase = phase;
         cudaError_t e = ctx->next_event(&sp.a);
         if (e == cudaSuccess) e = ctx->next_event(&sp.b);
-        if (e == cudaSuccess) e = cudaEventRecord(sp.a, st);
-        if (e == cudaSuccess) spans.push_back(sp);
-        return e;
+        if (e == cudaSuccess) e = cudaEventRecord(sp.a, on);
+        if (e != cudaSuccess) { span_err = e; return -1; }
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
     };
-    auto toc = [&]() -> cudaError_t { return cudaEventRecord(spans.back().b, st); };
+    auto toc = [&](int idx, cudaStream_t on) -> cudaError_t {
+        if (idx < 0) return span_err;
+        return cudaEventRecord(spans[(size_t)idx].b, on);
+    };
+    // single-stream adapters for the wide path
+    int wide_span = -1;
+    std::function<cudaError_t(int)> tic1 = [&](int phase) -> cudaError_t { wide_span = tic(phase, st); return wide_span < 0 ? span_err : cudaSuccess; };
+    std::function<cudaError_t()> toc1 = [&]() -> cudaError_t { return toc(wide_span, st); };
     (void)max_m;
 
     std::vector<int32_t> h_read_batch, h_read_slot_all, wide_reads_all;
     double ck_bytes = 0;
     int launches = 1, n_batches = 0;
-    CU(ctx->counters.reserve(8, st));
+    CU(ctx->counters.reserve(16, st));
 
     if (n_refs > 0 && n_reads > 0) {
         // group reads by rows-per-lane class, longest first inside a class
@@ -398,63 +419,83 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
             CU(cudaMemcpyAsync(ctx->v_skip.p, segs.skip.data(), nv * 4, cudaMemcpyHostToDevice, st));
             CU(cudaMemcpyAsync(ctx->v_end.p, segs.end.data(), nv * 4, cudaMemcpyHostToDevice, st));
             CU(cudaStreamSynchronize(st));         // segs is a local
+            // ---- batches of read pairs, two-stage pipeline on two streams -----------------------------
+            // stage F (ctx->stream_fill): fill of batch k+1;  stage T (ctx->stream): flag/locate/sort/trace of
+            // batch k.  The fill saturates the integer pipe, the traceback is latency-bound: run together they
+            // share the SMs.  Two checkpoint workspaces, ping-pong; events order the reuse.
             const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)KW * GL * 4 + GL * 4);
             int64_t rp_per_batch = std::max<int64_t>(1, ctx->ws_bytes / std::max<int64_t>(bytes_per_rp, 1));
+            const bool pipelined = !(flags & SWB_F_SCORES_ONLY) && n_rp_total > rp_per_batch / 2 && ctx->pipeline;
+            if (pipelined) rp_per_batch = std::max<int64_t>(1, rp_per_batch / 2);       // two workspaces
             rp_per_batch = std::min<int64_t>(rp_per_batch, 1 << 16);
             if (rp_per_batch * rs->n_refs * 2 >= ((int64_t)1 << 30)) rp_per_batch = std::max<int64_t>(1, (((int64_t)1 << 30) - 1) / (rs->n_refs * 2));
             // equal-sized batches (no small straggler batch at the end)
             const int64_t nb = (n_rp_total + rp_per_batch - 1) / rp_per_batch;
             rp_per_batch = (n_rp_total + nb - 1) / nb;
-            for (int64_t rp0 = 0; rp0 < n_rp_total; rp0 += rp_per_batch) {
-                const int n_rp = (int)std::min<int64_t>(rp_per_batch, n_rp_total - rp0);
-                ++n_batches;
-                std::vector<int32_t> h_rp((size_t)n_rp * 2, -1);
-                std::fill(h_slot.begin(), h_slot.end(), -1);
-                int m_max = 0;
-                for (int r = 0; r < n_rp; ++r)
+            cudaStream_t sF = pipelined ? ctx->stream_fill : st;
+
+            struct Stage { int n_rp = 0, m_max = 0, buf = 0; std::vector<int32_t> h_rp; BatchParams P; cudaEvent_t ev_fill = nullptr; };
+            std::vector<Stage> stages((size_t)nb);
+            cudaEvent_t ev_trace_done[2] = {nullptr, nullptr};
+
+            auto fill_stage = [&](int64_t k) -> int {
+                Stage &S = stages[(size_t)k];
+                const int64_t rp0 = k * rp_per_batch;
+                S.n_rp = (int)std::min<int64_t>(rp_per_batch, n_rp_total - rp0);
+                S.buf = pipelined ? (int)(k & 1) : 0;
+                S.h_rp.assign((size_t)S.n_rp * 2, -1);
+                for (int r = 0; r < S.n_rp; ++r)
                     for (int h = 0; h < 2; ++h) {
-                        const int64_t k = (rp0 + r) * 2 + h;
-                        if (k < (int64_t)idx.size()) {
-                            h_rp[(size_t)r * 2 + h] = idx[(size_t)k];
-                            h_slot[(size_t)idx[(size_t)k]] = r * 2 + h;
-                            m_max = std::max(m_max, rd->len[(size_t)idx[(size_t)k]]);
+                        const int64_t x = (rp0 + r) * 2 + h;
+                        if (x < (int64_t)idx.size()) {
+                            S.h_rp[(size_t)r * 2 + h] = idx[(size_t)x];
+                            S.m_max = std::max(S.m_max, rd->len[(size_t)idx[(size_t)x]]);
                         }
                     }
-                CU(ctx->rp.reserve(h_rp.size(), st));
-                CU(cudaMemcpyAsync(ctx->rp.p, h_rp.data(), h_rp.size() * 4, cudaMemcpyHostToDevice, st));
-                CU(cudaMemcpyAsync(ctx->slot.p, h_slot.data(), h_slot.size() * 4, cudaMemcpyHostToDevice, st));
-                const size_t ck_words = (size_t)n_rp * rs->blocks_per_rp * KW * GL;
-                const size_t tmx_words = (size_t)n_rp * rs->blocks_per_rp * GL;
-                CU(ctx->ck.reserve(ck_words, st));
-                CU(ctx->tmx.reserve(tmx_words, st));
+                ++n_batches;
+                DevBuf<uint32_t> &ck = ctx->ck2[S.buf], &tmx = ctx->tmx2[S.buf];
+                DevBuf<int32_t> &rpb = ctx->rp2[S.buf];
+                // the workspace of this parity is free once the traceback that last used it has finished
+                if (ev_trace_done[S.buf]) CU(cudaStreamWaitEvent(sF, ev_trace_done[S.buf], 0));
+                CU(rpb.reserve(S.h_rp.size(), sF));
+                CU(cudaMemcpyAsync(rpb.p, S.h_rp.data(), S.h_rp.size() * 4, cudaMemcpyHostToDevice, sF));
+                const size_t ck_words = (size_t)S.n_rp * rs->blocks_per_rp * KW * GL;
+                const size_t tmx_words = (size_t)S.n_rp * rs->blocks_per_rp * GL;
+                CU(ck.reserve(ck_words, sF));
+                CU(tmx.reserve(tmx_words, sF));
                 ck_bytes += (double)(ck_words + tmx_words) * 4;
-
-                BatchParams P;
+                BatchParams &P = S.P;
                 P.ref_words = rs->words.p; P.ref_word_off = rs->word_off.p; P.ref_len = rs->len.p;
                 P.ref_orig = rs->orig.p; P.ref_sorted_of = rs->sorted_of.p; P.ref_blk_off = rs->blk_off.p;
                 P.n_refs = (int32_t)n_refs; P.blocks_per_rp = rs->blocks_per_rp;
                 P.v_ref = ctx->v_ref.p; P.v_c0 = ctx->v_c0.p; P.v_len = ctx->v_len.p; P.v_skip = ctx->v_skip.p;
                 P.v_end = ctx->v_end.p; P.n_vrefs = (int32_t)nv;
-                P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = ctx->rp.p; P.read_slot = ctx->slot.p;
-                P.n_rp = n_rp; P.n_reads = n_reads;
+                P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = rpb.p; P.read_slot = nullptr;
+                P.n_rp = S.n_rp; P.n_reads = n_reads;
                 P.match = match; P.mismatch = mismatch; P.gap = gap;
-                P.scores = res->d_scores.p; P.ck = ctx->ck.p; P.tmx = ctx->tmx.p;
-                uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_work = ctx->counters.p + 2;
-
-                CU(tic(1));
-                if (fill_bias_ok(match, mismatch, gap, (int64_t)std::max(match, 0) * std::min<int64_t>(m_max, rs->max_len)))
-                    CU(launch_fill_bias(K, P, d_work, ctx->sm_count, st));
+                P.scores = res->d_scores.p; P.ck = ck.p; P.tmx = tmx.p;
+                uint32_t *d_work = ctx->counters.p + 4 + S.buf;
+                const int sp_fill = tic(1, sF);
+                if (fill_bias_ok(match, mismatch, gap, (int64_t)std::max(match, 0) * std::min<int64_t>(S.m_max, rs->max_len)))
+                    CU(launch_fill_bias(K, P, d_work, ctx->sm_count, sF));
                 else
-                    CU(launch_fill(K, P, d_work, ctx->sm_count, st));
+                    CU(launch_fill(K, P, d_work, ctx->sm_count, sF));
                 ++launches;
-                CU(toc());
-                if (flags & SWB_F_SCORES_ONLY) {
-                    CU(cudaStreamSynchronize(st));     // h_rp / h_slot are reused by the next batch
-                    continue;
-                }
+                CU(toc(sp_fill, sF));
+                CU(ctx->next_event(&S.ev_fill));
+                CU(cudaEventRecord(S.ev_fill, sF));
+                return SWB_OK;
+            };
 
+            auto trace_stage = [&](int64_t k) -> int {
+                Stage &S = stages[(size_t)k];
+                const BatchParams &P = S.P;
+                const int n_rp = S.n_rp;
+                if (sF != st) CU(cudaStreamWaitEvent(st, S.ev_fill, 0));
+                if (flags & SWB_F_SCORES_ONLY) return SWB_OK;
+                uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1;
                 // ---- flagged tiles -> max cells -> sorted keys (one host sync: the two counts) ----
-                CU(tic(2));
+                const int sp_loc = tic(2, st);
                 const int64_t pairs_b = (int64_t)n_rp * 2 * n_refs;
                 uint32_t cap_tasks = (uint32_t)std::min<int64_t>(pairs_b * 2 + 1024, (int64_t)1 << 31);
                 uint32_t cap_cells = (uint32_t)std::min<int64_t>(pairs_b * 2 + 4096, (int64_t)1 << 31);
@@ -483,39 +524,65 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 CU(ctx->sort_tmp.reserve(tmp_bytes, st));
                 CU(sort_keys(ctx->keys_tmp.p, bo.keys.p, n_cells, ctx->sort_tmp.p, tmp_bytes, st));
                 launches += 4;
-                CU(toc());
+                CU(toc(sp_loc, st));
 
                 // ---- traceback ----------------------------------------------------------
-                CU(tic(3));
+                const int sp_tr = tic(3, st);
                 const int64_t big = std::max({match, mismatch, 0});
-                int64_t lmax = (int64_t)m_max + (big * m_max - 1) / (-(int64_t)gap) + 1;
-                lmax = std::min<int64_t>(lmax, (int64_t)m_max + rs->max_len);
+                int64_t lmax = (int64_t)S.m_max + (big * S.m_max - 1) / (-(int64_t)gap) + 1;
+                lmax = std::min<int64_t>(lmax, (int64_t)S.m_max + rs->max_len);
                 bo.ops_stride = (int)((lmax + 15) / 16);
                 CU(bo.beg.alloc(n_cells, st));
                 CU(bo.oplen.alloc(n_cells, st));
                 CU(bo.ops.alloc((size_t)n_cells * bo.ops_stride, st));
-                CU(launch_trace(K, P, bo.keys.p, n_cells, bo.beg.p, bo.oplen.p, bo.ops.p, bo.ops_stride, ctx->sm_count, st));
+                CU(launch_trace(K, P, bo.keys.p, n_cells, bo.beg.p, bo.oplen.p, bo.ops.p, (int)bo.ops_stride, ctx->sm_count, st));
                 ++launches;
-                CU(toc());
+                CU(toc(sp_tr, st));
+                CU(ctx->next_event(&ev_trace_done[S.buf]));
+                CU(cudaEventRecord(ev_trace_done[S.buf], st));
                 res->stats[8] += n_cells;
-                for (size_t sl = 0; sl < h_rp.size(); ++sl)
-                    if (h_rp[sl] >= 0) {
-                        h_read_batch[(size_t)h_rp[sl]] = (int32_t)res->batches.size();
-                        h_read_slot_all[(size_t)h_rp[sl]] = (int32_t)sl;
-                    }
-                bo.slot_read = h_rp;
-                CU(bo.d_slot_read.alloc(h_rp.size(), st));
-                CU(cudaMemcpyAsync(bo.d_slot_read.p, bo.slot_read.data(), h_rp.size() * 4, cudaMemcpyHostToDevice, st));
+                bo.slot_read = S.h_rp;
+                CU(bo.d_slot_read.alloc(S.h_rp.size(), st));
+                CU(cudaMemcpyAsync(bo.d_slot_read.p, bo.slot_read.data(), S.h_rp.size() * 4, cudaMemcpyHostToDevice, st));
                 res->batches.push_back(std::move(bo));
+                return SWB_OK;
+            };
+
+            // the fill stream must see the scores memset and the segment tables issued on `st`
+            if (sF != st) {
+                cudaEvent_t ev0;
+                CU(ctx->next_event(&ev0));
+                CU(cudaEventRecord(ev0, st));
+                CU(cudaStreamWaitEvent(sF, ev0, 0));
             }
+            int rc = SWB_OK;
+            if (pipelined) {
+                if ((rc = fill_stage(0))) return rc;
+                for (int64_t k = 0; k < nb; ++k) {
+                    if (k + 1 < nb && (rc = fill_stage(k + 1))) return rc;
+                    if ((rc = trace_stage(k))) return rc;
+                }
+            } else {
+                for (int64_t k = 0; k < nb; ++k) {      // one workspace: strictly fill, then trace
+                    if ((rc = fill_stage(k))) return rc;
+                    if ((rc = trace_stage(k))) return rc;
+                }
+            }
+            if (sF != st) {                       // everything of this class is ordered before what follows on `st`
+                cudaEvent_t evl;
+                CU(ctx->next_event(&evl));
+                CU(cudaEventRecord(evl, sF));
+                CU(cudaStreamWaitEvent(st, evl, 0));
+            }
+            CU(cudaStreamSynchronize(st));        // stages hold host vectors used by async copies
         }
     }
     if (n_refs > 0 && !wide_reads_all.empty()) {
         int rc = run_wide_path(ctx, rs, rd, wide_reads_all, match, mismatch, gap, flags, res.get(), &launches, &n_batches,
-                               &ck_bytes, tic, toc);
+                               &ck_bytes, tic1, toc1);
         if (rc) return rc;
     }
-    CU(tic(4));
+    const int sp_misc = tic(4, st);
     CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
     CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, st));
     launches += 2;
@@ -566,14 +633,21 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
         CU(assemble_gather_ops(d_desc.p, (int)descs.size(), N, d_order.p, res->f_ops_off.p, res->f_ops.p, st));
         CU(assemble_offsets(d_pair_sorted.p, N, (int64_t)n_pairs, res->f_cell_off.p, res->d_best.p, n_reads, res->f_cells.p, st));
         launches += 8;
-        CU(toc());
+        CU(toc(sp_misc, st));
         CU(cudaStreamSynchronize(st));
         res->batches.clear();                     // per-batch buffers go back to the pool
     } else {
-        CU(toc());
+        CU(toc(sp_misc, st));
         CU(cudaStreamSynchronize(st));
     }
     double t_phase[5] = {0, 0, 0, 0, 0};
+    if (getenv("SWB_TIMELINE") && !spans.empty())
+        for (const Span &sp : spans) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, spans[0].a, sp.a);
+            cudaEventElapsedTime(&b, spans[0].a, sp.b);
+            fprintf(stderr, "[swb timeline] phase %d  %8.3f .. %8.3f ms\n", sp.phase, a, b);
+        }
     for (const Span &sp : spans) {
         float ms = 0;
         CU(cudaEventElapsedTime(&ms, sp.a, sp.b));
@@ -583,7 +657,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     int64_t read_bases = 0;
     for (int32_t m : rd->len) read_bases += m;
     res->stats[1] = t_phase[1]; res->stats[2] = t_phase[2]; res->stats[3] = t_phase[3];
-    res->stats[5] = t_phase[1] + t_phase[2] + t_phase[3] + t_phase[4];
+    res->stats[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();   // wall: phases overlap
     res->stats[6] = (double)rs->total_bases * (double)read_bases;
     res->stats[7] = (double)n_refs * (double)n_reads;
     res->stats[9] = launches; res->stats[10] = ck_bytes; res->stats[11] = n_batches;

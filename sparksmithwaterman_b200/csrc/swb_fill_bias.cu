@@ -226,6 +226,16 @@ static cudaError_t launch_fill_bias_k(const BatchParams &P, uint32_t *work_count
     const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count);   // one CTA per SM
     const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
     cudaError_t e = cudaSuccess;
+    {
+        // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of
+        // shared memory each) must be able to co-reside with this kernel's CTA on the same SM
+        static bool carve_set = false;
+        if (!carve_set) {
+            e = cudaFuncSetAttribute(fill_bias_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            if (e != cudaSuccess) return e;
+            carve_set = true;
+        }
+    }
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(fill_bias_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
