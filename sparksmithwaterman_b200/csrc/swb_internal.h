@@ -105,6 +105,7 @@ struct WideParams {
     const uint8_t *read_codes;
     const int64_t *read_off;
     int32_t match, mismatch, gap;
+    int32_t n_symbols;           // alphabet size of the reference set (codes 0 .. n_symbols-1)
     int64_t n_reads;
     const int64_t *band_off;     // [n_pairs + 1] prefix of bands
     const int64_t *blk_off;      // [n_pairs + 1] prefix of bands * blocks

@@ -132,10 +132,16 @@ __device__ __forceinline__ void load_wide_state(const WCtx &C, int band, int blk
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
+// Fill.  PROF = true (alphabets of up to 8 symbols): the substitution score comes from a per-warp
+// shared-memory profile of the band ([code][KL/4][lane][4], conflict-free LDS.128) and the NW + s add is an
+// IMAD on the FMA pipe, leaving two DPX ops per cell on the integer pipe.  PROF = false: compare + select.
+template <bool PROF>
 __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, const int2 *items, int n_items,
-                                                         uint32_t *ticket)
+                                                         uint32_t *ticket, int one)
 {
-    const int lane = threadIdx.x & 31;
+    extern __shared__ __align__(16) int32_t wprof_all[];          // PROF: per warp [8 codes][KL/4][32 lanes][4]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t *wprof = wprof_all + warp * (8 * KL * WL);
     for (;;) {
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(ticket, 1u);
@@ -145,6 +151,15 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
         const WCtx C = make_ctx(P, pair);
         int rc[KL]; bool all_valid;
         load_rows(C, band, lane, rc, all_valid);
+        if (PROF) {
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+#pragma unroll
+                for (int r = 0; r < KL; ++r)
+                    wprof[((c * (KL / 4) + (r >> 2)) * WL + lane) * 4 + (r & 3)] = (rc[r] == c) ? C.match : C.mismatch;
+            __syncwarp();
+        }
         int H[KL], diag = 0;
 #pragma unroll
         for (int r = 0; r < KL; ++r) H[r] = 0;
@@ -170,18 +185,47 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                 }
             }
             const int tbuf = top_prefetch(C, band, s0, lane);
-            wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
-                       [&](int, int, const int (&Hc)[KL], bool valid, int j) {
-                           if (!valid) return;
-                           if (lane == WL - 1) my_brow[j] = Hc[KL - 1];
-                           if (all_valid) {
+#pragma unroll 1
+            for (int u = 0; u < 32; ++u) {
+                const int s = s0 + u;
+                int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
+                const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
+                if (lane == 0) top = t0;
+                const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
+                const int j = s - lane + 1;
+                if ((j >= 1) && (j <= C.n)) {
+                    int sv[KL];
+                    if (PROF) {
+                        const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & 7) * (KL / 4) * WL + lane;
 #pragma unroll
-                               for (int r = 0; r < KL; ++r) tmax = max(tmax, Hc[r]);
-                           } else {
+                        for (int q = 0; q < KL / 4; ++q) {
+                            const int4 v = pp[q * WL];
+                            sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
+                        }
+                    } else {
 #pragma unroll
-                               for (int r = 0; r < KL; ++r) if (rc[r] < 0x100) tmax = max(tmax, Hc[r]);
-                           }
-                       });
+                        for (int r = 0; r < KL; ++r) sv[r] = (rc[r] == c) ? C.match : C.mismatch;
+                    }
+                    int nw = diag, nn = top;
+#pragma unroll
+                    for (int r = 0; r < KL; ++r) {
+                        const int tt = PROF ? nw * one + sv[r] : nw + sv[r];           // IMAD (FMA pipe) when PROF
+                        const int pre = __viaddmax_s32_relu(H[r], C.gap, tt);           // max(W+gap, NW+s, 0)
+                        nw = H[r];
+                        H[r] = __viaddmax_s32(nn, C.gap, pre);                          // max(N+gap, pre)
+                        nn = H[r];
+                    }
+                    if (lane == WL - 1) my_brow[j] = H[KL - 1];
+                    if (all_valid) {
+#pragma unroll
+                        for (int r = 0; r < KL; r += 2) tmax = __vimax3_s32(tmax, H[r], H[r + 1]);
+                    } else {
+#pragma unroll
+                        for (int r = 0; r < KL; ++r) if (rc[r] < 0x100) tmax = max(tmax, H[r]);
+                    }
+                }
+                diag = top;
+            }
             cprev = ccur;
             // publish: lane 31 has finished every column <= s0 + 1
             __threadfence();
@@ -371,7 +415,18 @@ cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * 4);
-    wide_fill_kernel<<<ctas, 128, 0, st>>>(P, items, n_items, ticket);
+    if (P.n_symbols <= 8) {
+        const size_t smem = (size_t)4 * 8 * KL * WL * sizeof(int32_t);      // 4 warps x 8 codes x BH rows
+        static bool attr_set = false;
+        if (!attr_set) {
+            e = cudaFuncSetAttribute(wide_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return e;
+            attr_set = true;
+        }
+        wide_fill_kernel<true><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
+    } else {
+        wide_fill_kernel<false><<<ctas, 128, 0, st>>>(P, items, n_items, ticket, 1);
+    }
     return cudaGetLastError();
 }
 
