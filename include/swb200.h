@@ -41,6 +41,10 @@ extern "C" {
 /* swb_align flags */
 #define SWB_F_SCORES_ONLY   1u  /* fill only: scores + ref totals + best hits, no cell lists     */
 #define SWB_F_NO_FETCH      2u  /* leave results in HBM; call swb_result_fetch() later           */
+#define SWB_F_TIE_GT        4u  /* DistributedSW.GetCellScore's strict '>' cascade (DistributedSW.java:300-330):
+                                   on equal candidates deletion wins over insertion over alignment.  Scores and
+                                   the max-cell SET are unchanged; cells are still listed row-major (the host
+                                   layer re-orders them diagonal-major + stable by beginning, :209, :480)   */
 
 typedef struct swb_ctx    swb_ctx;     /* one CUDA device + streams + workspace                */
 typedef struct swb_refset swb_refset;  /* packed reference set resident in HBM                  */

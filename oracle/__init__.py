@@ -52,7 +52,7 @@ def lib():
         L = C.CDLL(_LIB_PATH)
         sig = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
                C.POINTER(_Result)]
-        for name in ("sw_oracle_align", "sw_oracle_align_lowmem"):
+        for name in ("sw_oracle_align", "sw_oracle_align_lowmem", "sw_oracle_align_gt"):
             getattr(L, name).argtypes = sig
             getattr(L, name).restype = C.c_int
         L.sw_oracle_score.argtypes = [C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32,
@@ -86,12 +86,12 @@ def _b(s) -> bytes:
 
 
 def align(ref, read, match: int = 5, mismatch: int = -3, gap: int = -4,
-          lowmem: bool = False, max_cells: int | None = None) -> PairResult:
-    """One pair through the C oracle (SmithWaterman.java:62-92)."""
+          lowmem: bool = False, max_cells: int | None = None, tie_gt: bool = False) -> PairResult:
+    """One pair through the C oracle (SmithWaterman.java:62-92; tie_gt: DistributedSW.java semantics)."""
     L = lib()
     ref_b, read_b = _b(ref), _b(read)
     r = _Result()
-    fn = L.sw_oracle_align_lowmem if lowmem else L.sw_oracle_align
+    fn = L.sw_oracle_align_gt if tie_gt else (L.sw_oracle_align_lowmem if lowmem else L.sw_oracle_align)
     rc = fn(ref_b, len(ref_b), read_b, len(read_b), match, mismatch, gap, C.byref(r))
     if rc != 0:
         raise MemoryError("oracle allocation failed")

@@ -257,6 +257,98 @@ oom:
     return -1;
 }
 
+/* ---- DistributedSW variant -------------------------------------------------
+ * /root/reference/src/sw/DistributedSW.java: same recurrence, but
+ *  - GetCellScore (:280-330) tests with strict ">" in the order deletion, insertion, alignment, so on
+ *    equal candidates the FIRST one wins (d over i over a) and a zero cell keeps the type "none";
+ *  - ScoreMatrix (:143-245) walks anti-diagonals (i + j ascending), each sorted by j (:209, CellResultComp
+ *    :907-911), so the max-cell list is diagonal-major;
+ *  - GetAlignments (:456-490) stably sorts the alignments by beginning (MatchSiteComp).
+ * Output cells/sites are in that final (sorted) order. */
+int sw_oracle_align_gt(const char *ref, int64_t n, const char *read, int64_t m,
+                       int32_t match, int32_t mismatch, int32_t gap, sw_oracle_result *out)
+{
+    memset(out, 0, sizeof(*out));
+    const int64_t W = n + 1;
+    int32_t *S = (int32_t *)calloc((size_t)((m + 1) * W), sizeof(int32_t));
+    uint8_t *A = (uint8_t *)calloc((size_t)((m + 1) * W), 1);
+    ivec cells = {0, 0, 0};
+    if (!S || !A) goto oom;
+    int32_t max_score = 0;
+    if (m > 0 && n > 0)
+        for (int64_t d = 2; d <= m + n; ++d) {
+            int64_t jlo = d - m < 1 ? 1 : d - m, jhi = d - 1 > n ? n : d - 1;
+            for (int64_t j = jlo; j <= jhi; ++j) {
+                const int64_t i = d - j;
+                int32_t best = 0; uint8_t type = T_NONE;
+                int32_t t = (int32_t)((uint32_t)S[i * W + j - 1] + (uint32_t)gap);
+                if (t > best) { best = t; type = T_DEL; }
+                t = (int32_t)((uint32_t)S[(i - 1) * W + j] + (uint32_t)gap);
+                if (t > best) { best = t; type = T_INS; }
+                int32_t sc = (up((unsigned char)ref[j - 1]) == up((unsigned char)read[i - 1])) ? match : mismatch;
+                t = (int32_t)((uint32_t)S[(i - 1) * W + j - 1] + (uint32_t)sc);
+                if (t > best) { best = t; type = T_ALIGN; }
+                S[i * W + j] = best; A[i * W + j] = type;
+                if (best > max_score) { cells.n = 0; max_score = best; if (ivec_push2(&cells, (int32_t)i, (int32_t)j)) goto oom; }
+                else if (best == max_score) { if (ivec_push2(&cells, (int32_t)i, (int32_t)j)) goto oom; }
+            }
+        }
+    {
+        const int64_t nc = cells.n / 2;
+        out->score = max_score; out->n_cells = nc;
+        out->cells = (int32_t *)calloc((size_t)nc * 2 + 2, sizeof(int32_t));
+        out->beginning = (int32_t *)calloc((size_t)nc + 1, sizeof(int32_t));
+        out->aln_off = (int64_t *)calloc((size_t)nc + 1, sizeof(int64_t));
+        int32_t *beg = (int32_t *)calloc((size_t)nc + 1, sizeof(int32_t));
+        int64_t *len = (int64_t *)calloc((size_t)nc + 1, sizeof(int64_t));
+        int64_t *order = (int64_t *)calloc((size_t)nc + 1, sizeof(int64_t));
+        char **ra = (char **)calloc((size_t)nc + 1, sizeof(char *)), **qa = (char **)calloc((size_t)nc + 1, sizeof(char *));
+        char *stack = (char *)malloc((size_t)(2 * (m + n) + 2));
+        if (!out->cells || !out->beginning || !out->aln_off || !beg || !len || !order || !ra || !qa || !stack) goto oom;
+        for (int64_t k = 0; k < nc; ++k) {
+            int64_t i = cells.v[2 * k], j = cells.v[2 * k + 1];
+            int32_t score = S[i * W + j]; int64_t depth = 0;
+            while (score > 0) {
+                beg[k] = (int32_t)j;
+                const uint8_t t = A[i * W + j];
+                if (t == T_ALIGN) { stack[2 * depth] = ref[j - 1]; stack[2 * depth + 1] = read[i - 1]; --i; --j; }
+                else if (t == T_INS) { stack[2 * depth] = '_'; stack[2 * depth + 1] = read[i - 1]; --i; }
+                else { stack[2 * depth] = ref[j - 1]; stack[2 * depth + 1] = '_'; --j; }
+                ++depth; score = S[i * W + j];
+            }
+            len[k] = depth;
+            ra[k] = (char *)malloc((size_t)depth + 1); qa[k] = (char *)malloc((size_t)depth + 1);
+            for (int64_t p = 0; p < depth; ++p) { ra[k][p] = stack[2 * (depth - 1 - p)]; qa[k][p] = stack[2 * (depth - 1 - p) + 1]; }
+            order[k] = k;
+        }
+        /* stable insertion sort by beginning (lists are short in tests) */
+        for (int64_t a = 1; a < nc; ++a) {
+            const int64_t x = order[a]; int64_t b = a;
+            while (b > 0 && beg[order[b - 1]] > beg[x]) { order[b] = order[b - 1]; --b; }
+            order[b] = x;
+        }
+        int64_t total = 0;
+        for (int64_t k = 0; k < nc; ++k) total += len[k];
+        out->ref_aln = (char *)calloc((size_t)total + 1, 1); out->read_aln = (char *)calloc((size_t)total + 1, 1);
+        int64_t pos = 0;
+        for (int64_t k = 0; k < nc; ++k) {
+            const int64_t x = order[k];
+            out->cells[2 * k] = cells.v[2 * x]; out->cells[2 * k + 1] = cells.v[2 * x + 1];
+            out->beginning[k] = beg[x];
+            memcpy(out->ref_aln + pos, ra[x], (size_t)len[x]); memcpy(out->read_aln + pos, qa[x], (size_t)len[x]);
+            pos += len[x]; out->aln_off[k + 1] = pos;
+        }
+        for (int64_t k = 0; k < nc; ++k) { free(ra[k]); free(qa[k]); }
+        free(ra); free(qa); free(stack); free(beg); free(len); free(order);
+    }
+    free(S); free(A); free(cells.v);
+    return 0;
+oom:
+    free(S); free(A); free(cells.v);
+    sw_oracle_free(out);
+    return -1;
+}
+
 int sw_oracle_score(const char *ref, int64_t n, const char *read, int64_t m,
                     int32_t match, int32_t mismatch, int32_t gap,
                     int32_t *score, int64_t *n_cells)

@@ -47,13 +47,16 @@ int sw_oracle_align(const char *ref, int64_t n, const char *read, int64_t m,
                     int32_t match, int32_t mismatch, int32_t gap,
                     sw_oracle_result *out);
 
-/* Linear-memory variant for pairs whose matrices do not fit: two-row score fill
- * for the maximum + cell list, then a re-fill of the rows x columns window above
- * and left of each max cell (exact: cells outside that window cannot influence it).
- * Must agree with sw_oracle_align wherever both run. Returns 0 on success. */
+/* Low-memory variant for pairs whose int matrices do not fit: two score rows + a 2-bit
+ * plane per cell (0 = score is zero, 1/2/3 = a/i/d of a positive cell) -- all the walk
+ * ever reads.  Must agree with sw_oracle_align wherever both run. Returns 0 on success. */
 int sw_oracle_align_lowmem(const char *ref, int64_t n, const char *read, int64_t m,
                            int32_t match, int32_t mismatch, int32_t gap,
                            sw_oracle_result *out);
+
+/* DistributedSW.OptAlignments semantics (strict '>' ties, diagonal-major list, stable sort by beginning). */
+int sw_oracle_align_gt(const char *ref, int64_t n, const char *read, int64_t m,
+                       int32_t match, int32_t mismatch, int32_t gap, sw_oracle_result *out);
 
 /* Score + max-cell count only (no traceback), two-row memory. */
 int sw_oracle_score(const char *ref, int64_t n, const char *read, int64_t m,

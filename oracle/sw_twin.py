@@ -79,3 +79,32 @@ def map_ref(ref: str, reads, match: int = 5, mismatch: int = -3, gap: int = -4):
         sites.extend(s)
     sites.sort(key=lambda t: t[0])  # Python's sort is stable, like Collections.sort
     return total, sites
+
+
+def align_gt(ref: str, read: str, match: int = 5, mismatch: int = -3, gap: int = -4):
+    """DistributedSW.OptAlignments (reference src/sw/DistributedSW.java:77-104): same scores; ties between
+    candidates go to the FIRST of deletion, insertion, alignment (strict ">" cascade, :300-330); max cells
+    listed anti-diagonal by anti-diagonal, j ascending (:192-245, :907-911); alignments stably sorted by
+    beginning (:456-490).  Returns (score, cells, sites) in that final order."""
+    n, m = len(ref), len(read)
+    H = fill(ref, read, match, mismatch, gap)
+    best = max([0] + [H[i][j] for i in range(1, m + 1) for j in range(1, n + 1)])
+    cells = [(d - j, j) for d in range(2, m + n + 1) for j in range(max(1, d - m), min(n, d - 1) + 1)
+             if H[d - j][j] == best] if m and n else []
+    out = []
+    for (ci, cj) in cells:
+        i, j, ra, qa, beginning = ci, cj, [], [], 0
+        while H[i][j] > 0:
+            beginning = j
+            h = H[i][j]
+            s = match if _same(ref[j - 1], read[i - 1]) else mismatch
+            if _wrap32(H[i][j - 1] + gap) == h:
+                ra.append(ref[j - 1]); qa.append("_"); j -= 1
+            elif _wrap32(H[i - 1][j] + gap) == h:
+                ra.append("_"); qa.append(read[i - 1]); i -= 1
+            else:
+                assert _wrap32(H[i - 1][j - 1] + s) == h
+                ra.append(ref[j - 1]); qa.append(read[i - 1]); i -= 1; j -= 1
+        out.append(((ci, cj), (beginning, "".join(reversed(ra)), "".join(reversed(qa)))))
+    out.sort(key=lambda t: t[1][0])
+    return best, [c for c, _ in out], [s for _, s in out]

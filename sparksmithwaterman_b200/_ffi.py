@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "_lib", "libswb200.so")
 SWB_OK = 0
 SWB_F_SCORES_ONLY = 1
 SWB_F_NO_FETCH = 2
+SWB_F_TIE_GT = 4
 
 # every symbol include/swb200.h declares: name -> (restype, argtypes)
 _P = C.c_void_p

@@ -472,7 +472,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 P.v_end = ctx->v_end.p; P.n_vrefs = (int32_t)nv;
                 P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = rpb.p; P.read_slot = nullptr;
                 P.n_rp = S.n_rp; P.n_reads = n_reads;
-                P.match = match; P.mismatch = mismatch; P.gap = gap;
+                P.match = match; P.mismatch = mismatch; P.gap = gap; P.tie_gt = (flags & SWB_F_TIE_GT) ? 1 : 0;
                 P.scores = res->d_scores.p; P.ck = ck.p; P.tmx = tmx.p;
                 uint32_t *d_work = ctx->counters.p + 4 + S.buf;
                 const int sp_fill = tic(1, sF);

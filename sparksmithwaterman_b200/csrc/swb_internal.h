@@ -75,6 +75,7 @@ struct BatchParams {
     int64_t n_reads;                // reads in the whole call (pair index stride)
     // scores
     int32_t match, mismatch, gap;
+    int32_t tie_gt;                 // traceback tie rule: 0 = '>=' cascade (a > i > d), 1 = strict '>' (d > i > a)
     // outputs / workspace
     int32_t  *scores;               // [n_refs_orig * n_reads]
     uint32_t *ck;                   // checkpoints  [n_rp][blocks_per_rp][KW/4][GL][4]
@@ -105,6 +106,7 @@ struct WideParams {
     const uint8_t *read_codes;
     const int64_t *read_off;
     int32_t match, mismatch, gap;
+    int32_t tie_gt;
     int32_t n_symbols;           // alphabet size of the reference set (codes 0 .. n_symbols-1)
     int64_t n_reads;
     const int64_t *band_off;     // [n_pairs + 1] prefix of bands

@@ -472,11 +472,11 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                     // type of a positive cell = first of (alignment, insertion, deletion) whose candidate
                     // equals H: the ">=" cascade of GetCellScore.call.  Branch-free: both walkers of a
                     // warp's groups stay converged.
-                    const bool is_a = (hnw + sc == w_h);
-                    const bool is_i = !is_a && (hn + P.gap == w_h);
-                    const uint32_t op = is_a ? 1u : (is_i ? 2u : 3u);
+                    // (SWB_F_TIE_GT: DistributedSW's strict ">" cascade -- first of deletion, insertion, alignment.)
+                    const bool eq_a = (hnw + sc == w_h), eq_i = (hn + P.gap == w_h), eq_d = (hw + P.gap == w_h);
+                    const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
                     w_beg = cj;
-                    w_h = is_a ? hnw : (is_i ? hn : hw);
+                    w_h = op == 1u ? hnw : (op == 2u ? hn : hw);
                     ci -= (op != 3u);
                     cj -= (op != 2u);
                     w_opword |= op << (2 * (w_len & 15));

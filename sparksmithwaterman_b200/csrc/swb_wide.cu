@@ -382,11 +382,10 @@ __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, cons
                     const int32_t *lt = wtile + c * CW + tc * (KL + 1) + r;
                     const int hw = lt[-CW], hn = lt[-1], hnw = lt[-CW - 1];
                     const int sc = (C.read[ci - 1] == C.ref[cj - 1]) ? C.match : C.mismatch;
-                    const bool is_a = (hnw + sc == hcur);
-                    const bool is_i = !is_a && (hn + C.gap == hcur);
-                    const uint32_t op = is_a ? 1u : (is_i ? 2u : 3u);
+                    const bool eq_a = (hnw + sc == hcur), eq_i = (hn + C.gap == hcur), eq_d = (hw + C.gap == hcur);
+                    const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
                     beginning = cj;
-                    hcur = is_a ? hnw : (is_i ? hn : hw);
+                    hcur = op == 1u ? hnw : (op == 2u ? hn : hw);
                     ci -= (op != 3u);
                     cj -= (op != 2u);
                     opword |= op << (2 * (int)(oplen & 15));

@@ -79,7 +79,7 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         WideParams P;
         P.n_pairs = np; P.pair_ref = ctx->w_pair_ref.p; P.pair_read = ctx->w_pair_read.p;
         P.ref_codes = rs->codes8.p; P.ref_off = rs->off8.p; P.read_codes = rd->codes.p; P.read_off = rd->off.p;
-        P.match = match; P.mismatch = mismatch; P.gap = gap; P.n_reads = n_reads; P.n_symbols = rs->n_symbols;
+        P.match = match; P.mismatch = mismatch; P.gap = gap; P.n_reads = n_reads; P.n_symbols = rs->n_symbols; P.tie_gt = (flags & SWB_F_TIE_GT) ? 1 : 0;
         P.band_off = ctx->w_band_off.p; P.blk_off = ctx->w_blk_off.p; P.brow_off = ctx->w_brow_off.p;
         P.brow = ctx->w_brow.p; P.ck = ctx->w_ck.p; P.tmx = ctx->w_tmx.p; P.prog = ctx->w_prog.p;
         P.scores = res->d_scores.p;

@@ -8,7 +8,7 @@ from typing import List, Sequence, Tuple
 import numpy as np
 
 from . import _ffi
-from ._ffi import SWB_F_NO_FETCH, SWB_F_SCORES_ONLY, check
+from ._ffi import SWB_F_NO_FETCH, SWB_F_SCORES_ONLY, SWB_F_TIE_GT, check
 
 DEFAULT_SCORES = (5, -3, -4)          # Distribution.java:36 of the reference: match, mismatch, gap
 
@@ -92,12 +92,14 @@ class RefSet:
     def upload_reads(self, reads: Sequence) -> "Reads":
         return Reads(self, reads)
 
-    def align(self, reads, scores=DEFAULT_SCORES, scores_only: bool = False, fetch: bool = True) -> "AlignResult":
-        """Host-buffer path (swb_align): H2D of the reads, compute, D2H of the results."""
+    def align(self, reads, scores=DEFAULT_SCORES, scores_only: bool = False, fetch: bool = True,
+              tie_gt: bool = False) -> "AlignResult":
+        """Host-buffer path (swb_align): H2D of the reads, compute, D2H of the results.
+        tie_gt: DistributedSW's strict-'>' tie rule in the traceback (SWB_F_TIE_GT)."""
         if isinstance(reads, Reads):
-            return reads.align(scores, scores_only, fetch)
+            return reads.align(scores, scores_only, fetch, tie_gt)
         data, off, bs = concat(reads)
-        flags = (SWB_F_SCORES_ONLY if scores_only else 0) | (0 if fetch else SWB_F_NO_FETCH)
+        flags = (SWB_F_SCORES_ONLY if scores_only else 0) | (0 if fetch else SWB_F_NO_FETCH) | (SWB_F_TIE_GT if tie_gt else 0)
         h = C.c_void_p()
         check(self.eng.lib.swb_align(self.eng.h, self.h, len(bs), data, _i64p(off),
                                      scores[0], scores[1], scores[2], flags, C.byref(h)))
@@ -127,8 +129,9 @@ class Reads:
         except Exception:
             pass
 
-    def align(self, scores=DEFAULT_SCORES, scores_only: bool = False, fetch: bool = True) -> "AlignResult":
-        flags = (SWB_F_SCORES_ONLY if scores_only else 0) | (0 if fetch else SWB_F_NO_FETCH)
+    def align(self, scores=DEFAULT_SCORES, scores_only: bool = False, fetch: bool = True,
+              tie_gt: bool = False) -> "AlignResult":
+        flags = (SWB_F_SCORES_ONLY if scores_only else 0) | (0 if fetch else SWB_F_NO_FETCH) | (SWB_F_TIE_GT if tie_gt else 0)
         h = C.c_void_p()
         check(self.rs.eng.lib.swb_align_resident(self.rs.eng.h, self.rs.h, self.h,
                                                  scores[0], scores[1], scores[2], flags, C.byref(h)))

@@ -60,3 +60,34 @@ class SmithWaterman:
                     res.free()
             finally:
                 rs.free()
+
+
+def distributed_order(cells, sites):
+    """DistributedSW's result order: max cells anti-diagonal by anti-diagonal (i + j ascending), j ascending
+    inside one (DistributedSW.java:192-245, :907-911), then the alignments stably sorted by beginning
+    (:456-490, MatchSiteComp).  Input: row-major cells and their sites."""
+    order = sorted(range(len(cells)), key=lambda k: (cells[k][0] + cells[k][1], cells[k][1]))
+    order.sort(key=lambda k: sites[k][0])
+    return [cells[k] for k in order], [sites[k] for k in order]
+
+
+class DistributedSW:
+    """Drop-in for the reference's other operator, sw.DistributedSW.OptAlignments
+    (src/sw/DistributedSW.java:50,77-104): identical signature, strict-'>' tie rule.  The reference
+    runs one Spark job per anti-diagonal; here it is the same CUDA path with SWB_F_TIE_GT."""
+
+    class OptAlignments:
+        def call(self, seqs: Sequence[str], alignScores: Sequence[int] = ALIGN_SCORES,
+                 alignTypes: Sequence[str] = ALIGN_TYPES):
+            eng = default_engine()
+            rs = eng.load_refset([seqs[0]])
+            try:
+                res = rs.align([seqs[1]], tuple(alignScores), tie_gt=True).cache()
+                try:
+                    score, cells, sites = res.pair(0, 0)
+                    _, sites = distributed_order(cells, sites)
+                    return score, [(b, [ra, qa]) for (b, ra, qa) in sites]
+                finally:
+                    res.free()
+            finally:
+                rs.free()

@@ -114,3 +114,20 @@ def test_engineer_data_sweep_points(engine):
     assert [p[1] for p in datasets.change_ref_num()][:10] == [1, 10, 30, 50, 100, 500, 1000, 1500, 2000, 4000]
     assert len(list(datasets.change_ref_num())) == 28 and len(list(datasets.change_ref_len())) == 36   # runTest3/4 loop counts
     assert len(list(datasets.change_read_num())) == 33 and len(list(datasets.change_read_len())) == 25
+
+
+def test_distributed_sw_tie_mode(engine):
+    """N3: DistributedSW.OptAlignments (strict '>' ties, diagonal-major order, stable sort by beginning)."""
+    sw.set_default_engine(engine)
+    op = sw.DistributedSW.OptAlignments()
+    assert op.call(["GTTCA", "CTA"]) == (6, [(3, ["TCA", "T_A"])])            # '>=' gives (4, C_A, CTA)
+    assert sw.SmithWaterman.OptAlignments().call(["GTTCA", "CTA"]) == (6, [(4, ["C_A", "CTA"])])
+    rnd = random.Random(17)
+    cases = [("ATATATAT", "ATAT"), ("AAGGAA", "AAA"), ("CGTGAATTCAT", "GACTTAC"), ("AT" * 60, "AT" * 20)]
+    cases += [("".join(rnd.choice("ACGT") for _ in range(rnd.randint(10, 300))),
+               "".join(rnd.choice("ACGT") for _ in range(rnd.randint(5, 300)))) for _ in range(25)]
+    for scores in ((5, -3, -4), (1, -1, -1), (2, -1, -2)):
+        for ref, read in cases:
+            exp = oracle.align(ref, read, *scores, tie_gt=True)
+            got = op.call([ref, read], list(scores))
+            assert got == (exp.score, [(b, [ra, qa]) for (b, ra, qa) in exp.sites]), (ref[:20], read[:20], scores)

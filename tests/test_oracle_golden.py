@@ -123,3 +123,19 @@ def test_map_ref_reduction_matches_twin():
     assert out["pair_scores"] == [sw_twin.align(ref, q)[0] for q in reads]
     # both harness shapes walk the same pairs
     assert oracle.cpu_baseline([ref] * 5, reads, threads=3, mode=1)["checksum"] != 0
+
+
+@settings(max_examples=150, deadline=None)
+@given(seqs, seqs, st.sampled_from([(5, -3, -4), (1, -1, -1), (2, -2, -2), (3, -3, -1), (1, 0, 0), (2, 1, -1)]))
+def test_distributed_sw_variant_oracle_equals_twin(ref, read, sc):
+    """N3: DistributedSW semantics (strict '>' ties, diagonal-major list, stable sort by beginning)."""
+    r = oracle.align(ref, read, *sc, tie_gt=True)
+    assert (r.score, r.cells, r.sites) == sw_twin.align_gt(ref, read, *sc)
+    assert r.score == oracle.align(ref, read, *sc).score                     # the tie rule never changes H
+
+
+def test_distributed_sw_known_answers():
+    assert oracle.align("GTTCA", "CTA", tie_gt=True).sites == [(3, "TCA", "T_A")]      # SURVEY.md 8a
+    assert oracle.align("CCAAT", "CAT", tie_gt=True).sites == [(2, "CAAT", "CA_T")]    # ">=" gives C_AT
+    r = oracle.align("ATATATAT", "ATAT", tie_gt=True)
+    assert r.score == 20 and [s[0] for s in r.sites] == [1, 3, 5]
