@@ -420,7 +420,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 for (int r = K + 1; r < KW; ++r) v[r] = 0;
                 store_column<KW, KH>(tileA, tileB, 0, v, 0x00040004u);
             }
-#pragma unroll 2
+#pragma unroll 2   // measured: unroll 1 / 2 / 4 -> 17.6 / 15.7 / 17.5 ms per step
             for (int u = 0; u < CB; ++u) {
                 uint32_t top = __shfl_up_sync(gmask, H[K - 1], 1, GL);
                 if (t == 0) top = 0;
