@@ -224,37 +224,29 @@ template <int K> struct TraceGeo {
     // lanes of a half's tile: a walk of CB steps climbs at most CB rows (plus rare insertion runs,
     // which simply end the block early), i.e. ceil(CB / K) lanes above the current one
     static constexpr int NLW = ((CB + K - 1) / K + 1) < GL ? ((CB + K - 1) / K + 1) : GL;
-    static constexpr int KH = ((Geo<K>::KW / 2 + 1 + 3) / 4) * 4;      // + 1: a spare halfword pair for the column code
+    static constexpr int KW = Geo<K>::KW;
+    static constexpr int HALF_WORDS = NLW * (CB + 1) * KW;            // one half's tile: [slot][column][KW packed words]
+    static constexpr int CODE_WORDS = ((2 * NLW * (CB + 1) + 1 + 15) / 16) * 4;   // [half][slot][column] bytes + 1 trash byte
+    static constexpr int GROUP_WORDS = 2 * HALF_WORDS + CODE_WORDS + KW;         // + one trash column
 };
 
-// One tile column of this lane into the windows it belongs to (either may be null).  Each half's
-// tile keeps only ITS s16 half of the KW packed values: KW/2 words, padded to KH for STS.128.
-template <int KW, int KH>
-__device__ __forceinline__ void store_column(uint32_t *ta, uint32_t *tb, int c, const uint32_t (&v)[KW], uint32_t codes)
+__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+// one tile column: word 0 = boundary row received from the lane above, words 1..K = this lane's rows
+template <int K>
+__device__ __forceinline__ void store_col(uint32_t *dst, uint32_t top, const uint32_t (&H)[K])
 {
-    static_assert(2 * KH > KW, "need a spare halfword per column for the reference code");
-    // codes = (code of half 0's column) | (code of half 1's column) << 16, kept in halfword KW of the column
-    if (ta) {
-        uint32_t w[KH];
+    constexpr int KW = Geo<K>::KW;
 #pragma unroll
-        for (int q = 0; q < KH; ++q) w[q] = (2 * q + 1 < KW) ? __byte_perm(v[2 * q], v[(2 * q + 1 < KW) ? 2 * q + 1 : 0], 0x5410)
-                                                             : (2 * q == KW ? (codes & 0xffffu) : 0u);
-        uint4 *col = reinterpret_cast<uint4 *>(ta + c * KH);
-#pragma unroll
-        for (int q = 0; q < KH / 4; ++q) col[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
-    }
-    if (tb) {
-        uint32_t w[KH];
-#pragma unroll
-        for (int q = 0; q < KH; ++q) w[q] = (2 * q + 1 < KW) ? __byte_perm(v[2 * q], v[(2 * q + 1 < KW) ? 2 * q + 1 : 0], 0x7632)
-                                                             : (2 * q == KW ? (codes >> 16) : 0u);
-        uint4 *col = reinterpret_cast<uint4 *>(tb + c * KH);
-#pragma unroll
-        for (int q = 0; q < KH / 4; ++q) col[q] = make_uint4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+    for (int q = 0; q < KW / 4; ++q) {
+        uint4 v;
+        v.x = (4 * q == 0) ? top : ((4 * q - 1 < K) ? H[(4 * q - 1 < K && 4 * q >= 1) ? 4 * q - 1 : 0] : 0u);
+        v.y = (4 * q + 0 < K) ? H[(4 * q + 0 < K) ? 4 * q + 0 : 0] : 0u;
+        v.z = (4 * q + 1 < K) ? H[(4 * q + 1 < K) ? 4 * q + 1 : 0] : 0u;
+        v.w = (4 * q + 2 < K) ? H[(4 * q + 2 < K) ? 4 * q + 2 : 0] : 0u;
+        reinterpret_cast<uint4 *>(dst)[q] = v;
     }
 }
-
-__device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
 
 // ---------------------------------------------------------------------------------------
 // Traceback, packed: one 8-lane group walks TWO max cells at once, one per s16 half.
@@ -264,32 +256,39 @@ __device__ __forceinline__ void prefetch_l2(const void *p) { asm volatile("prefe
 //     prof2[cA*5 + cB][lane][row] = pack(s(read[row], cA), s(read[row], cB)),  code 4 = "no column"
 // (S_PAD: a column left of the matrix stays all-zero, one right of it is never read).
 // Each half restarts from ITS block's checkpoint (own ref, own block index); the group then
-// runs the same three-op cell as the fill for CB steps, storing every column:
-//     tile[lane][c][w]   c = 0..CB (c = 0: the checkpointed column), w = 0: boundary row
-//                        received from lane-1 (matrix row lane*K), w = 1..K: the lane's rows
-// so W, N and NW of a cell with c >= 1 lie in the same lane's tile.  Lane h of the group
-// walks half h (GetAlignment.call, SmithWaterman.java:380-409) until the path leaves the
-// block, then the block that holds the current cell is recomputed -- exact, because every
-// block starts from the fill's own registers.
+// runs the same three-op cell as the (unbiased) fill for CB steps.  Only the lanes a walk of CB
+// steps can reach are kept, [tc - NLW + 1, tc] around the current cell's lane tc, per half:
+//     tile[half][slot][c][w]   c = 0..CB (c = 0: the checkpointed column), w = 0: boundary row
+//                              received from lane-1 (matrix row lane*K), w = 1..K: the lane's rows
+// so W, N and NW of a cell with c >= 1 lie in the same slot.  Lanes outside a window store to a
+// trash column (no branches in the step loop).  Lane h of the group walks half h
+// (GetAlignment.call, SmithWaterman.java:380-409) until the path leaves what the block holds, then
+// the block that holds the current cell is recomputed -- exact, because every block starts
+// from the fill's own registers.
 template <int K>
 __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const uint64_t *keys, uint32_t n_cells,
                                                      int chunk, int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
                                                      int ops_stride, uint32_t zero)
 {
     using G = Geo<K>;
+    using TG = TraceGeo<K>;
     constexpr int KW = G::KW;
-    constexpr int NLW = TraceGeo<K>::NLW;                           // lanes kept per half: a CB-step walk climbs <= CB rows
-    constexpr int KH = TraceGeo<K>::KH;                             // words per tile column: KW s16 values of ONE half
-    constexpr int HALF_WORDS = NLW * (CB + 1) * KH;
-    constexpr int TILE_WORDS = 2 * HALF_WORDS;
+    constexpr int NLW = TG::NLW;
+    constexpr int HALF_WORDS = TG::HALF_WORDS;
+    constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t seg_next;
     uint32_t *prof2 = smem;                                         // [25][GL][KS]
     const int lane = threadIdx.x & 31, t = lane & (GL - 1), g = lane >> 3, warp = threadIdx.x >> 5;
-    const unsigned gmask = 0xffu << (8 * g);
-    uint32_t *tile = smem + 25 * G::CSTRIDE + (size_t)(warp * 4 + g) * TILE_WORDS;
-    uint8_t *rcodes_s = reinterpret_cast<uint8_t *>(smem + 25 * G::CSTRIDE + (size_t)(blockDim.x >> 3) * TILE_WORDS);   // [GL*K]
+    uint32_t *gbase = smem + 25 * G::CSTRIDE + (size_t)(warp * 4 + g) * TG::GROUP_WORDS;
+    uint32_t *tile = gbase;
+    uint8_t *codes = reinterpret_cast<uint8_t *>(gbase + 2 * HALF_WORDS);   // [half][slot][CB + 1]
+    uint8_t *trash_code = codes + 2 * NLW * (CB + 1);
+    uint32_t *trash = gbase + 2 * HALF_WORDS + TG::CODE_WORDS;
+    uint8_t *rcodes_s = reinterpret_cast<uint8_t *>(smem + 25 * G::CSTRIDE + (size_t)(blockDim.x >> 3) * TG::GROUP_WORDS);   // [GL*K]
     const uint32_t g2 = pack2(P.gap, P.gap);
+    const int my_prof = t * G::KS;
+
     const uint32_t c_lo = blockIdx.x * (uint32_t)chunk;
     const uint32_t c_hi = min(n_cells, c_lo + (uint32_t)chunk);
     uint32_t seg_lo = c_lo;
@@ -342,7 +341,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 const bool idle = h ? !busy1 : !busy0;
                 uint32_t e = 0xffffffffu;
                 if (idle && t == h) e = atomicAdd(&seg_next, 1u);
-                e = __shfl_sync(gmask, e, h, GL);
+                e = __shfl_sync(FULL, e, h, GL);
                 if (idle && e < seg_hi) {
                     const uint64_t key = keys[e];
                     const int ro = (int)(key_pair(key) - (uint64_t)slot * (uint64_t)P.n_refs);
@@ -358,17 +357,25 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                     }
                 }
             }
-            if (!__any_sync(0xffffffffu, busy0 || busy1)) break;
+            if (!__any_sync(FULL, busy0 || busy1)) break;
 
             // ---- block of each half, checkpoint -> registers ---------------------------------
-            const int b0 = busy0 ? (cj0 - 1 + (ci0 - 1) / K) / CB : 0;
-            const int b1 = busy1 ? (cj1 - 1 + (ci1 - 1) / K) / CB : 0;
-            // window of lanes whose columns the walk of each half may read: [tc - NLW + 1, tc]
             const int tca = (ci0 - 1) / K, tcb = (ci1 - 1) / K;
-            const int sa = busy0 ? t - (tca - NLW + 1) : -1;          // this lane's slot in half 0's tile, if any
+            const int b0 = busy0 ? (cj0 - 1 + tca) / CB : 0;
+            const int b1 = busy1 ? (cj1 - 1 + tcb) / CB : 0;
+            // this lane's slot in each half's window [tc - NLW + 1, tc]; outside: the trash column
+            const int sa = busy0 ? t - (tca - NLW + 1) : -1;
             const int sb = busy1 ? t - (tcb - NLW + 1) : -1;
-            uint32_t *tileA = (sa >= 0 && sa < NLW) ? tile + (size_t)sa * (CB + 1) * KH : nullptr;
-            uint32_t *tileB = (sb >= 0 && sb < NLW) ? tile + HALF_WORDS + (size_t)sb * (CB + 1) * KH : nullptr;
+            const bool ina = sa >= 0 && sa < NLW, inb = sb >= 0 && sb < NLW;
+            // ONE packed column store per lane and step (shared-memory bandwidth is this kernel's tightest
+            // resource): physical slots 0..NLW-1 hold half 0's window, NLW..2NLW-1 the lanes that are only in
+            // half 1's window; a lane in both windows lives in half 0's slot and half 1's walker looks it up there
+            const int phys = ina ? sa : (inb ? NLW + sb : -1);
+            uint32_t *pa = phys >= 0 ? tile + (size_t)phys * (CB + 1) * KW : trash;
+            uint8_t *qa = ina ? codes + sa * (CB + 1) : trash_code;
+            uint8_t *qb = inb ? codes + (NLW + sb) * (CB + 1) : trash_code;
+            const int inca = phys >= 0 ? KW : 0, incqa = ina ? 1 : 0, incqb = inb ? 1 : 0;
+
             uint32_t H[K], diag = 0;
             {
                 const uint4 *ckA = reinterpret_cast<const uint4 *>(P.ck + (bk0 + b0) * (int64_t)(KW * GL)) + t;
@@ -411,40 +418,56 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 ulo1 = -j1; uhi1 = busy1 ? n1 - j1 - 1 : -1;
             }
             // halo column c = 0
-            {
-                uint32_t v[KW];
-                v[0] = diag;
+            store_col<K>(pa, diag, H);
+            pa += inca; qa += incqa; qb += incqb;
+
+            // interior block: every step of every lane / half is a real column -> no per-step validity tests
+            const bool interior = ulo0 <= 0 && uhi0 >= CB - 1 && ulo1 <= 0 && uhi1 >= CB - 1;
+            if (__all_sync(FULL, interior)) {
+#pragma unroll 4
+                for (int u = 0; u < CB; ++u) {
+                    uint32_t top = __shfl_up_sync(FULL, H[K - 1], 1, GL);
+                    if (t == 0) top = 0;
+                    const uint32_t ca = (win0 >> (2 * u)) & 3u, cb = (win1 >> (2 * u)) & 3u;
+                    uint32_t sv[G::KP];
+                    load_profile<G::KP>(prof2 + (ca * 5 + cb) * G::CSTRIDE + my_prof, sv);
+                    uint32_t nw = diag, nn = top;
 #pragma unroll
-                for (int r = 0; r < K; ++r) v[r + 1] = H[r];
-#pragma unroll
-                for (int r = K + 1; r < KW; ++r) v[r] = 0;
-                store_column<KW, KH>(tileA, tileB, 0, v, 0x00040004u);
-            }
-#pragma unroll 2   // measured: unroll 1 / 2 / 4 -> 17.6 / 15.7 / 17.5 ms per step
-            for (int u = 0; u < CB; ++u) {
-                uint32_t top = __shfl_up_sync(gmask, H[K - 1], 1, GL);
-                if (t == 0) top = 0;
-                const int ca = (u >= ulo0 && u <= uhi0) ? (int)((win0 >> (2 * u)) & 3u) : 4;
-                const int cb = (u >= ulo1 && u <= uhi1) ? (int)((win1 >> (2 * u)) & 3u) : 4;
-                uint32_t sv[G::KP];
-                load_profile<G::KP>(prof2 + (ca * 5 + cb) * G::CSTRIDE + t * G::KS, sv);
-                uint32_t nw = diag, nn = top;
-#pragma unroll
-                for (int r = 0; r < K; ++r) {
-                    const uint32_t x = viaddmax_relu(nw, sv[r], zero);
-                    const uint32_t pre = viaddmax(H[r], g2, x);
-                    nw = H[r];
-                    H[r] = viaddmax(nn, g2, pre);
-                    nn = H[r];
+                    for (int r = 0; r < K; ++r) {
+                        const uint32_t x = viaddmax_relu(nw, sv[r], zero);
+                        const uint32_t pre = viaddmax(H[r], g2, x);
+                        nw = H[r];
+                        H[r] = viaddmax(nn, g2, pre);
+                        nn = H[r];
+                    }
+                    diag = top;
+                    store_col<K>(pa, top, H);
+                    *qa = (uint8_t)ca; *qb = (uint8_t)cb;
+                    pa += inca; qa += incqa; qb += incqb;
                 }
-                diag = top;
-                uint32_t v[KW];
-                v[0] = top;
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < CB; ++u) {
+                    uint32_t top = __shfl_up_sync(FULL, H[K - 1], 1, GL);
+                    if (t == 0) top = 0;
+                    const uint32_t ca = (u >= ulo0 && u <= uhi0) ? ((win0 >> (2 * u)) & 3u) : 4u;
+                    const uint32_t cb = (u >= ulo1 && u <= uhi1) ? ((win1 >> (2 * u)) & 3u) : 4u;
+                    uint32_t sv[G::KP];
+                    load_profile<G::KP>(prof2 + (ca * 5 + cb) * G::CSTRIDE + my_prof, sv);
+                    uint32_t nw = diag, nn = top;
 #pragma unroll
-                for (int r = 0; r < K; ++r) v[r + 1] = H[r];
-#pragma unroll
-                for (int r = K + 1; r < KW; ++r) v[r] = 0;
-                store_column<KW, KH>(tileA, tileB, u + 1, v, (uint32_t)ca | ((uint32_t)cb << 16));
+                    for (int r = 0; r < K; ++r) {
+                        const uint32_t x = viaddmax_relu(nw, sv[r], zero);
+                        const uint32_t pre = viaddmax(H[r], g2, x);
+                        nw = H[r];
+                        H[r] = viaddmax(nn, g2, pre);
+                        nn = H[r];
+                    }
+                    diag = top;
+                    store_col<K>(pa, top, H);
+                    *qa = (uint8_t)ca; *qb = (uint8_t)cb;
+                    pa += inca; qa += incqa; qb += incqb;
+                }
             }
             __syncwarp();
 
@@ -455,20 +478,30 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 int ci = h ? ci1 : ci0, cj = h ? cj1 : cj0;
                 const int b = h ? b1 : b0;
                 const int lane_lo = (h ? tcb : tca) - NLW + 1;              // first lane held in this half's tile
-                const uint32_t *th = tile + h * HALF_WORDS;
+                const int16_t *T16 = reinterpret_cast<const int16_t *>(tile);   // halfword 2*w + h of packed word w
+                // physical slot of window position s of this half (see the store side)
+                const int a_lo = tca - NLW + 1;
+                auto phys_of = [&](int s_) -> int {
+                    if (h == 0) return s_;
+                    const int in_a = (lane_lo + s_) - a_lo;                 // half 1's lane, as a position in half 0's window
+                    return (busy0 && in_a >= 0 && in_a < NLW) ? in_a : NLW + s_;
+                };
+                const uint8_t *tcodes = codes + h * NLW * (CB + 1);
                 uint32_t *myops = ops + (size_t)w_cell * ops_stride;
+                // position inside the tile, kept incrementally (no divisions in the loop):
+                //   sl = slot of the cell's lane, c = its column index there, r = row inside the lane (1..K)
+                const int tc0 = (ci - 1) / K;
+                int r = ci - tc0 * K;
+                int c = cj - (b * CB - tc0);
+                int sl = tc0 - lane_lo;
+                int idx = sl >= 0 ? 2 * ((phys_of(sl) * (CB + 1) + c) * KW + r) + h : 0;   // halfword index of (sl, c, r)
+                int cidx = sl * (CB + 1) + c;
                 while (w_h > 0) {
-                    const int tc = (ci - 1) / K;
-                    const int r = ci - tc * K;                              // 1..K
-                    const int c = cj - (b * CB - tc);                       // column index in lane tc's tile
-                    const int sl = tc - lane_lo;
-                    if (c < 1 || c > CB || sl < 0) break;                   // outside what this block holds
-                    const int16_t *lt = reinterpret_cast<const int16_t *>(th + ((size_t)sl * (CB + 1) + c) * KH) + r;
-                    const int hw = lt[-2 * KH];                             // W  = (c-1, r)
-                    const int hn = lt[-1];                                  // N  = (c, r-1)
-                    const int hnw = lt[-2 * KH - 1];                        // NW = (c-1, r-1)
-                    const int rc = lt[KW - r];                              // reference code of this column (halfword KW)
-                    const int sc = ((int)rcodes_s[ci - 1] == rc) ? P.match : P.mismatch;
+                    if (c < 1 || sl < 0) break;                             // outside what this block holds
+                    const int hw = T16[idx - 2 * KW];                       // W  = (c-1, r)
+                    const int hn = T16[idx - 2];                            // N  = (c, r-1)
+                    const int hnw = T16[idx - 2 * KW - 2];                  // NW = (c-1, r-1)
+                    const int sc = ((int)rcodes_s[ci - 1] == (int)tcodes[cidx]) ? P.match : P.mismatch;
                     // type of a positive cell = first of (alignment, insertion, deletion) whose candidate
                     // equals H: the ">=" cascade of GetCellScore.call.  Branch-free: both walkers of a
                     // warp's groups stay converged.
@@ -477,8 +510,16 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                     const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
                     w_beg = cj;
                     w_h = op == 1u ? hnw : (op == 2u ? hn : hw);
-                    ci -= (op != 3u);
-                    cj -= (op != 2u);
+                    const int up = (op != 3u), left = (op != 2u);
+                    ci -= up; cj -= left;
+                    r -= up; c -= left;
+                    idx -= 2 * up + 2 * KW * left;
+                    cidx -= left;
+                    if (r == 0) {                                           // into the lane above: same matrix column is one tile column further left
+                        r = K; --sl; --c;
+                        idx = sl >= 0 ? 2 * ((phys_of(sl) * (CB + 1) + c) * KW + r) + h : 0;
+                        cidx -= (CB + 1) + 1;
+                    }
                     w_opword |= op << (2 * (w_len & 15));
                     ++w_len;
                     if ((w_len & 15) == 0) { myops[(w_len >> 4) - 1] = w_opword; w_opword = 0; }
@@ -492,9 +533,9 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                 wi = ci; wj = cj;
             }
             {
-                const int d0 = __shfl_sync(gmask, done, 0, GL), d1 = __shfl_sync(gmask, done, 1, GL);
-                const int i0 = __shfl_sync(gmask, wi, 0, GL), j0 = __shfl_sync(gmask, wj, 0, GL);
-                const int i1 = __shfl_sync(gmask, wi, 1, GL), j1 = __shfl_sync(gmask, wj, 1, GL);
+                const int d0 = __shfl_sync(FULL, done, 0, GL), d1 = __shfl_sync(FULL, done, 1, GL);
+                const int i0 = __shfl_sync(FULL, wi, 0, GL), j0 = __shfl_sync(FULL, wj, 0, GL);
+                const int i1 = __shfl_sync(FULL, wi, 1, GL), j1 = __shfl_sync(FULL, wj, 1, GL);
                 if (busy0) { ci0 = i0; cj0 = j0; if (d0) busy0 = false; }
                 if (busy1) { ci1 = i1; cj1 = j1; if (d1) busy1 = false; }
             }
@@ -510,11 +551,12 @@ static cudaError_t launch_trace_k(const BatchParams &P, const uint64_t *keys, ui
 {
     using G = Geo<K>;
     if (n_cells == 0) return cudaSuccess;
-    const size_t per_group = (size_t)2 * TraceGeo<K>::NLW * (CB + 1) * TraceGeo<K>::KH * sizeof(uint32_t);
+    const size_t per_group = (size_t)TraceGeo<K>::GROUP_WORDS * sizeof(uint32_t);
     const size_t prof_bytes = (size_t)25 * G::CSTRIDE * sizeof(uint32_t);
+    const size_t tail_bytes = (((size_t)GL * K + 15) / 16) * 16;
     int warps = 4;
-    while (warps > 1 && prof_bytes + per_group * 4 * warps + 512 > 74 * 1024) --warps;   // three CTAs per SM
-    const size_t smem = prof_bytes + per_group * 4 * warps + (((size_t)GL * K + 15) / 16) * 16;
+    while (warps > 1 && prof_bytes + per_group * 4 * warps + tail_bytes > 112 * 1024) --warps;   // two CTAs per SM
+    const size_t smem = prof_bytes + per_group * 4 * warps + tail_bytes;
     static bool attr_set[64] = {false};
     if (!attr_set[K]) {
         cudaError_t e = cudaFuncSetAttribute(trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
