@@ -330,7 +330,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
         int ci0 = 0, cj0 = 0, ci1 = 0, cj1 = 0, n0 = 0, n1 = 0;
         const uint32_t *rw0 = P.ref_words, *rw1 = P.ref_words;
         int64_t bk0 = 0, bk1 = 0;
-        // walker state (lane 0 -> half 0, lane 1 -> half 1)
+        // walker state, replicated in the 4 lanes of a half's walk team (lanes 0-3: half 0, 4-7: half 1);
+        // the team leader (lane 0 / 4) writes the results
         uint32_t w_cell = 0, w_opword = 0;
         int w_h = 0, w_beg = 0, w_len = 0;
 
@@ -340,8 +341,8 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
             for (int h = 0; h < 2; ++h) {
                 const bool idle = h ? !busy1 : !busy0;
                 uint32_t e = 0xffffffffu;
-                if (idle && t == h) e = atomicAdd(&seg_next, 1u);
-                e = __shfl_sync(FULL, e, h, GL);
+                if (idle && t == 4 * h) e = atomicAdd(&seg_next, 1u);
+                e = __shfl_sync(FULL, e, 4 * h, GL);
                 if (idle && e < seg_hi) {
                     const uint64_t key = keys[e];
                     const int ro = (int)(key_pair(key) - (uint64_t)slot * (uint64_t)P.n_refs);
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                                   bk0 = (int64_t)(slot >> 1) * P.blocks_per_rp + P.ref_blk_off[ref]; }
                     else        { busy1 = true; ci1 = ii; cj1 = jj; n1 = P.ref_len[ref]; rw1 = P.ref_words + P.ref_word_off[ref];
                                   bk1 = (int64_t)(slot >> 1) * P.blocks_per_rp + P.ref_blk_off[ref]; }
-                    if (t == h) {
+                    if ((t >> 2) == h) {                             // the 4 lanes of this half's walk team
                         w_cell = e; w_opword = 0; w_beg = 0; w_len = 0;
                         w_h = P.scores[(int64_t)ro * P.n_reads + read_idx];
                     }
@@ -471,71 +472,96 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
             }
             __syncwarp();
 
-            // ---- walk: lane 0 walks half 0, lane 1 walks half 1 -------------------------------
-            int done = 0, wi = 0, wj = 0;
-            if (t < 2 && (t ? busy1 : busy0)) {
-                const int h = t;
-                int ci = h ? ci1 : ci0, cj = h ? cj1 : cj0;
-                const int b = h ? b1 : b0;
-                const int lane_lo = (h ? tcb : tca) - NLW + 1;              // first lane held in this half's tile
-                const int16_t *T16 = reinterpret_cast<const int16_t *>(tile);   // halfword 2*w + h of packed word w
-                // physical slot of window position s of this half (see the store side)
-                const int a_lo = tca - NLW + 1;
-                auto phys_of = [&](int s_) -> int {
-                    if (h == 0) return s_;
-                    const int in_a = (lane_lo + s_) - a_lo;                 // half 1's lane, as a position in half 0's window
-                    return (busy0 && in_a >= 0 && in_a < NLW) ? in_a : NLW + s_;
-                };
-                const uint8_t *tcodes = codes + h * NLW * (CB + 1);
-                uint32_t *myops = ops + (size_t)w_cell * ops_stride;
-                // position inside the tile, kept incrementally (no divisions in the loop):
-                //   sl = slot of the cell's lane, c = its column index there, r = row inside the lane (1..K)
-                const int tc0 = (ci - 1) / K;
-                int r = ci - tc0 * K;
-                int c = cj - (b * CB - tc0);
-                int sl = tc0 - lane_lo;
-                int idx = sl >= 0 ? 2 * ((phys_of(sl) * (CB + 1) + c) * KW + r) + h : 0;   // halfword index of (sl, c, r)
-                int cidx = sl * (CB + 1) + c;
-                while (w_h > 0) {
-                    if (c < 1 || sl < 0) break;                             // outside what this block holds
-                    const int hw = T16[idx - 2 * KW];                       // W  = (c-1, r)
-                    const int hn = T16[idx - 2];                            // N  = (c, r-1)
-                    const int hnw = T16[idx - 2 * KW - 2];                  // NW = (c-1, r-1)
-                    const int sc = ((int)rcodes_s[ci - 1] == (int)tcodes[cidx]) ? P.match : P.mismatch;
-                    // type of a positive cell = first of (alignment, insertion, deletion) whose candidate
-                    // equals H: the ">=" cascade of GetCellScore.call.  Branch-free: both walkers of a
-                    // warp's groups stay converged.
-                    // (SWB_F_TIE_GT: DistributedSW's strict ">" cascade -- first of deletion, insertion, alignment.)
-                    const bool eq_a = (hnw + sc == w_h), eq_i = (hn + P.gap == w_h), eq_d = (hw + P.gap == w_h);
-                    const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
-                    w_beg = cj;
-                    w_h = op == 1u ? hnw : (op == 2u ? hn : hw);
-                    const int up = (op != 3u), left = (op != 2u);
-                    ci -= up; cj -= left;
-                    r -= up; c -= left;
-                    idx -= 2 * up + 2 * KW * left;
-                    cidx -= left;
-                    if (r == 0) {                                           // into the lane above: same matrix column is one tile column further left
-                        r = K; --sl; --c;
-                        idx = sl >= 0 ? 2 * ((phys_of(sl) * (CB + 1) + c) * KW + r) + h : 0;
-                        cidx -= (CB + 1) + 1;
+            // ---- walk (GetAlignment.call, SmithWaterman.java:380-409), four lanes per half ----------------
+            // Lane q of a team looks at the cell q steps up the diagonal from the current one and derives ITS
+            // move from the tile.  Alignment paths are mostly diagonal, so a ballot finds the run of leading
+            // "alignment" moves and the whole run (plus the first gap move after it) is applied in one round:
+            // ~3 path steps per round instead of one load -> compare -> select chain per step.
+            const int h = t >> 2, q = t & 3;
+            const bool mybusy = h ? busy1 : busy0;
+            int ci = h ? ci1 : ci0, cj = h ? cj1 : cj0;
+            const int b = h ? b1 : b0;
+            const int lane_lo = (h ? tcb : tca) - NLW + 1;              // first lane held in this half's window
+            const int a_lo = tca - NLW + 1;
+            const int16_t *T16 = reinterpret_cast<const int16_t *>(tile);   // halfword 2*w + h of packed word w
+            const uint8_t *tcodes = codes + h * NLW * (CB + 1);
+            auto phys_of = [&](int s_) -> int {                           // physical slot of window position s_
+                if (h == 0) return s_;
+                const int in_a = (lane_lo + s_) - a_lo;
+                return (busy0 && in_a >= 0 && in_a < NLW) ? in_a : NLW + s_;
+            };
+            // position of the current cell inside the tile, kept incrementally
+            const int tc0 = (ci - 1) / K;
+            int r = ci - tc0 * K;                                        // 1..K
+            int c = cj - (b * CB - tc0);
+            int sl = tc0 - lane_lo;
+            bool walking = mybusy;                                        // this half still walks in this block
+            int done = 0;
+            const int team = lane & ~3;
+            while (__any_sync(FULL, walking)) {
+                // my cell: q steps up the diagonal
+                int r_q = r - q, sl_q = sl, c_q = c - q;
+                if (r_q <= 0) { r_q += K; --sl_q; --c_q; }
+                const int ci_q = ci - q, cj_q = cj - q;
+                const bool in = walking && ci_q >= 1 && cj_q >= 1 && c_q >= 1 && sl_q >= 0;
+                int hc = 0, hw = 0, hn = 0, hnw = 0, rc = 0, qc = 1;
+                if (in) {
+                    const int idx = 2 * ((phys_of(sl_q) * (CB + 1) + c_q) * KW + r_q) + h;
+                    hc = T16[idx]; hw = T16[idx - 2 * KW]; hn = T16[idx - 2]; hnw = T16[idx - 2 * KW - 2];
+                    rc = tcodes[sl_q * (CB + 1) + c_q];
+                    qc = rcodes_s[ci_q - 1];
+                }
+                const int sc = (qc == rc) ? P.match : P.mismatch;
+                // type of a positive cell = first of (alignment, insertion, deletion) whose candidate equals H:
+                // the ">=" cascade of GetCellScore.call; SWB_F_TIE_GT: first of (deletion, insertion, alignment)
+                const bool eq_a = (hnw + sc == hc), eq_i = (hn + P.gap == hc), eq_d = (hw + P.gap == hc);
+                const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
+                const bool alive = in && hc > 0;
+                const int hnext = op == 1u ? hnw : (op == 2u ? hn : hw);
+                const uint32_t bal = (__ballot_sync(FULL, alive && op == 1u) >> team) & 0xFu;
+                const int n_a = __ffs((int)(~bal & 0x1Fu)) - 1;         // leading alignment moves: 0..4
+                const int src = team + min(n_a, 3);
+                const bool alive_s = __shfl_sync(FULL, (int)alive, src) != 0;
+                const uint32_t op_s = __shfl_sync(FULL, op, src);
+                const int hnext_s = __shfl_sync(FULL, hnext, src);
+                const int hnw_prev = __shfl_sync(FULL, hnw, team + max(n_a - 1, 0));
+                const bool extra = n_a < 4 && alive_s;                   // lane n_a's own (gap) move is applied too
+                const int steps = n_a + (extra ? 1 : 0);
+                if (walking) {
+                    if (steps == 0) {
+                        // the current cell is outside what this block holds (or its score is 0: cannot happen here)
+                        walking = false;
+                    } else {
+                        const int up = extra ? (op_s != 3u) : 0, left = extra ? (op_s != 2u) : 0;
+                        w_beg = extra ? cj - n_a : cj - n_a + 1;        // column of the last cell that made a move
+                        const uint64_t bits = (n_a ? (0x55ull >> (8 - 2 * n_a)) : 0ull) | (extra ? (uint64_t)op_s << (2 * n_a) : 0ull);
+                        const uint64_t acc = (uint64_t)w_opword | (bits << (2 * (w_len & 15)));
+                        const int nl = w_len + steps;
+                        if ((nl >> 4) != (w_len >> 4)) {                 // a 16-column word is complete
+                            if (q == 0) ops[(size_t)w_cell * ops_stride + (w_len >> 4)] = (uint32_t)acc;
+                            w_opword = (uint32_t)(acc >> 32);
+                        } else {
+                            w_opword = (uint32_t)acc;
+                        }
+                        w_len = nl;
+                        w_h = extra ? hnext_s : ((n_a == 4) ? hnext_s : hnw_prev);
+                        ci -= n_a + up; cj -= n_a + left;
+                        r -= n_a + up; c -= n_a + left;
+                        if (r <= 0) { r += K; --sl; --c; }
+                        if (r <= 0) { r += K; --sl; --c; }
+                        if (w_h <= 0) { walking = false; done = 1; }
                     }
-                    w_opword |= op << (2 * (w_len & 15));
-                    ++w_len;
-                    if ((w_len & 15) == 0) { myops[(w_len >> 4) - 1] = w_opword; w_opword = 0; }
                 }
-                if (w_h <= 0) {
-                    if (w_len & 15) myops[w_len >> 4] = w_opword;
-                    beginnings[w_cell] = w_beg;
-                    op_lens[w_cell] = w_len;
-                    done = 1;
-                }
-                wi = ci; wj = cj;
+            }
+            if (done && q == 0) {
+                if (w_len & 15) ops[(size_t)w_cell * ops_stride + (w_len >> 4)] = w_opword;
+                beginnings[w_cell] = w_beg;
+                op_lens[w_cell] = w_len;
             }
             {
-                const int d0 = __shfl_sync(FULL, done, 0, GL), d1 = __shfl_sync(FULL, done, 1, GL);
-                const int i0 = __shfl_sync(FULL, wi, 0, GL), j0 = __shfl_sync(FULL, wj, 0, GL);
-                const int i1 = __shfl_sync(FULL, wi, 1, GL), j1 = __shfl_sync(FULL, wj, 1, GL);
+                const int d0 = __shfl_sync(FULL, done, 0, GL), d1 = __shfl_sync(FULL, done, 4, GL);
+                const int i0 = __shfl_sync(FULL, ci, 0, GL), j0 = __shfl_sync(FULL, cj, 0, GL);
+                const int i1 = __shfl_sync(FULL, ci, 4, GL), j1 = __shfl_sync(FULL, cj, 4, GL);
                 if (busy0) { ci0 = i0; cj0 = j0; if (d0) busy0 = false; }
                 if (busy1) { ci1 = i1; cj1 = j1; if (d1) busy1 = false; }
             }
