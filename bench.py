@@ -47,6 +47,8 @@ def parse():
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workspace-gb", type=float, default=16.0)
+    ap.add_argument("--refs-per-gpu", type=int, default=N_REFS_PER_GPU,
+                    help="10000 = BASELINE config 2 per GPU; 15402 x 8 GPUs = config 4 (123,212 refs, ~266 Mbp)")
     return ap.parse_args()
 
 
@@ -206,7 +208,7 @@ def main():
 
     B, K, W = args.reads_per_step, args.steps, args.warmup
     # weak scaling: 10k refs per GPU; every rank generates the same global set and keeps its shard
-    all_refs = synth.make_refs(N_REFS_PER_GPU * world)
+    all_refs = synth.make_refs(args.refs_per_gpu * world)
     refs, my_ids = shard_refs(all_refs, rank, world)
     reads_pool = synth.make_reads(B * (W + K), READ_LEN, all_refs)
     step_reads = [reads_pool[k * B:(k + 1) * B] for k in range(W + K)]
@@ -354,7 +356,7 @@ def main():
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "s16x2", "data": "synthetic",
-            "config": {"workload": "cfg2: 150 bp reads vs 10,000 RefSeq-shaped refs per GPU, scores 5/-3/-4; "
+            "config": {"workload": f"cfg2: 150 bp reads vs {args.refs_per_gpu:,} RefSeq-shaped refs per GPU, scores 5/-3/-4; "
                                    f"step = {B} reads of the 100k-read job x all refs, fill + all max cells + traceback",
                        "reads_per_step": B, "refs_per_gpu": len(refs), "ref_bases_per_gpu": int(ref_bases),
                        "pairs_per_step": B * len(refs) * world,
