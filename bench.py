@@ -46,7 +46,7 @@ def parse():
     ap.add_argument("--reads-per-step", type=int, default=128)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workspace-gb", type=float, default=16.0)
+    ap.add_argument("--workspace-gb", type=float, default=64.0)
     ap.add_argument("--refs-per-gpu", type=int, default=N_REFS_PER_GPU,
                     help="10000 = BASELINE config 2 per GPU; 15402 x 8 GPUs = config 4 (123,212 refs, ~266 Mbp)")
     return ap.parse_args()
