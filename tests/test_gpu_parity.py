@@ -81,3 +81,18 @@ def test_long_references_are_segmented_exactly(engine):
     reads += [base[950:1010] + base[1030:1100], "AT" * 75, base[2000:2100] + "ACGTACGT" + base[2100:2140]]
     check_pairs(engine, refs, reads)
     check_pairs(engine, refs[:2], reads[:5], (2, -1, -1))                           # wide windows: W = m + 2m
+
+
+def test_long_gap_runs_leave_the_trace_window(engine):
+    """Cheap gaps give alignments with long vertical / horizontal runs: the walk leaves the lanes a
+    traceback block keeps (re-anchoring) and crosses many blocks without a diagonal step."""
+    rnd = random.Random(91)
+    base = "".join(rnd.choice("ACGT") for _ in range(1500))
+    ins = "".join(rnd.choice("ACGT") for _ in range(60))
+    reads = [base[100:170] + ins + base[170:240],                    # 60-row insertion run
+             base[400:460] + base[560:640],                          # 100-column deletion run
+             base[700:730] + ins[:45] + base[730:760] + ins[10:50] + base[760:800],
+             ("ACGT" * 60)[:230], "A" * 40 + base[900:1000] + "T" * 60]
+    refs = [base, base[50:900], "ACGT" * 300, base[::-1]]
+    for scores in ((5, -4, -1), (4, -6, -1), (3, -2, -1), (10, -9, -1)):
+        check_pairs(engine, refs, reads, scores, max_cells=200)
