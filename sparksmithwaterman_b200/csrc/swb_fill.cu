@@ -102,6 +102,14 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
             wprev = wnew;
             const bool fast = (s0 >= GL - 1) && (s0 + 16 <= nmin);
 
+            // SEAMS: the boundary row this lane receives at every step (matrix row t*K) goes to HBM next to
+            // the block checkpoints, so that the traceback can recompute ONE lane's tile (K rows x CB steps)
+            // without the lanes above it.  Layout per block: [CB/4 quads][GL lanes][4 steps], one STG.128 per
+            // lane every 4 steps = 128 contiguous bytes per group.  Only for blocks this segment owns.
+            const bool own_chunk = (s0 < my_steps) && ((s0 >> 4) >= skip);
+            uint32_t *sq = P.seam + (blk0 + (s0 >> 4)) * (int64_t)(CB * GL) + t * 4;
+            uint32_t t0 = 0, t1 = 0, t2 = 0;
+
             if (fast) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
@@ -120,29 +128,37 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
                     }
                     diag = top;
                     tmax = colmax<K>(tmax, H);
+                    if ((u & 3) == 0) t0 = top; else if ((u & 3) == 1) t1 = top; else if ((u & 3) == 2) t2 = top;
+                    else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (u >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
                 }
             } else {
 #pragma unroll 1
-                for (int u = 0; u < 16; ++u) {
-                    const int s = s0 + u;
-                    const uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1) & lmask;
-                    const uint32_t c = (win >> (2 * u)) & 3u;
-                    const bool valid = (s >= t) && (s < n_g + t);        // column j = s-t+1 in [1, n_g]
-                    if (valid) {
-                        uint32_t sv[G::KP];
-                        load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
-                        uint32_t nw = diag, nn = top;
+                for (int uq = 0; uq < 16; uq += 4) {
 #pragma unroll
-                        for (int r = 0; r < K; ++r) {
-                            const uint32_t x = viaddmax_relu(nw, sv[r], zero);
-                            const uint32_t pre = viaddmax(H[r], g2, x);
-                            nw = H[r];
-                            H[r] = viaddmax(nn, g2, pre);
-                            nn = H[r];
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int u = uq + uu;
+                        const int s = s0 + u;
+                        const uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1) & lmask;
+                        const uint32_t c = (win >> (2 * u)) & 3u;
+                        const bool valid = (s >= t) && (s < n_g + t);        // column j = s-t+1 in [1, n_g]
+                        if (valid) {
+                            uint32_t sv[G::KP];
+                            load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
+                            uint32_t nw = diag, nn = top;
+#pragma unroll
+                            for (int r = 0; r < K; ++r) {
+                                const uint32_t x = viaddmax_relu(nw, sv[r], zero);
+                                const uint32_t pre = viaddmax(H[r], g2, x);
+                                nw = H[r];
+                                H[r] = viaddmax(nn, g2, pre);
+                                nn = H[r];
+                            }
+                            tmax = colmax<K>(tmax, H);
                         }
-                        tmax = colmax<K>(tmax, H);
+                        diag = top;
+                        if (uu == 0) t0 = top; else if (uu == 1) t1 = top; else if (uu == 2) t2 = top;
+                        else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (uq >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
                     }
-                    diag = top;
                 }
             }
 

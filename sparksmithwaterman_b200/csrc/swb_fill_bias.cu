@@ -116,6 +116,12 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
             wprev = wnew;
             const bool fast = (s0 >= GL - 1) && (s0 + 16 <= nmin);
 
+            // SEAMS (see swb_fill.cu): the boundary row this lane receives at every step, stored BIASED -- the
+            // bias of step u of a block is |gap| * (9 - t + u) in both halves (P.seam_bias tells the traceback).
+            const bool own_chunk = (s0 < my_steps) && ((s0 >> 4) >= skip);
+            uint32_t *sq = P.seam + (blk0 + (s0 >> 4)) * (int64_t)(CB * GL) + t * 4;
+            uint32_t t0 = 0, t1 = 0, t2 = 0;
+
             if (fast) {
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
@@ -137,36 +143,44 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     }
                     diag = top;
                     tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
+                    if ((u & 3) == 0) t0 = top; else if ((u & 3) == 1) t1 = top; else if ((u & 3) == 2) t2 = top;
+                    else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (u >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
                 }
             } else {
 #pragma unroll 1
-                for (int u = 0; u < 16; ++u) {
-                    const int s = s0 + u;
-                    floorv = imad_add(floorv, one, gpos);
-                    negfloor = viadd2(negfloor, g2);
-                    uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
-                    if (t == 0) top = floorv;
-                    const uint32_t c = (win >> (2 * u)) & 3u;
-                    const bool valid = (s >= t) && (s < n_g + t);
-                    if (valid) {
-                        uint32_t sv[G::KP];
-                        load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
-                        uint32_t nw = diag, nn = top;
+                for (int uq = 0; uq < 16; uq += 4) {
 #pragma unroll
-                        for (int r = 0; r < K; ++r) {
-                            const uint32_t tt = imad_add(nw, one, sv[r]);
-                            const uint32_t pre = vmax3(tt, H[r], floorv);
-                            nw = H[r];
-                            H[r] = viaddmax(nn, g2, pre);
-                            nn = H[r];
+                    for (int uu = 0; uu < 4; ++uu) {
+                        const int u = uq + uu;
+                        const int s = s0 + u;
+                        floorv = imad_add(floorv, one, gpos);
+                        negfloor = viadd2(negfloor, g2);
+                        uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
+                        if (t == 0) top = floorv;
+                        const uint32_t c = (win >> (2 * u)) & 3u;
+                        const bool valid = (s >= t) && (s < n_g + t);
+                        if (valid) {
+                            uint32_t sv[G::KP];
+                            load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
+                            uint32_t nw = diag, nn = top;
+#pragma unroll
+                            for (int r = 0; r < K; ++r) {
+                                const uint32_t tt = imad_add(nw, one, sv[r]);
+                                const uint32_t pre = vmax3(tt, H[r], floorv);
+                                nw = H[r];
+                                H[r] = viaddmax(nn, g2, pre);
+                                nn = H[r];
+                            }
+                            tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);
+                        } else {
+                            // outside the matrix: the column is all zero (left of it) or never read (right of it)
+#pragma unroll
+                            for (int r = 0; r < K; ++r) H[r] = floorv;
                         }
-                        tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);
-                    } else {
-                        // outside the matrix: the column is all zero (left of it) or never read (right of it)
-#pragma unroll
-                        for (int r = 0; r < K; ++r) H[r] = floorv;
+                        diag = top;
+                        if (uu == 0) t0 = top; else if (uu == 1) t1 = top; else if (uu == 2) t2 = top;
+                        else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (uq >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
                     }
-                    diag = top;
                 }
             }
 

@@ -24,6 +24,7 @@ namespace swb {
 constexpr int GL = 8;        // lanes per group
 constexpr int CB = 16;       // steps per checkpoint block (multiple of 16; the trace kernel's code window needs 16)
 constexpr int MAX_SHORT_ROWS = GL * 32;
+static_assert(CB == 16, "the fill kernels store one seam quad per 4 steps of a 16-step chunk");
 
 // rows-per-lane variants compiled for the short path
 constexpr int kNumK = 7;
@@ -80,6 +81,8 @@ struct BatchParams {
     int32_t  *scores;               // [n_refs_orig * n_reads]
     uint32_t *ck;                   // checkpoints  [n_rp][blocks_per_rp][KW/4][GL][4]
     uint32_t *tmx;                  // tile maxima  [n_rp][blocks_per_rp][GL]
+    uint32_t *seam;                 // lane seams   [n_rp][blocks_per_rp][CB/4][GL][4]: boundary row received per step
+    int32_t seam_bias;              // seam word of step u, lane t = H + seam_bias * (9 - t + u) (biased fill), 0 = plain
 };
 
 // ---- general ("wide") int32 path: bands of 32 lanes x KL rows, see swb_wide.cu ------------------
@@ -160,6 +163,11 @@ cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, co
 cudaError_t launch_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells,
                          int32_t *beginnings, int32_t *op_lens, uint32_t *ops, int ops_stride_words,
                          int sm_count, cudaStream_t st);
+// swb_trace_tile.cu: one thread per max cell, single-lane tiles from checkpoint + seam (default when the scores allow)
+cudaError_t launch_tile_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells,
+                              int32_t *beginnings, int32_t *op_lens, uint32_t *ops, int ops_stride_words,
+                              int sm_count, cudaStream_t st);
+bool tile_trace_ok(int match, int mismatch, int gap);
 cudaError_t launch_cell_offsets(const uint64_t *keys, uint32_t n_cells, const int64_t *pair_ids, int64_t n_pairs,
                                 int64_t *offsets, cudaStream_t st);
 cudaError_t launch_ref_totals(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *totals, cudaStream_t st);

@@ -1,0 +1,304 @@
+// swb_trace_tile.cu -- traceback of the short-read path, one THREAD per maximum cell.
+//
+// GetAlignment.call (reference SmithWaterman.java:354-436): from a maximum cell walk while the
+// score is positive; the type of a positive cell is the first of alignment / insertion /
+// deletion whose candidate equals H, i.e. the ">=" cascade of GetCellScore.call (:228,:236,:245)
+// (SWB_F_TIE_GT: deletion / insertion / alignment, DistributedSW.java:310-326).
+//
+// The fill leaves, per (read pair, reference, block of CB steps):
+//   * the CHECKPOINT: every lane's K cells + diagonal boundary at the block start,
+//   * the SEAMS: per lane and step the boundary row the lane received from the lane above
+//     (matrix row t*K of the step's column).
+// A TILE = (lane t, block b) = K rows x CB skewed columns is therefore recomputable on its own:
+// left column from the checkpoint, top row from the seam, corner = the checkpointed diagonal.
+// A path of ~170 columns crosses ~19 tiles of 304 cells (5.8k cells) instead of the ~12 full
+// 8-lane blocks (29k cells) the group-based kernel (swb_trace.cu) recomputes.
+//
+// One thread owns one maximum cell at a time: it recomputes the tile that holds the current
+// cell (unpacked int32 DPX ops, the three-op cell of the fill) into its private column-major
+// byte tile in shared memory, walks until the path leaves the tile, and repeats.  No lane
+// ever talks to another lane, so there are no shuffles and no barriers inside a traceback.
+//
+// Bytes are enough: the walker knows the exact score of its current cell (it starts from the
+// pair's maximum and subtracts the score of every move), and a candidate (NW+s, N+gap, W+gap)
+// never lies more than 2*(smax+|gap|)+max|s| below H, so equality of the low 8 bits IS equality
+// (tile8_ok() checks that bound; other score sets use swb_trace.cu).
+#include "swb_internal.h"
+#include "swb_device.cuh"
+
+#include <algorithm>
+#include <cstdlib>
+
+namespace swb {
+
+namespace {
+
+constexpr int NT = 128;                      // threads per CTA
+
+template <int K> struct TileGeo {
+    static constexpr int ROWW = Geo<K>::KW / 4;          // words per tile column: boundary row + K rows, one byte each
+    static constexpr int COLS = CB + 1;                   // column 0 = the checkpointed column
+    static constexpr int TILE_WORDS = ROWW * COLS;        // per thread
+    static constexpr int PROF_WORDS = 5 * GL * Geo<K>::KS;   // int32 scores: [lane*4 + code] + [32 + lane] for "no column"
+};
+
+// byte (row rr, column cc) of this thread's tile; words are interleaved over the CTA's threads
+// (word index * NT + tid), so every access of a warp is conflict-free whatever (rr, cc) each lane reads
+template <int K>
+__device__ __forceinline__ int tile_byte(const uint8_t *tile8, int rr, int cc)
+{
+    return tile8[(size_t)((cc * TileGeo<K>::ROWW + (rr >> 2)) * NT) * 4 + (rr & 3)];
+}
+
+// one tile column: byte 0 = boundary row, bytes 1..K = the lane's rows (low 8 bits of each score).
+// Two scores per IMAD (FMA pipe: v1 * 65536 + v0, scores are in [0, 32767]), one PRMT per word.
+template <int K>
+__device__ __forceinline__ void store_col8(uint32_t *col, int top, const int (&H)[K], uint32_t k64k)
+{
+    constexpr int ROWW = TileGeo<K>::ROWW;
+#pragma unroll
+    for (int w = 0; w < ROWW; ++w) {
+        const uint32_t v0 = (w == 0) ? (uint32_t)top : (uint32_t)H[4 * w - 1 < K ? 4 * w - 1 : 0];
+        const uint32_t v1 = (4 * w + 0 < K) ? (uint32_t)H[4 * w + 0 < K ? 4 * w + 0 : 0] : 0u;
+        const uint32_t v2 = (4 * w + 1 < K) ? (uint32_t)H[4 * w + 1 < K ? 4 * w + 1 : 0] : 0u;
+        const uint32_t v3 = (4 * w + 2 < K) ? (uint32_t)H[4 * w + 2 < K ? 4 * w + 2 : 0] : 0u;
+        const uint32_t p01 = v1 * k64k + ((w == 0 || 4 * w - 1 < K) ? v0 : 0u);
+        const uint32_t p23 = v3 * k64k + v2;
+        col[w * NT] = __byte_perm(p01, p23, 0x6420);
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, const uint64_t *keys, uint32_t n_cells,
+                                                        int chunk, int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
+                                                        int ops_stride, uint32_t k64k)
+{
+    using G = Geo<K>;
+    using TG = TileGeo<K>;
+    constexpr int KW = G::KW, KS = G::KS, ROWW = TG::ROWW;
+    constexpr unsigned FULL = 0xffffffffu;
+    extern __shared__ __align__(16) uint32_t smem[];
+    __shared__ uint32_t seg_next;
+    int *prof = reinterpret_cast<int *>(smem);                                   // [5*GL][KS]
+    uint32_t *tile = smem + TG::PROF_WORDS + threadIdx.x;                         // + word * NT
+    const uint8_t *tile8 = reinterpret_cast<const uint8_t *>(tile);
+    uint8_t *rcodes_s = reinterpret_cast<uint8_t *>(smem + TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT);   // [GL*K]
+    const int gap = P.gap, match = P.match, mismatch = P.mismatch, tie_gt = P.tie_gt, sbias = P.seam_bias;
+
+    const uint32_t c_lo = blockIdx.x * (uint32_t)chunk;
+    const uint32_t c_hi = min(n_cells, c_lo + (uint32_t)chunk);
+    uint32_t seg_lo = c_lo;
+    while (seg_lo < c_hi) {
+        // ---- segment = run of cells of one read (slot): one score profile for the whole CTA ----------
+        const uint32_t slot = (uint32_t)(key_pair(keys[seg_lo]) / (uint64_t)P.n_refs);
+        uint32_t seg_hi;
+        {
+            const uint64_t target = make_key((uint64_t)(slot + 1) * (uint64_t)P.n_refs, 0, 0);
+            uint32_t lo = seg_lo, hi = c_hi;
+            while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < target) lo = mid + 1; else hi = mid; }
+            seg_hi = lo;
+        }
+        const int read_idx = P.rp_reads[slot];
+        const int rh = (int)(slot & 1u);                             // the read's half in the fill's checkpoints
+        const int64_t roff = P.read_off[read_idx];
+        const int m = (int)(P.read_off[read_idx + 1] - roff);
+        __syncthreads();
+        for (int idx = threadIdx.x; idx < 5 * GL * K; idx += NT) {
+            const int cc = idx / (GL * K), rem = idx - cc * GL * K;
+            const int tt = rem / K, r = rem - tt * K;
+            const int row = tt * K + r;
+            int s = S_PAD;
+            if (row < m && cc < 4) s = ((int)P.read_codes[roff + row] == cc) ? match : mismatch;
+            prof[(cc < 4 ? tt * 4 + cc : 4 * GL + tt) * KS + r] = s;
+        }
+        for (int idx = threadIdx.x; idx < GL * K; idx += NT)
+            rcodes_s[idx] = idx < m ? P.read_codes[roff + idx] : (uint8_t)0xFE;
+        if (threadIdx.x == 0) seg_next = seg_lo;
+        __syncthreads();
+
+        bool busy = false;
+        int ci = 0, cj = 0, n = 0;
+        const uint32_t *rw = P.ref_words;
+        int64_t bk = 0;
+        uint32_t w_cell = 0, w_opword = 0;
+        int w_h = 0, w_beg = 0, w_len = 0;
+
+        for (;;) {
+            if (!busy) {
+                const uint32_t e = atomicAdd(&seg_next, 1u);
+                if (e < seg_hi) {
+                    const uint64_t key = keys[e];
+                    const int ro = (int)(key_pair(key) - (uint64_t)slot * (uint64_t)P.n_refs);
+                    const int ref = P.ref_sorted_of[ro];
+                    ci = (int)key_i(key); cj = (int)key_j(key);
+                    n = P.ref_len[ref];
+                    rw = P.ref_words + P.ref_word_off[ref];
+                    bk = (int64_t)(slot >> 1) * P.blocks_per_rp + P.ref_blk_off[ref];
+                    w_cell = e; w_opword = 0; w_beg = 0; w_len = 0;
+                    w_h = P.scores[(int64_t)ro * P.n_reads + read_idx];
+                    busy = w_h > 0;
+                    if (!busy) { beginnings[e] = 0; op_lens[e] = 0; }       // cannot happen: keys exist for positive scores only
+                }
+            }
+            if (!__any_sync(FULL, busy)) break;
+
+            // ---- the tile that holds the current cell: lane t, block b -------------------------------
+            const int t = busy ? (ci - 1) / K : 0;
+            const int step = cj - 1 + t;
+            const int b = busy ? step / CB : 0;
+            int H[K], diag = 0;
+            {
+                const uint4 *ck = reinterpret_cast<const uint4 *>(P.ck + (bk + b) * (int64_t)(KW * GL)) + t;
+                const bool ld = busy && b > 0;
+                const uint4 z = make_uint4(0, 0, 0, 0);
+#pragma unroll
+                for (int q = 0; q < KW / 4; ++q) {
+                    const uint4 a = ld ? __ldg(ck + q * GL) : z;
+                    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int w = 4 * q + e;
+                        if (w < K) H[w < K ? w : 0] = half_of(v[e], rh);
+                        else if (w == K) diag = half_of(v[e], rh);
+                    }
+                }
+            }
+            int top[CB];
+            {
+                const uint4 *sq = reinterpret_cast<const uint4 *>(P.seam + (bk + b) * (int64_t)(CB * GL)) + t;
+                const bool ld = busy && t > 0;                      // lane 0's boundary row is matrix row 0
+                const uint4 z = make_uint4(0, 0, 0, 0);
+                const int bias0 = sbias * (9 - t);
+#pragma unroll
+                for (int q = 0; q < CB / 4; ++q) {
+                    const uint4 a = ld ? __ldg(sq + q * GL) : z;
+                    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e)
+                        top[4 * q + e] = ld ? half_of(v[e], rh) - (bias0 + sbias * (4 * q + e)) : 0;
+                }
+            }
+            // reference codes of the block's 16 steps for this lane: 0-based columns j0 .. j0 + 15
+            uint32_t win; int ulo, uhi;
+            {
+                const int j0 = b * CB - t;
+                const int wi = j0 >> 4;                                  // floor (j0 may be negative in block 0)
+                const uint32_t a0 = (busy && wi >= 0 && wi * 16 < n) ? __ldg(rw + wi) : 0u;
+                const uint32_t a1 = (busy && wi + 1 >= 0 && (wi + 1) * 16 < n) ? __ldg(rw + wi + 1) : 0u;
+                win = __funnelshift_r(a0, a1, 2 * (j0 & 15));
+                ulo = -j0; uhi = busy ? n - j0 - 1 : -1;                  // step u is a real column iff ulo <= u <= uhi
+            }
+            store_col8<K>(tile, diag, H, k64k);
+
+            const int *pbase = prof + t * 4 * KS, *ppad = prof + (4 * GL + t) * KS;
+#pragma unroll
+            for (int u = 0; u < CB; ++u) {
+                const bool real = (u >= ulo) && (u <= uhi);
+                const int *pv = real ? pbase + ((win >> (2 * u)) & 3u) * KS : ppad;
+                int sv[G::KP];
+                {
+                    const int4 *p4 = reinterpret_cast<const int4 *>(pv);
+#pragma unroll
+                    for (int q = 0; q < G::KP / 4; ++q) {
+                        const int4 v = p4[q];
+                        sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
+                    }
+                }
+                int nw = diag, nn = top[u];
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const int x = __viaddmax_s32_relu(nw, sv[r], 0);     // max(NW + s, 0)
+                    const int pre = __viaddmax_s32(H[r], gap, x);        // max(W + gap, .)
+                    nw = H[r];
+                    H[r] = __viaddmax_s32(nn, gap, pre);                 // max(N + gap, .)
+                    nn = H[r];
+                }
+                diag = top[u];
+                store_col8<K>(tile + (u + 1) * ROWW * NT, top[u], H, k64k);
+            }
+
+            // ---- walk inside the tile (SmithWaterman.java:380-409) ------------------------------------
+            if (busy) {
+                int r = ci - t * K;                                     // 1..K
+                int c = step - b * CB + 1;                              // 1..CB
+                for (;;) {
+                    const int hw = tile_byte<K>(tile8, r, c - 1), hn = tile_byte<K>(tile8, r - 1, c),
+                              hnw = tile_byte<K>(tile8, r - 1, c - 1);
+                    const int rc = (int)((win >> (2 * (c - 1))) & 3u);
+                    const int qc = rcodes_s[ci - 1];
+                    const int sc = (qc == rc) ? match : mismatch;
+                    const bool eq_a = ((hnw + sc - w_h) & 0xff) == 0, eq_i = ((hn + gap - w_h) & 0xff) == 0,
+                               eq_d = ((hw + gap - w_h) & 0xff) == 0;
+                    const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
+                    w_beg = cj;
+                    w_opword |= op << (2 * (w_len & 15));
+                    if ((w_len & 15) == 15) { ops[(size_t)w_cell * ops_stride + (w_len >> 4)] = w_opword; w_opword = 0; }
+                    ++w_len;
+                    const int up = op != 3u, left = op != 2u;
+                    w_h -= (op == 1u) ? sc : gap;
+                    ci -= up; r -= up; cj -= left; c -= left;
+                    if (w_h <= 0) {
+                        if (w_len & 15) ops[(size_t)w_cell * ops_stride + (w_len >> 4)] = w_opword;
+                        beginnings[w_cell] = w_beg;
+                        op_lens[w_cell] = w_len;
+                        busy = false;
+                        break;
+                    }
+                    if (r == 0 || c == 0) break;                        // the path left this tile
+                }
+            }
+        }
+        seg_lo = seg_hi;
+    }
+}
+
+template <int K>
+cudaError_t launch_tile_trace_k(const BatchParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+                                int32_t *op_lens, uint32_t *ops, int ops_stride, int sm_count, cudaStream_t st)
+{
+    using TG = TileGeo<K>;
+    if (n_cells == 0) return cudaSuccess;
+    const size_t smem = ((size_t)TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT) * sizeof(uint32_t) + (((size_t)GL * K + 15) / 16) * 16;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(tile_trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    // chunks of the sorted cell list: many per SM for balance, each long enough to amortise its profile
+    static const int env_div = getenv("SWB_TRACE_CHUNKS_PER_SM") ? atoi(getenv("SWB_TRACE_CHUNKS_PER_SM")) : 0;
+    const int per_sm = env_div > 0 ? env_div : 16;
+    const int chunk = (int)std::max<int64_t>(2 * NT, ((int64_t)n_cells + (int64_t)sm_count * per_sm - 1) / ((int64_t)sm_count * per_sm));
+    const int64_t ctas = ((int64_t)n_cells + chunk - 1) / chunk;
+    tile_trace_kernel<K><<<(unsigned)ctas, NT, smem, st>>>(P, keys, n_cells, chunk, beginnings, op_lens, ops, ops_stride, 65536u);
+    return cudaGetLastError();
+}
+
+}  // namespace
+
+// Equality of the low 8 bits must be equality: a candidate lies at most 2*(smax+|gap|) + max|s| below H.
+bool tile_trace_ok(int match, int mismatch, int gap)
+{
+    static const bool disabled = getenv("SWB_NO_TILE_TRACE") != nullptr;
+    if (disabled || gap >= 0) return false;
+    const int64_t smax = std::max<int64_t>({match, mismatch, 0});
+    const int64_t sabs = std::max<int64_t>(std::llabs((long long)match), std::llabs((long long)mismatch));
+    return 2 * (smax - (int64_t)gap) + sabs < 250;
+}
+
+cudaError_t launch_tile_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+                              int32_t *op_lens, uint32_t *ops, int ops_stride_words, int sm_count, cudaStream_t st)
+{
+    switch (K) {
+        case 4:  return launch_tile_trace_k<4>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 8:  return launch_tile_trace_k<8>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 13: return launch_tile_trace_k<13>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 16: return launch_tile_trace_k<16>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 19: return launch_tile_trace_k<19>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 25: return launch_tile_trace_k<25>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 32: return launch_tile_trace_k<32>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace swb
