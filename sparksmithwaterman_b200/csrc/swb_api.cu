@@ -508,7 +508,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                     CU(ctx->tasks.reserve(cap_tasks, st));
                     CU(ctx->keys_tmp.reserve(cap_cells, st));
                     CU(cudaMemsetAsync(ctx->counters.p, 0, 8, st));
-                    CU(launch_flag_tiles(P, ctx->tasks.p, cap_tasks, d_ntasks, st));
+                    CU(launch_flag_tiles(P, ctx->tasks.p, cap_tasks, d_ntasks, ctx->sm_count, st));
                     CU(launch_locate(K, P, ctx->tasks.p, d_ntasks, cap_tasks, ctx->keys_tmp.p, cap_cells, d_ncells,
                                      ctx->sm_count, st));
                     launches += 2;
@@ -591,8 +591,8 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     }
     const int sp_misc = tic(4, st);
     CU(launch_ref_totals(res->d_scores.p, n_refs, n_reads, res->d_totals.p, st));
-    CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, st));
-    launches += 2;
+    CU(launch_best_hits(res->d_scores.p, n_refs, n_reads, res->d_best.p, ctx->sm_count, st));
+    launches += 3;
     // ---- assemble the final, ABI-ordered result on the device (swb_assemble.cu) ----------------
     if (!(flags & SWB_F_SCORES_ONLY)) {
         std::vector<BatchDesc> descs;

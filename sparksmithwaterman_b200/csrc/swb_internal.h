@@ -51,7 +51,7 @@ __host__ __device__ inline uint64_t key_pair(uint64_t k) { return k >> (KEY_J_BI
 __host__ __device__ inline uint32_t key_i(uint64_t k) { return (uint32_t)(k >> KEY_J_BITS) & ((1u << KEY_I_BITS) - 1); }
 __host__ __device__ inline uint32_t key_j(uint64_t k) { return (uint32_t)k & ((1u << KEY_J_BITS) - 1); }
 
-struct TileTask { uint32_t rp_half; uint32_t ref_sorted; uint32_t block; uint32_t lane_mask; };
+struct TileTask { uint32_t rp_half; uint32_t ref_sorted; uint32_t block; uint32_t lane; };   // one flagged tile
 
 // Everything the short-path kernels need for one batch of read pairs of one K class.
 struct BatchParams {
@@ -156,7 +156,7 @@ cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int
 cudaError_t launch_fill_bias(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st);
 bool fill_bias_ok(int match, int mismatch, int gap, int64_t max_score);
 // swb_trace.cu
-cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, cudaStream_t st);
+cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st);
 cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
                           uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
                           cudaStream_t st);
@@ -171,10 +171,7 @@ bool tile_trace_ok(int match, int mismatch, int gap);
 cudaError_t launch_cell_offsets(const uint64_t *keys, uint32_t n_cells, const int64_t *pair_ids, int64_t n_pairs,
                                 int64_t *offsets, cudaStream_t st);
 cudaError_t launch_ref_totals(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *totals, cudaStream_t st);
-cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, cudaStream_t st);
-cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, int64_t n_refs, const int32_t *read_batch,
-                              const int32_t *read_slot, const uint64_t *const *batch_keys, const uint32_t *batch_n,
-                              cudaStream_t st);
+cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, int sm_count, cudaStream_t st);
 cudaError_t sort_keys(uint64_t *keys_in, uint64_t *keys_out, uint32_t n, void *tmp, size_t tmp_bytes, cudaStream_t st);
 size_t      sort_keys_tmp_bytes(uint32_t n);
 

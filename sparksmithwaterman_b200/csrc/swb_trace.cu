@@ -3,7 +3,7 @@
 // The fill (swb_fill.cu) leaves, per pair, the maximum score, per-(lane, block) tile
 // maxima and per-block register checkpoints.  Here:
 //   flag_tiles : tiles whose maximum equals the pair's maximum (and is > 0)
-//   locate     : recompute each flagged block from its checkpoint, emit every cell == max
+//   locate     : (swb_trace_tile.cu) recompute each flagged tile from checkpoint + seam, emit every cell == max
 //                -> the reference's max-cell list (ScoreMatrix.call, SmithWaterman.java:176-185);
 //                keys (pair, i, j) are radix-sorted, which IS the row-major list order
 //   trace      : per max cell, GetAlignment.call (SmithWaterman.java:354-436): walk while
@@ -16,208 +16,84 @@
 #include "swb_internal.h"
 #include "swb_device.cuh"
 
+#include <algorithm>
 #include <cub/device/device_radix_sort.cuh>
 
 namespace swb {
 
 // ---------------------------------------------------------------------------------------
+// warp-aggregated slot reservation: every lane asks for `n` slots, one atomicAdd per warp
+__device__ __forceinline__ uint32_t warp_reserve(uint32_t *count, uint32_t n)
+{
+    const int lane = threadIdx.x & 31;
+    uint32_t inc = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+    const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+    uint32_t base = 0;
+    if (lane == 31 && total) base = atomicAdd(count, total);
+    base = __shfl_sync(0xffffffffu, base, 31);
+    return base + inc - n;
+}
+
+// One thread per global checkpoint block gb (x) and slice of the read pairs (y): the owning reference is
+// searched once and reused for every read pair; one task per (half, lane) whose tile maximum is the pair's.
 __global__ void flag_tiles_kernel(const BatchParams P, TileTask *tasks, uint32_t cap, uint32_t *count)
 {
-    // one thread per (read pair, sorted ref, block)
-    const int64_t total = (int64_t)P.n_rp * P.blocks_per_rp;
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
-         idx += (int64_t)gridDim.x * blockDim.x) {
-        const int rp = (int)(idx / P.blocks_per_rp);
-        const int64_t gb = idx - (int64_t)rp * P.blocks_per_rp;
-        // sorted ref that owns global block gb: binary search in ref_blk_off
+    const int64_t gb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const bool in = gb < P.blocks_per_rp;
+    int ref = 0, b = 0;
+    int64_t ro = 0;
+    if (in) {
         int lo = 0, hi = P.n_refs;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.ref_blk_off[mid] <= gb) lo = mid; else hi = mid; }
-        const int ref = lo;
-        const int b = (int)(gb - P.ref_blk_off[ref]);
-        const int64_t ro = P.ref_orig[ref];
-        const int ra = P.rp_reads[2 * rp], rb = P.rp_reads[2 * rp + 1];
-        const int sa = P.scores[ro * P.n_reads + ra];
-        const int sb = rb >= 0 ? P.scores[ro * P.n_reads + rb] : 0;
-        if (sa <= 0 && sb <= 0) continue;
-        const uint4 *tm = reinterpret_cast<const uint4 *>(P.tmx + idx * GL);
-        const uint4 v0 = tm[0], v1 = tm[1];
-        const uint32_t w[GL] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-        uint32_t ma = 0, mb = 0;
-#pragma unroll
-        for (int t = 0; t < GL; ++t) {
-            if (sa > 0 && half_of(w[t], 0) == sa) ma |= 1u << t;
-            if (sb > 0 && half_of(w[t], 1) == sb) mb |= 1u << t;
-        }
-        if (ma) {
-            const uint32_t k = atomicAdd(count, 1u);
-            if (k < cap) tasks[k] = TileTask{(uint32_t)rp * 2u, (uint32_t)ref, (uint32_t)b, ma};
-        }
-        if (mb) {
-            const uint32_t k = atomicAdd(count, 1u);
-            if (k < cap) tasks[k] = TileTask{(uint32_t)rp * 2u + 1u, (uint32_t)ref, (uint32_t)b, mb};
-        }
+        ref = lo;
+        b = (int)(gb - P.ref_blk_off[ref]);
+        ro = P.ref_orig[ref];
     }
-}
-
-cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, cudaStream_t st)
-{
-    const int64_t total = (int64_t)P.n_rp * P.blocks_per_rp;
-    const int threads = 256;
-    const int64_t blocks = std::min<int64_t>((total + threads - 1) / threads, 1 << 20);
-    if (blocks == 0) return cudaSuccess;
-    flag_tiles_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, tasks, cap, count);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------
-// One block (CB steps) of the wavefront for one group, unpacked int32.
-// State in/out: H[K] (this lane's column), diag.  sink(u, top, H, valid, j) after each step.
-template <int K>
-struct GroupCtx {
-    const uint32_t *ref_words;   // this ref's packed codes
-    int n;                       // ref length
-    int m;                       // read length
-    int rc[K];                   // read codes of this lane's rows (0xFE beyond the read)
-    int match, mismatch, gap;
-};
-
-template <int K>
-__device__ __forceinline__ void load_state(const BatchParams &P, int64_t blk0, int b, int half, int t,
-                                           int (&H)[K], int &diag)
-{
-    if (b == 0) {
+    // four read pairs per round: all loads of a round are issued before any is used (the kernel is latency-bound)
+    for (int rp0 = blockIdx.y * 4; rp0 < P.n_rp; rp0 += gridDim.y * 4) {
+        uint4 v0[4], v1[4];
+        int sa[4], sb[4];
 #pragma unroll
-        for (int r = 0; r < K; ++r) H[r] = 0;
-        diag = 0;
-        return;
-    }
-    const uint32_t *blk = P.ck + (blk0 + b) * (int64_t)(Geo<K>::KW * GL);
+        for (int k = 0; k < 4; ++k) {
+            const int rp = rp0 + k;
+            const bool ok = in && rp < P.n_rp;
+            const int ra = ok ? P.rp_reads[2 * rp] : 0, rb = ok ? P.rp_reads[2 * rp + 1] : -1;
+            sa[k] = ok ? P.scores[ro * P.n_reads + ra] : 0;
+            sb[k] = rb >= 0 ? P.scores[ro * P.n_reads + rb] : 0;
+            const uint4 *tm = reinterpret_cast<const uint4 *>(P.tmx + ((int64_t)rp * P.blocks_per_rp + gb) * GL);
+            v0[k] = ok ? __ldcs(tm) : make_uint4(0, 0, 0, 0);
+            v1[k] = ok ? __ldcs(tm + 1) : make_uint4(0, 0, 0, 0);
+        }
 #pragma unroll
-    for (int r = 0; r < K; ++r) H[r] = half_of(load_checkpoint_word<K>(blk, t, r), half);
-    diag = half_of(load_checkpoint_word<K>(blk, t, K), half);
-}
-
-template <int K, class Sink>
-__device__ __forceinline__ void run_block(const GroupCtx<K> &C, int b, int t, unsigned gmask,
-                                          int (&H)[K], int &diag, Sink &&sink)
-{
-#pragma unroll 1
-    for (int u = 0; u < CB; ++u) {
-        const int s = b * CB + u;
-        int top = __shfl_up_sync(gmask, H[K - 1], 1, GL);
-        if (t == 0) top = 0;
-        const int j = s - t + 1;
-        const bool valid = (j >= 1) && (j <= C.n);
-        if (valid) {
-            const int col = j - 1;
-            const int c = (int)((__ldg(C.ref_words + (col >> 4)) >> (2 * (col & 15))) & 3u);
-            int nw = diag, nn = top;
+        for (int k = 0; k < 4; ++k) {
+            const int rp = rp0 + k;
+            uint32_t ma = 0, mb = 0;
+            const uint32_t w[GL] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
 #pragma unroll
-            for (int r = 0; r < K; ++r) {
-                const int sc = (C.rc[r] == c) ? C.match : C.mismatch;
-                const int pre = __viaddmax_s32_relu(H[r], C.gap, nw + sc);   // max(W+gap, NW+s, 0)
-                nw = H[r];
-                H[r] = __viaddmax_s32(nn, C.gap, pre);                        // max(N+gap, pre)
-                nn = H[r];
+            for (int t = 0; t < GL; ++t) {
+                if (sa[k] > 0 && half_of(w[t], 0) == sa[k]) ma |= 1u << t;
+                if (sb[k] > 0 && half_of(w[t], 1) == sb[k]) mb |= 1u << t;
             }
+            if (!__any_sync(0xffffffffu, (ma | mb) != 0u)) continue;
+            uint32_t kk = warp_reserve(count, (uint32_t)(__popc(ma) + __popc(mb)));
+            for (uint32_t mm = ma; mm; mm &= mm - 1, ++kk)
+                if (kk < cap) tasks[kk] = TileTask{(uint32_t)rp * 2u, (uint32_t)ref, (uint32_t)b, (uint32_t)(__ffs((int)mm) - 1)};
+            for (uint32_t mm = mb; mm; mm &= mm - 1, ++kk)
+                if (kk < cap) tasks[kk] = TileTask{(uint32_t)rp * 2u + 1u, (uint32_t)ref, (uint32_t)b, (uint32_t)(__ffs((int)mm) - 1)};
         }
-        sink(u, top, H, valid, j);
-        diag = top;
     }
 }
 
-template <int K>
-__device__ __forceinline__ void init_group(const BatchParams &P, int rp, int half, int ref, int t, GroupCtx<K> &C,
-                                           int64_t &blk0, int64_t &pair, int &read_idx)
+cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st)
 {
-    read_idx = P.rp_reads[2 * rp + half];
-    const int64_t off = P.read_off[read_idx];
-    C.m = (int)(P.read_off[read_idx + 1] - off);
-    C.n = P.ref_len[ref];
-    C.ref_words = P.ref_words + P.ref_word_off[ref];
-    C.match = P.match; C.mismatch = P.mismatch; C.gap = P.gap;
-#pragma unroll
-    for (int r = 0; r < K; ++r) {
-        const int row = t * K + r;
-        C.rc[r] = (row < C.m) ? (int)P.read_codes[off + row] : 0xFE;
-    }
-    blk0 = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref];
-    pair = (int64_t)P.ref_orig[ref] * P.n_reads + read_idx;
-}
-
-// ---------------------------------------------------------------------------------------
-template <int K>
-__global__ void __launch_bounds__(128) locate_kernel(const BatchParams P, const TileTask *tasks,
-                                                      const uint32_t *n_tasks_ptr, uint32_t cap_tasks,
-                                                      uint64_t *keys, uint32_t cap, uint32_t *count)
-{
-    const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);        // written by flag_tiles on the same stream
-    const int lane = threadIdx.x & 31, t = lane & (GL - 1), g = lane >> 3;
-    const unsigned gmask = 0xffu << (8 * g);
-    const uint32_t n_groups = gridDim.x * (blockDim.x >> 3);
-    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
-    // all 4 groups of a warp iterate the same number of times (tasks padded with idle turns)
-    const uint32_t iters = (n_tasks + n_groups - 1) / n_groups;
-    for (uint32_t it = 0; it < iters; ++it) {
-        const uint32_t task = it * n_groups + gid;
-        const bool live = task < n_tasks;
-        TileTask T = live ? tasks[task] : TileTask{0, 0, 0, 0};
-        GroupCtx<K> C;
-        int64_t blk0 = 0, pair = 0; int read_idx = 0;
-        int H[K], diag = 0;
-        int S = 0;
-        uint64_t pkey = 0;
-        if (live) {
-            init_group<K>(P, (int)(T.rp_half >> 1), (int)(T.rp_half & 1), (int)T.ref_sorted, t, C, blk0, pair, read_idx);
-            load_state<K>(P, blk0, (int)T.block, (int)(T.rp_half & 1), t, H, diag);
-            S = P.scores[pair];
-            pkey = (uint64_t)T.rp_half * (uint64_t)P.n_refs + (uint64_t)P.ref_orig[T.ref_sorted];
-        } else {
-            C.n = 0; C.m = 0; C.ref_words = P.ref_words; C.match = C.mismatch = C.gap = 0;
-#pragma unroll
-            for (int r = 0; r < K; ++r) { H[r] = 0; C.rc[r] = 0xFE; }
-        }
-        const bool mine = live && ((T.lane_mask >> t) & 1u);
-        run_block<K>(C, (int)T.block, t, gmask, H, diag,
-                     [&](int, int, const int (&Hc)[K], bool valid, int j) {
-                         if (!(valid && mine)) return;
-#pragma unroll
-                         for (int r = 0; r < K; ++r) {
-                             const int i = t * K + r + 1;
-                             if (Hc[r] == S && i <= C.m) {
-                                 const uint32_t k = atomicAdd(count, 1u);
-                                 if (k < cap) keys[k] = make_key(pkey, (uint32_t)i, (uint32_t)j);
-                             }
-                         }
-                     });
-    }
-}
-
-template <int K>
-static cudaError_t launch_locate_k(const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
-                                   uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
-                                   cudaStream_t st)
-{
-    const int threads = 128;                      // 16 groups per CTA; the task count is read on the device
-    int64_t ctas = std::min<int64_t>(((int64_t)cap_tasks + 15) / 16, (int64_t)sm_count * 16);
-    locate_kernel<K><<<(unsigned)std::max<int64_t>(ctas, 1), threads, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count);
+    if (P.blocks_per_rp == 0 || P.n_rp == 0) return cudaSuccess;
+    const int threads = 256;
+    const int64_t bx = (P.blocks_per_rp + threads - 1) / threads;
+    const int64_t by = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>((P.n_rp + 3) / 4, 65535), ((int64_t)sm_count * 16 + bx - 1) / bx));
+    flag_tiles_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(P, tasks, cap, count);
     return cudaGetLastError();
-}
-
-cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
-                          uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
-                          cudaStream_t st)
-{
-    switch (K) {
-        case 4:  return launch_locate_k<4>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 8:  return launch_locate_k<8>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 13: return launch_locate_k<13>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 16: return launch_locate_k<16>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 19: return launch_locate_k<19>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 25: return launch_locate_k<25>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 32: return launch_locate_k<32>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-    }
-    return cudaErrorInvalidValue;
 }
 
 template <int K> struct TraceGeo {
@@ -656,55 +532,47 @@ cudaError_t launch_ref_totals(const int32_t *scores, int64_t n_refs, int64_t n_r
     return cudaGetLastError();
 }
 
-// per-read best reference: highest score, lowest ref index on ties. best[4q] = score, [4q+1] = ref
-__global__ void best_hits_kernel(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best)
+// per-read best reference: highest score, lowest ref index on ties.  best[4q] = score, [4q+1] = ref.
+// Phase 1: thread = (read q, slice of the references), coalesced over q; 64-bit atomicMax of
+// (score << 32 | ~ref) into the first two words of the read's record.  Phase 2 decodes.
+__global__ void best_hits_scan_kernel(const int32_t *scores, int64_t n_refs, int64_t n_reads, unsigned long long *best64)
 {
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n_reads) return;
-    int bs = -1, br = -1;
-    for (int64_t r = 0; r < n_refs; ++r) {
+    int bs = -1; int64_t br = -1;
+    for (int64_t r = blockIdx.y; r < n_refs; r += gridDim.y) {
         const int s = scores[r * n_reads + q];
-        if (s > bs) { bs = s; br = (int)r; }
+        if (s > bs) { bs = s; br = r; }
     }
-    best[4 * q] = bs < 0 ? 0 : bs; best[4 * q + 1] = br; best[4 * q + 2] = 0; best[4 * q + 3] = 0;
+    if (br >= 0)
+        atomicMax(best64 + 2 * q, ((unsigned long long)(uint32_t)max(bs, 0) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)br));
 }
 
-cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, cudaStream_t st)
-{
-    if (n_reads == 0) return cudaSuccess;
-    const int threads = 128;
-    best_hits_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(scores, n_refs, n_reads, best);
-    return cudaGetLastError();
-}
-
-// fill (i, j) of each read's best hit: first key of pair (best ref, read) in the read's batch
-__global__ void best_cells_kernel(int32_t *best, int64_t n_reads, int64_t n_refs, const int32_t *read_batch,
-                                  const int32_t *read_slot, const uint64_t *const *batch_keys, const uint32_t *batch_n)
+__global__ void best_hits_finish_kernel(int32_t *best, int64_t n_reads)
 {
     const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     if (q >= n_reads) return;
-    const int b = read_batch[q];
-    const int ref = best[4 * q + 1];
-    if (b < 0 || ref < 0 || best[4 * q] <= 0) return;
-    const uint64_t *keys = batch_keys[b];
-    const uint64_t p = (uint64_t)read_slot[q] * (uint64_t)n_refs + (uint64_t)ref;   // key order: (read slot, ref)
-    const uint64_t target = make_key(p, 0, 0);
-    uint32_t lo = 0, hi = batch_n[b];
-    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if (keys[mid] < target) lo = mid + 1; else hi = mid; }
-    if (lo < batch_n[b] && key_pair(keys[lo]) == p) {
-        best[4 * q + 2] = (int32_t)key_i(keys[lo]);
-        best[4 * q + 3] = (int32_t)key_j(keys[lo]);
-    }
+    const unsigned long long k = reinterpret_cast<const unsigned long long *>(best)[2 * q];
+    int4 o;
+    o.x = (int)(uint32_t)(k >> 32);
+    o.y = k ? (int)(0xffffffffu - (uint32_t)k) : -1;          // no reference at all: (0, -1)
+    o.z = 0; o.w = 0;
+    reinterpret_cast<int4 *>(best)[q] = o;
 }
 
-cudaError_t launch_best_cells(int32_t *best, int64_t n_reads, int64_t n_refs, const int32_t *read_batch,
-                              const int32_t *read_slot, const uint64_t *const *batch_keys, const uint32_t *batch_n,
-                              cudaStream_t st)
+cudaError_t launch_best_hits(const int32_t *scores, int64_t n_refs, int64_t n_reads, int32_t *best, int sm_count, cudaStream_t st)
 {
     if (n_reads == 0) return cudaSuccess;
+    cudaError_t e = cudaMemsetAsync(best, 0, (size_t)n_reads * 16, st);
+    if (e != cudaSuccess) return e;
     const int threads = 128;
-    best_cells_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(best, n_reads, n_refs, read_batch,
-                                                                                        read_slot, batch_keys, batch_n);
+    const int64_t bx = (n_reads + threads - 1) / threads;
+    if (n_refs > 0) {
+        const int64_t by = std::max<int64_t>(1, std::min<int64_t>(std::min<int64_t>(n_refs, 65535), ((int64_t)sm_count * 16 + bx - 1) / bx));
+        best_hits_scan_kernel<<<dim3((unsigned)bx, (unsigned)by), threads, 0, st>>>(scores, n_refs, n_reads,
+                                                                                    reinterpret_cast<unsigned long long *>(best));
+    }
+    best_hits_finish_kernel<<<(unsigned)bx, threads, 0, st>>>(best, n_reads);
     return cudaGetLastError();
 }
 

@@ -252,6 +252,149 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
     }
 }
 
+// ---------------------------------------------------------------------------------------
+// Max-cell enumeration (ScoreMatrix.call, SmithWaterman.java:176-185): one thread per flagged tile
+// (half, reference, block, lane) recomputes the tile from checkpoint + seam and emits every cell whose
+// score equals the pair's maximum as a key (pair, i, j); the radix sort of the keys is the row-major order.
+// Up to 4 hits per tile wait in shared memory and are written with one warp-aggregated reservation;
+// tie-heavy tiles with more hits pay one atomic per extra hit.  The step loop is rolled in quads (the fully
+// unrolled version thrashed the instruction cache: 68 warps stalled on no_instruction per issue).
+template <int K>
+__global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, const TileTask *tasks,
+                                                         const uint32_t *n_tasks_ptr, uint32_t cap_tasks,
+                                                         uint64_t *keys, uint32_t cap, uint32_t *count)
+{
+    using G = Geo<K>;
+    constexpr int KW = G::KW;
+    __shared__ uint32_t hitbuf[4 * NT];
+    const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);        // written by flag_tiles on the same stream
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_threads = gridDim.x * blockDim.x;
+    const uint32_t iters = (n_tasks + n_threads - 1) / n_threads; // whole warps iterate together
+    const int gap = P.gap, match = P.match, mismatch = P.mismatch;
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t task = it * n_threads + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = task < n_tasks;
+        const TileTask T = live ? tasks[task] : TileTask{0, 0, 0, 0};
+        const int rp = (int)(T.rp_half >> 1), rh = (int)(T.rp_half & 1u), ref = (int)T.ref_sorted, b = (int)T.block, t = (int)T.lane;
+        int S = 0x7fffffff;
+        uint64_t pkey = 0;
+        int rc[K];
+        int H[K], diag = 0;
+        uint32_t win = 0, rowok = 0;
+        int ulo = 0, uhi = -1;
+        const uint4 *sq = reinterpret_cast<const uint4 *>(P.seam) + t;
+        bool has_top = false;
+#pragma unroll
+        for (int r = 0; r < K; ++r) { rc[r] = 0xFE; H[r] = 0; }
+        if (live) {
+            const int read_idx = P.rp_reads[2 * rp + rh];
+            const int64_t off = P.read_off[read_idx];
+            const int m = (int)(P.read_off[read_idx + 1] - off);
+            const int n = P.ref_len[ref];
+            const int64_t ro = P.ref_orig[ref];
+            S = P.scores[ro * P.n_reads + read_idx];
+            pkey = (uint64_t)T.rp_half * (uint64_t)P.n_refs + (uint64_t)ro;
+#pragma unroll
+            for (int r = 0; r < K; ++r) {
+                const int row = t * K + r;
+                rc[r] = (row < m) ? (int)P.read_codes[off + row] : 0xFE;
+                if (row < m) rowok |= 1u << r;
+            }
+            const int64_t blk = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref] + b;
+            if (b > 0) {
+                const uint4 *ck = reinterpret_cast<const uint4 *>(P.ck + blk * (int64_t)(KW * GL)) + t;
+#pragma unroll
+                for (int q = 0; q < KW / 4; ++q) {
+                    const uint4 a = __ldg(ck + q * GL);
+                    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int w = 4 * q + e;
+                        if (w < K) H[w < K ? w : 0] = half_of(v[e], rh);
+                        else if (w == K) diag = half_of(v[e], rh);
+                    }
+                }
+            }
+            sq = reinterpret_cast<const uint4 *>(P.seam + blk * (int64_t)(CB * GL)) + t;
+            has_top = t > 0;                                         // lane 0's boundary row is matrix row 0
+            const uint32_t *rw = P.ref_words + P.ref_word_off[ref];
+            const int j0 = b * CB - t;
+            const int wi = j0 >> 4;
+            const uint32_t a0 = (wi >= 0 && wi * 16 < n) ? __ldg(rw + wi) : 0u;
+            const uint32_t a1 = (wi + 1 >= 0 && (wi + 1) * 16 < n) ? __ldg(rw + wi + 1) : 0u;
+            win = __funnelshift_r(a0, a1, 2 * (j0 & 15));
+            ulo = -j0; uhi = n - j0 - 1;
+        }
+        const int bias0 = P.seam_bias * (9 - t);
+        uint32_t n_hit = 0;
+        uint4 nxt = has_top ? __ldg(sq) : make_uint4(0, 0, 0, 0);
+#pragma unroll 1
+        for (int q = 0; q < CB / 4; ++q) {
+            const uint4 a = nxt;
+            if (q + 1 < CB / 4 && has_top) nxt = __ldg(sq + (q + 1) * GL);
+            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = 4 * q + e;
+                const int top = has_top ? half_of(av[e], rh) - (bias0 + P.seam_bias * u) : 0;
+                const bool real = (u >= ulo) && (u <= uhi);
+                const int c = real ? (int)((win >> (2 * u)) & 3u) : 0xFD;       // 0xFD: matches no row
+                int nw = diag, nn = top, cmax = 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) {
+                    const int sc = (rc[r] == c) ? match : mismatch;
+                    const int x = __viaddmax_s32_relu(nw, sc, 0);
+                    const int pre = __viaddmax_s32(H[r], gap, x);
+                    nw = H[r];
+                    H[r] = real ? __viaddmax_s32(nn, gap, pre) : 0;       // left of the matrix: zeros; right of it: never used
+                    nn = H[r];
+                    cmax = max(cmax, H[r]);
+                }
+                diag = top;
+                // S is the pair's maximum over the real rows, so some H == S needs max(H) >= S (rows beyond the read's end
+                // sit below every real row, never feed one, and may exceed S when mismatch > 0: hence >=, not ==)
+                if (real && cmax >= S) {
+                    uint32_t rm = 0;
+#pragma unroll
+                    for (int r = 0; r < K; ++r) rm |= (H[r] == S) ? (1u << r) : 0u;
+                    rm &= rowok;
+                    const uint32_t j = (uint32_t)(b * CB - t + u + 1);
+                    while (rm) {
+                        const int r = __ffs((int)rm) - 1;
+                        rm &= rm - 1;
+                        const uint32_t code = ((uint32_t)(t * K + r + 1) << KEY_J_BITS) | j;
+                        if (n_hit < 4) hitbuf[n_hit * NT + threadIdx.x] = code;
+                        else { const uint32_t k = atomicAdd(count, 1u); if (k < cap) keys[k] = (pkey << (KEY_J_BITS + KEY_I_BITS)) | code; }
+                        ++n_hit;
+                    }
+                }
+            }
+        }
+        // one reservation per warp for the (up to 4) buffered hits of every lane
+        const uint32_t mine = min(n_hit, 4u);
+        uint32_t inc = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        uint32_t base = 0;
+        if (lane == 31 && total) base = atomicAdd(count, total);
+        base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
+        for (uint32_t h = 0; h < mine; ++h)
+            if (base + h < cap) keys[base + h] = (pkey << (KEY_J_BITS + KEY_I_BITS)) | hitbuf[h * NT + threadIdx.x];
+    }
+}
+
+template <int K>
+cudaError_t launch_tile_locate_k(const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
+                                 uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st)
+{
+    // the task count is read on the device; size the grid for the capacity, capped at a few waves
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(((int64_t)cap_tasks + NT - 1) / NT, (int64_t)sm_count * 32));
+    tile_locate_kernel<K><<<(unsigned)ctas, NT, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count);
+    return cudaGetLastError();
+}
+
 template <int K>
 cudaError_t launch_tile_trace_k(const BatchParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
                                 int32_t *op_lens, uint32_t *ops, int ops_stride, int sm_count, cudaStream_t st)
@@ -284,6 +427,22 @@ bool tile_trace_ok(int match, int mismatch, int gap)
     const int64_t smax = std::max<int64_t>({match, mismatch, 0});
     const int64_t sabs = std::max<int64_t>(std::llabs((long long)match), std::llabs((long long)mismatch));
     return 2 * (smax - (int64_t)gap) + sabs < 250;
+}
+
+cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
+                          uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
+                          cudaStream_t st)
+{
+    switch (K) {
+        case 4:  return launch_tile_locate_k<4>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 8:  return launch_tile_locate_k<8>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 13: return launch_tile_locate_k<13>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 16: return launch_tile_locate_k<16>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 19: return launch_tile_locate_k<19>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 25: return launch_tile_locate_k<25>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 32: return launch_tile_locate_k<32>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+    }
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_tile_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
