@@ -68,7 +68,14 @@ __device__ __forceinline__ void store_col8(uint32_t *col, int top, const int (&H
     }
 }
 
-template <int K>
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t r;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(sel));
+    return r;
+}
+
+template <int K, bool TIE_GT>
 __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, const uint64_t *keys, uint32_t n_cells,
                                                         int chunk, int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
                                                         int ops_stride, uint32_t k64k)
@@ -83,7 +90,7 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
     uint32_t *tile = smem + TG::PROF_WORDS + threadIdx.x;                         // + word * NT
     const uint8_t *tile8 = reinterpret_cast<const uint8_t *>(tile);
     uint8_t *rcodes_s = reinterpret_cast<uint8_t *>(smem + TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT);   // [GL*K]
-    const int gap = P.gap, match = P.match, mismatch = P.mismatch, tie_gt = P.tie_gt, sbias = P.seam_bias;
+    const int gap = P.gap, match = P.match, mismatch = P.mismatch, sbias = P.seam_bias;
 
     const uint32_t c_lo = blockIdx.x * (uint32_t)chunk;
     const uint32_t c_hi = min(n_cells, c_lo + (uint32_t)chunk);
@@ -218,33 +225,53 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             }
 
             // ---- walk inside the tile (SmithWaterman.java:380-409) ------------------------------------
+            // pw = shared-memory address of the tile word that holds the current cell (row r = 4*w + rb, column c);
+            // the word above (rows 4w-4..4w-1) and the two words of column c-1 sit at constant offsets, and one
+            // PRMT over (word above : word) picks byte rb+3 = row r-1 or rb+4 = row r, whatever rb is.
             if (busy) {
+                constexpr int UPB = NT * 4, COLB = ROWW * NT * 4;       // byte offsets: one word up, one column left
                 int r = ci - t * K;                                     // 1..K
                 int c = step - b * CB + 1;                              // 1..CB
+                const int cbase = cj - c;                               // global column = cbase + c
+                const uint8_t *pw = tile8 + (size_t)((c * ROWW + (r >> 2)) * NT) * 4;
+                uint32_t sel3 = (uint32_t)(r & 3) + 3u;                 // PRMT selector of row r-1; +1: row r
+                // codes of the block's columns in reverse order: column c at bits 2*(CB - c), so a step left is >> 2
+                uint32_t wsh = __brev(win);
+                wsh = ((wsh & 0x55555555u) << 1) | ((wsh >> 1) & 0x55555555u);
+                wsh >>= 2 * (CB - c);                                   // reference code of column c in bits 0..1
+                const uint8_t *qp = rcodes_s + (ci - 1);
+                uint32_t *op_ptr = ops + (size_t)w_cell * ops_stride + (w_len >> 4);
+                uint32_t sh = 2u * ((uint32_t)w_len & 15u);
+                int lastc = c;
                 for (;;) {
-                    const int hw = tile_byte<K>(tile8, r, c - 1), hn = tile_byte<K>(tile8, r - 1, c),
-                              hnw = tile_byte<K>(tile8, r - 1, c - 1);
-                    const int rc = (int)((win >> (2 * (c - 1))) & 3u);
-                    const int qc = rcodes_s[ci - 1];
-                    const int sc = (qc == rc) ? match : mismatch;
+                    const uint32_t w_c = *reinterpret_cast<const uint32_t *>(pw), u_c = *reinterpret_cast<const uint32_t *>(pw - UPB);
+                    const uint32_t w_l = *reinterpret_cast<const uint32_t *>(pw - COLB), u_l = *reinterpret_cast<const uint32_t *>(pw - COLB - UPB);
+                    // low byte = the score's low 8 bits; the other bytes are masked after the add
+                    const int hn = (int)prmt(u_c, w_c, sel3), hw = (int)prmt(u_l, w_l, sel3 + 1u), hnw = (int)prmt(u_l, w_l, sel3);
+                    const int sc = ((uint32_t)*qp == (wsh & 3u)) ? match : mismatch;
                     const bool eq_a = ((hnw + sc - w_h) & 0xff) == 0, eq_i = ((hn + gap - w_h) & 0xff) == 0,
                                eq_d = ((hw + gap - w_h) & 0xff) == 0;
-                    const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
-                    w_beg = cj;
-                    w_opword |= op << (2 * (w_len & 15));
-                    if ((w_len & 15) == 15) { ops[(size_t)w_cell * ops_stride + (w_len >> 4)] = w_opword; w_opword = 0; }
+                    const uint32_t op = TIE_GT ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
+                    lastc = c;
+                    w_opword |= op << sh;
+                    sh = (sh + 2u) & 31u;
+                    if (sh == 0u) { *op_ptr = w_opword; w_opword = 0; }
+                    op_ptr += (sh == 0u);
                     ++w_len;
-                    const int up = op != 3u, left = op != 2u;
                     w_h -= (op == 1u) ? sc : gap;
-                    ci -= up; r -= up; cj -= left; c -= left;
-                    if (w_h <= 0) {
-                        if (w_len & 15) ops[(size_t)w_cell * ops_stride + (w_len >> 4)] = w_opword;
-                        beginnings[w_cell] = w_beg;
-                        op_lens[w_cell] = w_len;
-                        busy = false;
-                        break;
-                    }
-                    if (r == 0 || c == 0) break;                        // the path left this tile
+                    const int up = op != 3u, left = op != 2u;           // alignment: both
+                    r -= up; qp -= up; sel3 -= up;
+                    if (sel3 < 3u) { sel3 = 6u; pw -= UPB; }
+                    c -= left; pw -= left ? COLB : 0; wsh >>= 2 * left;
+                    if (w_h <= 0 || r == 0 || c == 0) break;            // done, or the path left this tile
+                }
+                ci = t * K + r; cj = cbase + c;
+                w_beg = cbase + lastc;
+                if (w_h <= 0) {
+                    if (sh) *op_ptr = w_opword;
+                    beginnings[w_cell] = w_beg;
+                    op_lens[w_cell] = w_len;
+                    busy = false;
                 }
             }
         }
@@ -404,7 +431,8 @@ cudaError_t launch_tile_trace_k(const BatchParams &P, const uint64_t *keys, uint
     const size_t smem = ((size_t)TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT) * sizeof(uint32_t) + (((size_t)GL * K + 15) / 16) * 16;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(tile_trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(tile_trace_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_trace_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
@@ -413,7 +441,8 @@ cudaError_t launch_tile_trace_k(const BatchParams &P, const uint64_t *keys, uint
     const int per_sm = env_div > 0 ? env_div : 16;
     const int chunk = (int)std::max<int64_t>(2 * NT, ((int64_t)n_cells + (int64_t)sm_count * per_sm - 1) / ((int64_t)sm_count * per_sm));
     const int64_t ctas = ((int64_t)n_cells + chunk - 1) / chunk;
-    tile_trace_kernel<K><<<(unsigned)ctas, NT, smem, st>>>(P, keys, n_cells, chunk, beginnings, op_lens, ops, ops_stride, 65536u);
+    if (P.tie_gt) tile_trace_kernel<K, true><<<(unsigned)ctas, NT, smem, st>>>(P, keys, n_cells, chunk, beginnings, op_lens, ops, ops_stride, 65536u);
+    else          tile_trace_kernel<K, false><<<(unsigned)ctas, NT, smem, st>>>(P, keys, n_cells, chunk, beginnings, op_lens, ops, ops_stride, 65536u);
     return cudaGetLastError();
 }
 

@@ -96,3 +96,14 @@ def test_long_gap_runs_leave_the_trace_window(engine):
     refs = [base, base[50:900], "ACGT" * 300, base[::-1]]
     for scores in ((5, -4, -1), (4, -6, -1), (3, -2, -1), (10, -9, -1)):
         check_pairs(engine, refs, reads, scores, max_cells=200)
+
+
+def test_large_scores_fall_back_to_the_group_traceback(engine):
+    """Byte tiles need every candidate within 250 of H (tile_trace_ok); larger score sets take the
+    group-based traceback kernel (swb_trace.cu), which keeps full s16 tiles."""
+    rnd = random.Random(92)
+    base = "".join(rnd.choice("ACGT") for _ in range(900))
+    refs = [base, base[200:700], "ACGT" * 100, "".join(rnd.choice("ACGT") for _ in range(333))]
+    reads = [base[50:200], base[300:380] + "TT" + base[380:440], "ACGT" * 30, base[600:700][::-1], "A" * 20]
+    for scores in ((100, -90, -30), (60, -50, -40), (90, 10, -80)):
+        check_pairs(engine, refs, reads, scores, max_cells=200)
