@@ -73,7 +73,7 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
     c->tasks.release(); c->keys_tmp.release(); c->sort_tmp.release();
-    for (int k = 0; k < 2; ++k) { c->ck2[k].release(); c->tmx2[k].release(); c->seam2[k].release(); c->rp2[k].release(); }
+    for (int k = 0; k < 2; ++k) { c->ck2[k].release(); c->tmx2[k].release(); c->rp2[k].release(); }
     cudaStreamSynchronize(c->stream_fill);
     c->v_ref.release(); c->v_c0.release(); c->v_len.release(); c->v_skip.release(); c->v_end.release();
     c->w_brow.release(); c->w_ck.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
@@ -423,7 +423,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
             // stage F (ctx->stream_fill): fill of batch k+1;  stage T (ctx->stream): flag/locate/sort/trace of
             // batch k.  The fill saturates the integer pipe, the traceback is latency-bound: run together they
             // share the SMs.  Two checkpoint workspaces, ping-pong; events order the reuse.
-            const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)KW * GL * 4 + GL * 4 + CB * GL * 4);   // checkpoint + tile max + seams
+            const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)(KW + CB) * GL * 4 + GL * 4);   // block records (checkpoint + seam) + tile max
             int64_t rp_per_batch = std::max<int64_t>(1, ctx->ws_bytes / std::max<int64_t>(bytes_per_rp, 1));
             const bool pipelined = !(flags & SWB_F_SCORES_ONLY) && n_rp_total > rp_per_batch / 2 && ctx->pipeline;
             if (pipelined) rp_per_batch = std::max<int64_t>(1, rp_per_batch / 2);       // two workspaces
@@ -453,19 +453,17 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                         }
                     }
                 ++n_batches;
-                DevBuf<uint32_t> &ck = ctx->ck2[S.buf], &tmx = ctx->tmx2[S.buf], &seam = ctx->seam2[S.buf];
+                DevBuf<uint32_t> &ck = ctx->ck2[S.buf], &tmx = ctx->tmx2[S.buf];
                 DevBuf<int32_t> &rpb = ctx->rp2[S.buf];
                 // the workspace of this parity is free once the traceback that last used it has finished
                 if (ev_trace_done[S.buf]) CU(cudaStreamWaitEvent(sF, ev_trace_done[S.buf], 0));
                 CU(rpb.reserve(S.h_rp.size(), sF));
                 CU(cudaMemcpyAsync(rpb.p, S.h_rp.data(), S.h_rp.size() * 4, cudaMemcpyHostToDevice, sF));
-                const size_t ck_words = (size_t)S.n_rp * rs->blocks_per_rp * KW * GL;
+                const size_t ck_words = (size_t)S.n_rp * rs->blocks_per_rp * (KW + CB) * GL;
                 const size_t tmx_words = (size_t)S.n_rp * rs->blocks_per_rp * GL;
                 CU(ck.reserve(ck_words, sF));
-                const size_t seam_words = (size_t)S.n_rp * rs->blocks_per_rp * CB * GL;
                 CU(tmx.reserve(tmx_words, sF));
-                CU(seam.reserve(seam_words, sF));
-                ck_bytes += (double)(ck_words + tmx_words + seam_words) * 4;
+                ck_bytes += (double)(ck_words + tmx_words) * 4;
                 BatchParams &P = S.P;
                 P.ref_words = rs->words.p; P.ref_word_off = rs->word_off.p; P.ref_len = rs->len.p;
                 P.ref_orig = rs->orig.p; P.ref_sorted_of = rs->sorted_of.p; P.ref_blk_off = rs->blk_off.p;
@@ -475,7 +473,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = rpb.p; P.read_slot = nullptr;
                 P.n_rp = S.n_rp; P.n_reads = n_reads;
                 P.match = match; P.mismatch = mismatch; P.gap = gap; P.tie_gt = (flags & SWB_F_TIE_GT) ? 1 : 0;
-                P.scores = res->d_scores.p; P.ck = ck.p; P.tmx = tmx.p; P.seam = seam.p;
+                P.scores = res->d_scores.p; P.rec = ck.p; P.tmx = tmx.p;
                 uint32_t *d_work = ctx->counters.p + 4 + S.buf;
                 const bool biased = fill_bias_ok(match, mismatch, gap, (int64_t)std::max(match, 0) * std::min<int64_t>(S.m_max, rs->max_len));
                 P.seam_bias = biased ? -gap : 0;               // the biased fill stores its seams biased

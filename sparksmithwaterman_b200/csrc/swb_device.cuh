@@ -69,11 +69,11 @@ __device__ __forceinline__ void load_profile(const uint32_t *p, uint32_t (&sv)[K
     }
 }
 
-// checkpoint of one lane: words 0..K-1 = H, word K = diag.  Layout per block:
-// [KW/4 quads][GL lanes][4 words] so that each STG.128 of a group is 128 contiguous bytes.
-// `ck` already points at this lane's first quad (+ t*4 words).
+// Block record of one lane (Geo<K>::RW words, contiguous): words 0..K-1 = H at the block start, word K = diag,
+// words KW..KW+CB-1 = the seam.  The fill stages a group's 8 records in shared memory (lane t at stage + t*RW;
+// 8 lanes x 16 B at a 144 B stride: conflict-free) and copies them out with coalesced STG.128.
 template <int K>
-__device__ __forceinline__ void store_checkpoint(uint32_t *ck, const uint32_t (&H)[K], uint32_t diag)
+__device__ __forceinline__ void stage_checkpoint(uint32_t *my_stage, const uint32_t (&H)[K], uint32_t diag)
 {
     constexpr int KW = Geo<K>::KW;
 #pragma unroll
@@ -83,15 +83,20 @@ __device__ __forceinline__ void store_checkpoint(uint32_t *ck, const uint32_t (&
         v.y = (4 * q + 1 < K) ? H[(4 * q + 1 < K) ? 4 * q + 1 : 0] : ((4 * q + 1 == K) ? diag : 0u);
         v.z = (4 * q + 2 < K) ? H[(4 * q + 2 < K) ? 4 * q + 2 : 0] : ((4 * q + 2 == K) ? diag : 0u);
         v.w = (4 * q + 3 < K) ? H[(4 * q + 3 < K) ? 4 * q + 3 : 0] : ((4 * q + 3 == K) ? diag : 0u);
-        *reinterpret_cast<uint4 *>(ck + q * (GL * 4)) = v;
+        *reinterpret_cast<uint4 *>(my_stage + 4 * q) = v;
     }
 }
 
-// word w (0..K) of lane t's checkpoint in block-relative layout
+// the group's staged block (GL * RW words) -> global, 128 contiguous bytes per round of the 8 lanes
 template <int K>
-__device__ __forceinline__ uint32_t load_checkpoint_word(const uint32_t *blk, int t, int w)
+__device__ __forceinline__ void copy_out_block(uint32_t *dst, const uint32_t *stage, int t)
 {
-    return blk[(w >> 2) * (GL * 4) + t * 4 + (w & 3)];
+    constexpr int RW = Geo<K>::RW;
+#pragma unroll
+    for (int q = 0; q < RW / 4; ++q) {
+        const uint4 v = *reinterpret_cast<const uint4 *>(stage + q * (GL * 4) + t * 4);
+        *reinterpret_cast<uint4 *>(dst + q * (GL * 4) + t * 4) = v;
+    }
 }
 
 __device__ __forceinline__ int half_of(uint32_t w, int half)

@@ -29,7 +29,9 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
-    uint32_t *prof = prof_all + warp * G::PROF_WORDS;
+    uint32_t *prof = prof_all + warp * (G::PROF_WORDS + 4 * GL * G::RW);
+    uint32_t *stage = prof + G::PROF_WORDS + g * (GL * G::RW);    // this group's block records, staged for a coalesced copy-out
+    uint32_t *my_stage = stage + t * G::RW;
     const int n_quads = (P.n_vrefs + 3) >> 2;
     const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
@@ -102,12 +104,11 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
             wprev = wnew;
             const bool fast = (s0 >= GL - 1) && (s0 + 16 <= nmin);
 
-            // SEAMS: the boundary row this lane receives at every step (matrix row t*K) goes to HBM next to
-            // the block checkpoints, so that the traceback can recompute ONE lane's tile (K rows x CB steps)
-            // without the lanes above it.  Layout per block: [CB/4 quads][GL lanes][4 steps], one STG.128 per
-            // lane every 4 steps = 128 contiguous bytes per group.  Only for blocks this segment owns.
+            // SEAMS: the boundary row this lane receives at every step (matrix row t*K) is kept next to the block
+            // checkpoint, so that the traceback can recompute ONE lane's tile (K rows x CB steps) without the lanes
+            // above it.  Record of (block, lane) = checkpoint + seam, contiguous (Geo::RW words): staged in shared
+            // memory (one STS.128 per 4 steps) and copied out at the block end, 128 contiguous bytes per group store.
             const bool own_chunk = (s0 < my_steps) && ((s0 >> 4) >= skip);
-            uint32_t *sq = P.seam + (blk0 + (s0 >> 4)) * (int64_t)(CB * GL) + t * 4;
             uint32_t t0 = 0, t1 = 0, t2 = 0;
 
             if (fast) {
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
                     diag = top;
                     tmax = colmax<K>(tmax, H);
                     if ((u & 3) == 0) t0 = top; else if ((u & 3) == 1) t1 = top; else if ((u & 3) == 2) t2 = top;
-                    else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (u >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
+                    else *reinterpret_cast<uint4 *>(my_stage + G::KW + (u >> 2) * 4) = make_uint4(t0, t1, t2, top);
                 }
             } else {
 #pragma unroll 1
@@ -157,24 +158,24 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
                         }
                         diag = top;
                         if (uu == 0) t0 = top; else if (uu == 1) t1 = top; else if (uu == 2) t2 = top;
-                        else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (uq >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
+                        else *reinterpret_cast<uint4 *>(my_stage + G::KW + (uq >> 2) * 4) = make_uint4(t0, t1, t2, top);
                     }
                 }
             }
 
-            // ---- end of a checkpoint block: state before step s0+16, tile max of the block
+            // ---- end of a checkpoint block: copy out its record, tile max, stage the next block's checkpoint
+            __syncwarp();
+            if (own_chunk) copy_out_block<K>(P.rec + (blk0 + (s0 >> 4)) * (int64_t)(GL * G::RW), stage, t);
+            __syncwarp();
             const int s_next = s0 + 16;
-            if ((s_next % CB) == 0) {
+            {
                 const int b = s_next / CB;                       // block that starts at s_next
                 if (s_next - CB < my_steps && b - 1 >= skip) {    // block b-1 is owned by this group
                     P.tmx[(blk0 + b - 1) * GL + t] = tmax;
                     gmax = vmax2(gmax, tmax);
                 }
                 tmax = 0;
-                if (s_next < my_steps && b >= skip) {             // block b is owned: checkpoint it
-                    uint32_t *ck = P.ck + (blk0 + b) * (int64_t)(G::KW * GL) + t * 4;
-                    store_checkpoint<K>(ck, H, diag);
-                }
+                stage_checkpoint<K>(my_stage, H, diag);           // state before step s_next
             }
         }
         // last (partial) block
@@ -213,7 +214,7 @@ static cudaError_t launch_fill_k(const BatchParams &P, uint32_t *work_counter, i
     const int64_t items = (int64_t)n_quads * P.n_rp;
     // persistent CTAs, never more than there is work
     const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count * ctas_per_sm);
-    const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
+    const size_t smem = (size_t)warps * (G::PROF_WORDS + 4 * GL * G::RW) * sizeof(uint32_t);
     cudaError_t e = cudaSuccess;
     {
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of

@@ -41,7 +41,9 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
-    uint32_t *prof = prof_all + warp * G::PROF_WORDS;
+    uint32_t *prof = prof_all + warp * (G::PROF_WORDS + 4 * GL * G::RW);
+    uint32_t *stage = prof + G::PROF_WORDS + g * (GL * G::RW);    // this group's block records (see swb_fill.cu)
+    uint32_t *my_stage = stage + t * G::RW;
     const int n_quads = (P.n_vrefs + 3) >> 2;
     const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
@@ -119,7 +121,6 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
             // SEAMS (see swb_fill.cu): the boundary row this lane receives at every step, stored BIASED -- the
             // bias of step u of a block is |gap| * (9 - t + u) in both halves (P.seam_bias tells the traceback).
             const bool own_chunk = (s0 < my_steps) && ((s0 >> 4) >= skip);
-            uint32_t *sq = P.seam + (blk0 + (s0 >> 4)) * (int64_t)(CB * GL) + t * 4;
             uint32_t t0 = 0, t1 = 0, t2 = 0;
 
             if (fast) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     diag = top;
                     tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
                     if ((u & 3) == 0) t0 = top; else if ((u & 3) == 1) t1 = top; else if ((u & 3) == 2) t2 = top;
-                    else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (u >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
+                    else *reinterpret_cast<uint4 *>(my_stage + G::KW + (u >> 2) * 4) = make_uint4(t0, t1, t2, top);
                 }
             } else {
 #pragma unroll 1
@@ -179,14 +180,18 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                         }
                         diag = top;
                         if (uu == 0) t0 = top; else if (uu == 1) t1 = top; else if (uu == 2) t2 = top;
-                        else if (own_chunk) *reinterpret_cast<uint4 *>(sq + (uq >> 2) * (GL * 4)) = make_uint4(t0, t1, t2, top);
+                        else *reinterpret_cast<uint4 *>(my_stage + G::KW + (uq >> 2) * 4) = make_uint4(t0, t1, t2, top);
                     }
                 }
             }
 
-            // ---- block boundary: move jref by CB columns, then (un-biased) tile max + checkpoint ----
+            // ---- block boundary: copy out the finished block's record, move jref by CB columns, then (un-biased)
+            // tile max + the next block's checkpoint into the staging record
+            __syncwarp();
+            if (own_chunk) copy_out_block<K>(P.rec + (blk0 + (s0 >> 4)) * (int64_t)(GL * G::RW), stage, t);
+            __syncwarp();
             const int s_next = s0 + 16;
-            if ((s_next % CB) == 0) {
+            {
 #pragma unroll
                 for (int r = 0; r < K; ++r) H[r] = imad_add(H[r], one, renorm);
                 diag = imad_add(diag, one, renorm);
@@ -198,13 +203,10 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     gmax = vmax2(gmax, tmax);
                 }
                 tmax = 0;
-                if (s_next < my_steps && b >= skip) {
-                    uint32_t U[K];
+                uint32_t U[K];
 #pragma unroll
-                    for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
-                    uint32_t *ck = P.ck + (blk0 + b) * (int64_t)(G::KW * GL) + t * 4;
-                    store_checkpoint<K>(ck, U, imad_add(diag, one, unbias));
-                }
+                for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
+                stage_checkpoint<K>(my_stage, U, imad_add(diag, one, unbias));
             }
         }
         {
@@ -238,7 +240,7 @@ static cudaError_t launch_fill_bias_k(const BatchParams &P, uint32_t *work_count
     const int warps = env_warps > 0 ? env_warps : 16;         // measured: 10/12/14/16 warps -> 42.0/39.8/39.4/39.2 ms
     const int64_t items = (int64_t)n_quads * P.n_rp;
     const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count);   // one CTA per SM
-    const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
+    const size_t smem = (size_t)warps * (G::PROF_WORDS + 4 * GL * G::RW) * sizeof(uint32_t);
     cudaError_t e = cudaSuccess;
     {
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of

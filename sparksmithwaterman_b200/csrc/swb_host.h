@@ -64,7 +64,7 @@ struct swb_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t stream_fill = nullptr;         // second stream: fill of batch k+1 runs beside the traceback of batch k
     bool pipeline = true;
-    DevBuf<uint32_t> ck2[2], tmx2[2], seam2[2];           // ping-pong checkpoint workspaces
+    DevBuf<uint32_t> ck2[2], tmx2[2];           // ping-pong checkpoint workspaces
     DevBuf<int32_t> rp2[2];
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::recursive_mutex mu;

@@ -32,6 +32,7 @@ constexpr int kKList[kNumK] = {4, 8, 13, 16, 19, 25, 32};
 
 template <int K> struct Geo {
     static constexpr int KW = ((K + 1 + 3) / 4) * 4;            // checkpoint words per lane (K cells + diag)
+    static constexpr int RW = KW + CB;                          // record words per (block, lane): checkpoint + seam
     static constexpr int KP = ((K + 3) / 4) * 4;                // profile words per lane per code
     static constexpr int KS = ((KP / 4) % 2 == 1) ? KP : KP + 4; // padded: odd number of 16B units -> conflict-free LDS.128
     static constexpr int CSTRIDE = GL * KS;                     // words per reference code
@@ -79,9 +80,11 @@ struct BatchParams {
     int32_t tie_gt;                 // traceback tie rule: 0 = '>=' cascade (a > i > d), 1 = strict '>' (d > i > a)
     // outputs / workspace
     int32_t  *scores;               // [n_refs_orig * n_reads]
-    uint32_t *ck;                   // checkpoints  [n_rp][blocks_per_rp][KW/4][GL][4]
+    // block records [n_rp][blocks_per_rp][GL lanes][RW words]: per lane, contiguous, the CHECKPOINT at the block
+    // start (K cells + diagonal boundary, unbiased) followed by the SEAM of the block (the boundary row the lane
+    // receives at each of its CB steps) -- everything a traceback needs to recompute the tile (block, lane).
+    uint32_t *rec;
     uint32_t *tmx;                  // tile maxima  [n_rp][blocks_per_rp][GL]
-    uint32_t *seam;                 // lane seams   [n_rp][blocks_per_rp][CB/4][GL][4]: boundary row received per step
     int32_t seam_bias;              // seam word of step u, lane t = H + seam_bias * (9 - t + u) (biased fill), 0 = plain
 };
 

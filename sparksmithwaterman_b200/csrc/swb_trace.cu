@@ -266,15 +266,15 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
 
             uint32_t H[K], diag = 0;
             {
-                const uint4 *ckA = reinterpret_cast<const uint4 *>(P.ck + (bk0 + b0) * (int64_t)(KW * GL)) + t;
-                const uint4 *ckB = reinterpret_cast<const uint4 *>(P.ck + (bk1 + b1) * (int64_t)(KW * GL)) + t;
+                const uint4 *ckA = reinterpret_cast<const uint4 *>(P.rec + ((bk0 + b0) * GL + t) * (int64_t)G::RW);
+                const uint4 *ckB = reinterpret_cast<const uint4 *>(P.rec + ((bk1 + b1) * GL + t) * (int64_t)G::RW);
                 const bool la = busy0 && b0 > 0, lb = busy1 && b1 > 0;
                 const uint32_t sel = rh ? 0x7632u : 0x5410u;        // (A.half rh) | (B.half rh) << 16
                 const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int q = 0; q < KW / 4; ++q) {
-                    const uint4 a = la ? __ldg(ckA + q * GL) : z;
-                    const uint4 bq = lb ? __ldg(ckB + q * GL) : z;
+                    const uint4 a = la ? __ldg(ckA + q) : z;
+                    const uint4 bq = lb ? __ldg(ckB + q) : z;
                     const uint32_t v[4] = {__byte_perm(a.x, bq.x, sel), __byte_perm(a.y, bq.y, sel),
                                            __byte_perm(a.z, bq.z, sel), __byte_perm(a.w, bq.w, sel)};
 #pragma unroll
@@ -285,11 +285,9 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
                     }
                 }
             }
-            // the path almost always continues into the block to the left: pull its checkpoints towards L2
-            if (t < KW / 4) {
-                if (busy0 && b0 > 1) prefetch_l2(P.ck + (bk0 + b0 - 1) * (int64_t)(KW * GL) + t * (GL * 4));
-                if (busy1 && b1 > 1) prefetch_l2(P.ck + (bk1 + b1 - 1) * (int64_t)(KW * GL) + t * (GL * 4));
-            }
+            // the path almost always continues into the block to the left: pull its records towards L2
+            if (busy0 && b0 > 1) prefetch_l2(P.rec + ((bk0 + b0 - 1) * GL + t) * (int64_t)G::RW);
+            if (busy1 && b1 > 1) prefetch_l2(P.rec + ((bk1 + b1 - 1) * GL + t) * (int64_t)G::RW);
             // reference-code windows of this lane for the block: 0-based columns j0 .. j0+15
             uint32_t win0, win1; int ulo0, uhi0, ulo1, uhi1;
             {

@@ -155,12 +155,12 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             const int b = busy ? step / CB : 0;
             int H[K], diag = 0;
             {
-                const uint4 *ck = reinterpret_cast<const uint4 *>(P.ck + (bk + b) * (int64_t)(KW * GL)) + t;
+                const uint4 *ck = reinterpret_cast<const uint4 *>(P.rec + ((bk + b) * GL + t) * (int64_t)G::RW);
                 const bool ld = busy && b > 0;
                 const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
                 for (int q = 0; q < KW / 4; ++q) {
-                    const uint4 a = ld ? __ldg(ck + q * GL) : z;
+                    const uint4 a = ld ? __ldg(ck + q) : z;
                     const uint32_t v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -172,13 +172,13 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             }
             int top[CB];
             {
-                const uint4 *sq = reinterpret_cast<const uint4 *>(P.seam + (bk + b) * (int64_t)(CB * GL)) + t;
+                const uint4 *sq = reinterpret_cast<const uint4 *>(P.rec + ((bk + b) * GL + t) * (int64_t)G::RW + KW);
                 const bool ld = busy && t > 0;                      // lane 0's boundary row is matrix row 0
                 const uint4 z = make_uint4(0, 0, 0, 0);
                 const int bias0 = sbias * (9 - t);
 #pragma unroll
                 for (int q = 0; q < CB / 4; ++q) {
-                    const uint4 a = ld ? __ldg(sq + q * GL) : z;
+                    const uint4 a = ld ? __ldg(sq + q) : z;
                     const uint32_t v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e)
@@ -310,7 +310,7 @@ __global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, co
         int H[K], diag = 0;
         uint32_t win = 0, rowok = 0;
         int ulo = 0, uhi = -1;
-        const uint4 *sq = reinterpret_cast<const uint4 *>(P.seam) + t;
+        const uint4 *sq = reinterpret_cast<const uint4 *>(P.rec);
         bool has_top = false;
 #pragma unroll
         for (int r = 0; r < K; ++r) { rc[r] = 0xFE; H[r] = 0; }
@@ -330,10 +330,10 @@ __global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, co
             }
             const int64_t blk = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref] + b;
             if (b > 0) {
-                const uint4 *ck = reinterpret_cast<const uint4 *>(P.ck + blk * (int64_t)(KW * GL)) + t;
+                const uint4 *ck = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW);
 #pragma unroll
                 for (int q = 0; q < KW / 4; ++q) {
-                    const uint4 a = __ldg(ck + q * GL);
+                    const uint4 a = __ldg(ck + q);
                     const uint32_t v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
@@ -343,7 +343,7 @@ __global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, co
                     }
                 }
             }
-            sq = reinterpret_cast<const uint4 *>(P.seam + blk * (int64_t)(CB * GL)) + t;
+            sq = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW + KW);
             has_top = t > 0;                                         // lane 0's boundary row is matrix row 0
             const uint32_t *rw = P.ref_words + P.ref_word_off[ref];
             const int j0 = b * CB - t;
@@ -359,7 +359,7 @@ __global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, co
 #pragma unroll 1
         for (int q = 0; q < CB / 4; ++q) {
             const uint4 a = nxt;
-            if (q + 1 < CB / 4 && has_top) nxt = __ldg(sq + (q + 1) * GL);
+            if (q + 1 < CB / 4 && has_top) nxt = __ldg(sq + q + 1);
             const uint32_t av[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
