@@ -138,6 +138,15 @@ def cpu_baseline_leg(refs, reads, threads, target_cells=2.0e10):
             "seconds": round(r["seconds"], 3)}
 
 
+def workload_config(B, refs_per_gpu, world, n_refs_local, ref_bases_local):
+    return {"workload": f"cfg2: 150 bp reads vs {refs_per_gpu:,} RefSeq-shaped refs per GPU, scores 5/-3/-4; "
+                        f"step = {B} reads of the 100k-read job x all refs, fill + all max cells + traceback",
+            "reads_per_step": B, "refs_per_gpu": n_refs_local, "ref_bases_per_gpu": int(ref_bases_local),
+            "pairs_per_step": B * n_refs_local * world,
+            "l2": "per-step working set (block records, tens of GB) exceeds the 126 MB L2; no explicit flush",
+            "parallelism": f"refshard{world}" if world > 1 else "single"}
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path, all host cores."""
     rank = int(os.environ.get("RANK", "0"))
@@ -168,8 +177,10 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 2),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": "cfg2 sample: 150 bp reads vs first 1,000 of the 10k RefSeq-shaped refs",
-                       "reads_per_step": per, "refs": len(refs)},
+            "config": dict(workload_config(args.reads_per_step, args.refs_per_gpu, 1, args.refs_per_gpu,
+                                           sum(len(r) for r in synth.make_refs(args.refs_per_gpu))),
+                           sample=f"each timed step = {per} reads x the first {len(refs)} refs of that workload "
+                                  f"({ref_bases * READ_LEN * per:.3g} cells), rate is size-invariant"),
             "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{per} reads x {len(refs)} refs per step, {args.steps} steps; "
                                        "C restatement of SmithWaterman.java + MapRef loop (no JVM in this image), "
@@ -328,14 +339,15 @@ def main():
     fill_gcups = cells_per_step_local * K / 1e9 / (agg["fill_ms"] * 1e-3) if agg["fill_ms"] > 0 else 0.0
     run_clock = clocks.get("sm_mhz") or sm_max
     # DRAM bytes of the fill kernel per launch, scaled from the committed ncu --set full capture
-    # (profiles/ncu_fill_trace_r01.json: 14.307 GB read+written for a 17-read-pair launch of this refset)
+    # (profiles/ncu_kernels_r01.json: one fill launch over a batch of `read_pairs_per_launch` read pairs of this refset)
     traffic = None
     try:
-        with open(os.path.join(ROOT, "profiles", "ncu_fill_trace_r01.json")) as f:
-            cap = json.load(f)[0]
+        with open(os.path.join(ROOT, "profiles", "ncu_kernels_r01.json")) as f:
+            prof = json.load(f)
+        cap = next(k for k in prof["kernels"] if "fill_bias_kernel" in k["kernel"])
         gb = float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])
         rp_per_launch = (B / 2.0) / max(agg["batches"] / K, 1)
-        traffic = round(gb * 1e9 / 17.0 * rp_per_launch)
+        traffic = round(gb * 1e9 / float(prof["meta"]["read_pairs_per_launch"]) * rp_per_launch)
     except Exception:
         traffic = None
     roofline = {"bound": "int_dpx", "kernel": "fill_bias_kernel<19>",
@@ -350,18 +362,13 @@ def main():
                         "achieved_gbs": round(agg["checkpoint_bytes"] / 1e9 / (agg["fill_ms"] * 1e-3), 1)
                         if agg["fill_ms"] > 0 else 0.0,
                         "peak_gbs": hbm_peak, "peak_kind": peak_kind,
-                        "note": "checkpoint + tile-max writes of the fill; HBM is the secondary bound"},
+                        "note": "block records (checkpoints + seams) + tile maxima written by the fill; HBM is the secondary bound"},
                 "fill_ms_per_step": round(agg["fill_ms"] / K, 3), "locate_ms_per_step": round(agg["locate_ms"] / K, 3),
                 "trace_ms_per_step": round(agg["trace_ms"] / K, 3)}
     line = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": round(step_ms, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "s16x2", "data": "synthetic",
-            "config": {"workload": f"cfg2: 150 bp reads vs {args.refs_per_gpu:,} RefSeq-shaped refs per GPU, scores 5/-3/-4; "
-                                   f"step = {B} reads of the 100k-read job x all refs, fill + all max cells + traceback",
-                       "reads_per_step": B, "refs_per_gpu": len(refs), "ref_bases_per_gpu": int(ref_bases),
-                       "pairs_per_step": B * len(refs) * world,
-                       "l2": "per-step working set (checkpoints, GBs) exceeds the 126 MB L2; no explicit flush",
-                       "parallelism": f"refshard{world}" if world > 1 else "single"},
+            "config": workload_config(B, args.refs_per_gpu, world, len(refs), ref_bases),
             "reads_per_s": round(B / (step_ms * 1e-3), 1),
             "refset_load_ms": round(refset_load_ms, 1),
             "roofline": roofline, "clocks": clocks,
