@@ -72,7 +72,7 @@ void swb_destroy(swb_ctx *c)
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
-    c->tasks.release(); c->keys_tmp.release(); c->sort_tmp.release();
+    c->tasks.release(); c->task_hits.release(); c->keys_tmp.release(); c->sort_tmp.release();
     for (int k = 0; k < 2; ++k) { c->ck2[k].release(); c->tmx2[k].release(); c->rp2[k].release(); }
     cudaStreamSynchronize(c->stream_fill);
     c->v_ref.release(); c->v_c0.release(); c->v_len.release(); c->v_skip.release(); c->v_end.release();
@@ -477,6 +477,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 uint32_t *d_work = ctx->counters.p + 4 + S.buf;
                 const bool biased = fill_bias_ok(match, mismatch, gap, (int64_t)std::max(match, 0) * std::min<int64_t>(S.m_max, rs->max_len));
                 P.seam_bias = biased ? -gap : 0;               // the biased fill stores its seams biased
+                P.tmx_slack = biased ? fill_sub_slack(match, mismatch, gap) : 0;
                 const int sp_fill = tic(1, sF);
                 if (biased)
                     CU(launch_fill_bias(K, P, d_work, ctx->sm_count, sF));
@@ -494,29 +495,38 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 const BatchParams &P = S.P;
                 const int n_rp = S.n_rp;
                 if (sF != st) CU(cudaStreamWaitEvent(st, S.ev_fill, 0));
-                if (flags & SWB_F_SCORES_ONLY) return SWB_OK;
+                const bool scores_only = (flags & SWB_F_SCORES_ONLY) != 0;
+                if (scores_only && P.tmx_slack == 0) return SWB_OK;      // the fill's pair scores are exact
                 uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1;
-                // ---- flagged tiles -> max cells -> sorted keys (one host sync: the two counts) ----
+                // ---- candidate tiles -> exact scores + max cells -> sorted keys (one host sync: the two counts) ----
                 const int sp_loc = tic(2, st);
                 const int64_t pairs_b = (int64_t)n_rp * 2 * n_refs;
-                uint32_t cap_tasks = (uint32_t)std::min<int64_t>(pairs_b * 2 + 1024, (int64_t)1 << 31);
+                uint32_t cap_tasks = (uint32_t)std::min<int64_t>(pairs_b * (P.tmx_slack > 0 ? 4 : 2) + 1024, (int64_t)1 << 31);
                 uint32_t cap_cells = (uint32_t)std::min<int64_t>(pairs_b * 2 + 4096, (int64_t)1 << 31);
                 uint32_t h_counts[2] = {0, 0};
                 for (int attempt = 0; attempt < 3; ++attempt) {
                     CU(ctx->tasks.reserve(cap_tasks, st));
+                    CU(ctx->task_hits.reserve((size_t)cap_tasks * locate_hit_bytes(), st));
                     CU(ctx->keys_tmp.reserve(cap_cells, st));
                     CU(cudaMemsetAsync(ctx->counters.p, 0, 8, st));
                     CU(launch_flag_tiles(P, ctx->tasks.p, cap_tasks, d_ntasks, ctx->sm_count, st));
-                    CU(launch_locate(K, P, ctx->tasks.p, d_ntasks, cap_tasks, ctx->keys_tmp.p, cap_cells, d_ncells,
-                                     ctx->sm_count, st));
+                    CU(launch_locate(K, P, ctx->tasks.p, d_ntasks, cap_tasks, ctx->task_hits.p, ctx->keys_tmp.p, cap_cells, d_ncells,
+                                     ctx->sm_count, 0, st));
                     launches += 2;
+                    if (!scores_only) {
+                        CU(launch_locate(K, P, ctx->tasks.p, d_ntasks, cap_tasks, ctx->task_hits.p, ctx->keys_tmp.p, cap_cells, d_ncells,
+                                         ctx->sm_count, 1, st));
+                        ++launches;
+                    }
                     CU(cudaMemcpyAsync(h_counts, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
                     CU(cudaStreamSynchronize(st));
                     if (h_counts[0] <= cap_tasks && h_counts[1] <= cap_cells) break;
                     if (attempt == 2) return fail(SWB_E_NOMEM, "swb_align: max-cell list did not fit after two retries");
+                    // a partial scan only raised pair scores towards their exact value: the retry stays correct
                     cap_tasks = std::max(cap_tasks, h_counts[0]);
                     cap_cells = std::max<uint32_t>(cap_cells, (uint32_t)std::min<uint64_t>((uint64_t)h_counts[1] * 2, 1ull << 31));
                 }
+                if (scores_only) { CU(toc(sp_loc, st)); return SWB_OK; }
                 const uint32_t n_cells = h_counts[1];
                 BatchOut bo;
                 bo.K = K;

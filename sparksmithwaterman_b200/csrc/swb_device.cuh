@@ -57,6 +57,21 @@ __device__ __forceinline__ uint32_t colmax(uint32_t m, const uint32_t (&H)[K])
     return m;
 }
 
+// SUBSAMPLED running maximum: rows 0, 2, 4, ... and the lane's last row K-1 only.  A cell in an odd row r has
+// the tracked cell (r+1, same column) right below it in the same lane, and H(r+1) >= H(r) + gap.
+template <int K>
+__device__ __forceinline__ uint32_t colmax_even(uint32_t m, const uint32_t (&H)[K])
+{
+    constexpr int NE = (K + 1) / 2;                 // even rows 0 .. 2*(NE-1)
+#pragma unroll
+    for (int e = 0; e + 1 < NE; e += 2) m = vmax3(m, H[2 * e], H[2 * e + 2]);
+    if (NE & 1) {
+        if (!(K & 1)) m = vmax3(m, H[2 * (NE - 1)], H[K - 1]);       // K even: last even row + the odd last row
+        else m = vmax2(m, H[2 * (NE - 1)]);                           // K odd: the last even row IS row K-1
+    } else if (!(K & 1)) m = vmax2(m, H[K - 1]);
+    return m;
+}
+
 // KP profile words of one reference code for this lane: KP/4 conflict-free LDS.128
 template <int KP>
 __device__ __forceinline__ void load_profile(const uint32_t *p, uint32_t (&sv)[KP])

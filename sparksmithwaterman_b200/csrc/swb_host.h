@@ -73,6 +73,7 @@ struct swb_ctx {
     DevBuf<int32_t> rp, slot;
     DevBuf<int32_t> v_ref, v_c0, v_len, v_skip, v_end;   // fill work units (reference segments) of the current class
     DevBuf<TileTask> tasks;
+    DevBuf<uint8_t> task_hits;                 // per candidate tile: exact maximum + buffered cells (locate scan -> emit)
     DevBuf<uint64_t> keys_tmp;
     DevBuf<uint8_t> sort_tmp;
     // wide (int32, long-pair) path scratch

@@ -85,6 +85,7 @@ struct BatchParams {
     // receives at each of its CB steps) -- everything a traceback needs to recompute the tile (block, lane).
     uint32_t *rec;
     uint32_t *tmx;                  // tile maxima  [n_rp][blocks_per_rp][GL]
+    int32_t tmx_slack;              // 0: tile maxima / pair scores of the fill are exact; > 0: subsampled, true max - slack <= tmx <= true max
     int32_t seam_bias;              // seam word of step u, lane t = H + seam_bias * (9 - t + u) (biased fill), 0 = plain
 };
 
@@ -158,11 +159,13 @@ cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int
 // swb_fill_bias.cu: same contract, horizontal gap folded into a column bias (2.5 instead of 3.5 ALU ops / cell pair)
 cudaError_t launch_fill_bias(int K, const BatchParams &P, uint32_t *work_counter, int sm_count, cudaStream_t st);
 bool fill_bias_ok(int match, int mismatch, int gap, int64_t max_score);
+int fill_sub_slack(int match, int mismatch, int gap);
 // swb_trace.cu
 cudaError_t launch_flag_tiles(const BatchParams &P, TileTask *tasks, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st);
 cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
-                          uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
-                          cudaStream_t st);
+                          uint32_t cap_tasks, void *hits, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
+                          int phase, cudaStream_t st);
+size_t      locate_hit_bytes();
 cudaError_t launch_trace(int K, const BatchParams &P, const uint64_t *keys, uint32_t n_cells,
                          int32_t *beginnings, int32_t *op_lens, uint32_t *ops, int ops_stride_words,
                          int sm_count, cudaStream_t st);

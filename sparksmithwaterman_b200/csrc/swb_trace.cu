@@ -23,13 +23,15 @@ namespace swb {
 
 // ---------------------------------------------------------------------------------------
 // One thread per global checkpoint block gb (x) and slice of the read pairs (y): the owning reference is
-// searched once and reused for every read pair; one task per (half, lane) whose tile maximum is the pair's.
+// searched once and reused for every read pair; one task per (half, lane) whose tile maximum is within
+// P.tmx_slack of the pair's (tracked) maximum -- with exact tile maxima (slack 0) that is equality.
 constexpr int FLAG_WARPS = 8;
 __global__ void __launch_bounds__(FLAG_WARPS * 32) flag_tiles_kernel(const BatchParams P, TileTask *tasks, uint32_t cap, uint32_t *count)
 {
     __shared__ uint32_t wsum[FLAG_WARPS];
     __shared__ uint32_t bbase;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int slack = P.tmx_slack;                               // 0: exact tile maxima; > 0: subsampled (swb_fill_bias.cu)
     const int64_t gb = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const bool in = gb < P.blocks_per_rp;
     int ref = 0, b = 0;
@@ -63,8 +65,9 @@ __global__ void __launch_bounds__(FLAG_WARPS * 32) flag_tiles_kernel(const Batch
             const uint32_t w[GL] = {v0[k].x, v0[k].y, v0[k].z, v0[k].w, v1[k].x, v1[k].y, v1[k].z, v1[k].w};
 #pragma unroll
             for (int t = 0; t < GL; ++t) {
-                if (sa[k] > 0 && half_of(w[t], 0) == sa[k]) ma[k] |= 1u << t;
-                if (sb[k] > 0 && half_of(w[t], 1) == sb[k]) mb[k] |= 1u << t;
+                const int wa = half_of(w[t], 0), wb = half_of(w[t], 1);
+                if (sa[k] > 0 && wa > 0 && wa >= sa[k] - slack) ma[k] |= 1u << t;
+                if (sb[k] > 0 && wb > 0 && wb >= sb[k] - slack) mb[k] |= 1u << t;
             }
             nt += (uint32_t)(__popc(ma[k]) + __popc(mb[k]));
         }

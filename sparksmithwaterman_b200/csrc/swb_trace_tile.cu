@@ -280,81 +280,89 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
 }
 
 // ---------------------------------------------------------------------------------------
-// Max-cell enumeration (ScoreMatrix.call, SmithWaterman.java:176-185): one thread per flagged tile
-// (half, reference, block, lane) recomputes the tile from checkpoint + seam and emits every cell whose
-// score equals the pair's maximum as a key (pair, i, j); the radix sort of the keys is the row-major order.
-// Up to 4 hits per tile wait in shared memory and are written with one warp-aggregated reservation;
-// tie-heavy tiles with more hits pay one atomic per extra hit.  The step loop is rolled in quads (the fully
-// unrolled version thrashed the instruction cache: 68 warps stalled on no_instruction per issue).
+// Max-cell enumeration (ScoreMatrix.call, SmithWaterman.java:176-185), one thread per candidate tile.
+//
+// The fill's tile maxima may be SUBSAMPLED (BatchParams::tmx_slack > 0): flag_tiles then hands over every tile
+// whose tracked maximum is within the slack of the pair's tracked maximum, and the pair score in P.scores is a
+// lower bound (score - slack <= tracked <= score).  Two passes make everything exact:
+//   scan : recompute the tile from its record (unpacked int32 DPX, 3 ops/cell + compare/select score), find its
+//          exact maximum E over the real rows (only values >= the tracked pair score matter) and the cells == E
+//          (<= 4 buffered per tile); atomicMax of E into the pair score  ->  P.scores is exact after the pass
+//   emit : tiles with E == the (now exact) pair score write their cells as keys (pair, i, j) -- one
+//          warp-aggregated reservation; tiles with more than 4 such cells (tie-heavy) recompute and emit directly.
+// The radix sort of the keys is the reference's row-major list order.  With exact tile maxima (slack 0) every
+// candidate is a real one and the scan finds E == score at once.
+// The step loop is rolled in quads (fully unrolled it thrashed the instruction cache: 68 warps stalled on
+// no_instruction per issue, 1.86 ms instead of 0.19).
 template <int K>
-__global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, const TileTask *tasks,
-                                                         const uint32_t *n_tasks_ptr, uint32_t cap_tasks,
-                                                         uint64_t *keys, uint32_t cap, uint32_t *count)
-{
-    using G = Geo<K>;
-    constexpr int KW = G::KW;
-    __shared__ uint32_t hitbuf[4 * NT];
-    const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);        // written by flag_tiles on the same stream
-    const int lane = threadIdx.x & 31;
-    const uint32_t n_threads = gridDim.x * blockDim.x;
-    const uint32_t iters = (n_tasks + n_threads - 1) / n_threads; // whole warps iterate together
-    const int gap = P.gap, match = P.match, mismatch = P.mismatch;
-    for (uint32_t it = 0; it < iters; ++it) {
-        const uint32_t task = it * n_threads + blockIdx.x * blockDim.x + threadIdx.x;
-        const bool live = task < n_tasks;
-        const TileTask T = live ? tasks[task] : TileTask{0, 0, 0, 0};
-        const int rp = (int)(T.rp_half >> 1), rh = (int)(T.rp_half & 1u), ref = (int)T.ref_sorted, b = (int)T.block, t = (int)T.lane;
-        int S = 0x7fffffff;
-        uint64_t pkey = 0;
-        int rc[K];
-        int H[K], diag = 0;
-        uint32_t win = 0, rowok = 0;
-        int ulo = 0, uhi = -1;
-        const uint4 *sq = reinterpret_cast<const uint4 *>(P.rec);
-        bool has_top = false;
+struct TileSweep {
+    int rc[K], H[K];
+    int diag, S, t, b;
+    uint32_t win, rowok;
+    int ulo, uhi;
+    const uint4 *sq;
+    bool has_top;
+    uint64_t pkey;
+    int64_t pair;
+
+    __device__ __forceinline__ void setup(const BatchParams &P, const TileTask &T, bool live)
+    {
+        using G = Geo<K>;
+        constexpr int KW = G::KW;
+        const int rp = (int)(T.rp_half >> 1), rh = (int)(T.rp_half & 1u), ref = (int)T.ref_sorted;
+        t = (int)T.lane; b = (int)T.block;
+        S = 0x7fffffff; pkey = 0; pair = 0; diag = 0; win = 0; rowok = 0; ulo = 0; uhi = -1;
+        sq = reinterpret_cast<const uint4 *>(P.rec); has_top = false;
 #pragma unroll
         for (int r = 0; r < K; ++r) { rc[r] = 0xFE; H[r] = 0; }
-        if (live) {
-            const int read_idx = P.rp_reads[2 * rp + rh];
-            const int64_t off = P.read_off[read_idx];
-            const int m = (int)(P.read_off[read_idx + 1] - off);
-            const int n = P.ref_len[ref];
-            const int64_t ro = P.ref_orig[ref];
-            S = P.scores[ro * P.n_reads + read_idx];
-            pkey = (uint64_t)T.rp_half * (uint64_t)P.n_refs + (uint64_t)ro;
+        if (!live) return;
+        const int read_idx = P.rp_reads[2 * rp + rh];
+        const int64_t off = P.read_off[read_idx];
+        const int m = (int)(P.read_off[read_idx + 1] - off);
+        const int n = P.ref_len[ref];
+        const int64_t ro = P.ref_orig[ref];
+        pair = ro * P.n_reads + read_idx;
+        S = P.scores[pair];
+        pkey = (uint64_t)T.rp_half * (uint64_t)P.n_refs + (uint64_t)ro;
 #pragma unroll
-            for (int r = 0; r < K; ++r) {
-                const int row = t * K + r;
-                rc[r] = (row < m) ? (int)P.read_codes[off + row] : 0xFE;
-                if (row < m) rowok |= 1u << r;
-            }
-            const int64_t blk = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref] + b;
-            if (b > 0) {
-                const uint4 *ck = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW);
+        for (int r = 0; r < K; ++r) {
+            const int row = t * K + r;
+            rc[r] = (row < m) ? (int)P.read_codes[off + row] : 0xFE;
+            if (row < m) rowok |= 1u << r;
+        }
+        const int64_t blk = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref] + b;
+        if (b > 0) {
+            const uint4 *ck = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW);
 #pragma unroll
-                for (int q = 0; q < KW / 4; ++q) {
-                    const uint4 a = __ldg(ck + q);
-                    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
+            for (int q = 0; q < KW / 4; ++q) {
+                const uint4 a = __ldg(ck + q);
+                const uint32_t v[4] = {a.x, a.y, a.z, a.w};
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int w = 4 * q + e;
-                        if (w < K) H[w < K ? w : 0] = half_of(v[e], rh);
-                        else if (w == K) diag = half_of(v[e], rh);
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    const int w = 4 * q + e;
+                    if (w < K) H[w < K ? w : 0] = half_of(v[e], rh);
+                    else if (w == K) diag = half_of(v[e], rh);
                 }
             }
-            sq = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW + KW);
-            has_top = t > 0;                                         // lane 0's boundary row is matrix row 0
-            const uint32_t *rw = P.ref_words + P.ref_word_off[ref];
-            const int j0 = b * CB - t;
-            const int wi = j0 >> 4;
-            const uint32_t a0 = (wi >= 0 && wi * 16 < n) ? __ldg(rw + wi) : 0u;
-            const uint32_t a1 = (wi + 1 >= 0 && (wi + 1) * 16 < n) ? __ldg(rw + wi + 1) : 0u;
-            win = __funnelshift_r(a0, a1, 2 * (j0 & 15));
-            ulo = -j0; uhi = n - j0 - 1;
         }
+        sq = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW + KW);
+        has_top = t > 0;                                         // lane 0's boundary row is matrix row 0
+        const uint32_t *rw = P.ref_words + P.ref_word_off[ref];
+        const int j0 = b * CB - t;
+        const int wi = j0 >> 4;
+        const uint32_t a0 = (wi >= 0 && wi * 16 < n) ? __ldg(rw + wi) : 0u;
+        const uint32_t a1 = (wi + 1 >= 0 && (wi + 1) * 16 < n) ? __ldg(rw + wi + 1) : 0u;
+        win = __funnelshift_r(a0, a1, 2 * (j0 & 15));
+        ulo = -j0; uhi = n - j0 - 1;
+        (void)rh;
+    }
+
+    // fn(j, cmax, H) after every real column; cmax = maximum over ALL K rows of the column
+    template <class Fn>
+    __device__ __forceinline__ void run(const BatchParams &P, int rh, Fn &&fn)
+    {
+        const int gap = P.gap, match = P.match, mismatch = P.mismatch;
         const int bias0 = P.seam_bias * (9 - t);
-        uint32_t n_hit = 0;
         uint4 nxt = has_top ? __ldg(sq) : make_uint4(0, 0, 0, 0);
 #pragma unroll 1
         for (int q = 0; q < CB / 4; ++q) {
@@ -379,27 +387,83 @@ __global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, co
                     cmax = max(cmax, H[r]);
                 }
                 diag = top;
-                // S is the pair's maximum over the real rows, so some H == S needs max(H) >= S (rows beyond the read's end
-                // sit below every real row, never feed one, and may exceed S when mismatch > 0: hence >=, not ==)
-                if (real && cmax >= S) {
-                    uint32_t rm = 0;
-#pragma unroll
-                    for (int r = 0; r < K; ++r) rm |= (H[r] == S) ? (1u << r) : 0u;
-                    rm &= rowok;
-                    const uint32_t j = (uint32_t)(b * CB - t + u + 1);
-                    while (rm) {
-                        const int r = __ffs((int)rm) - 1;
-                        rm &= rm - 1;
-                        const uint32_t code = ((uint32_t)(t * K + r + 1) << KEY_J_BITS) | j;
-                        if (n_hit < 4) hitbuf[n_hit * NT + threadIdx.x] = code;
-                        else { const uint32_t k = atomicAdd(count, 1u); if (k < cap) keys[k] = (pkey << (KEY_J_BITS + KEY_I_BITS)) | code; }
-                        ++n_hit;
-                    }
-                }
+                if (real) fn(b * CB - t + u + 1, cmax, H);
             }
         }
-        // one reservation per warp for the (up to 4) buffered hits of every lane
-        const uint32_t mine = min(n_hit, 4u);
+    }
+};
+
+struct TileHit { int32_t emax; uint32_t n; uint32_t code[4]; };
+
+template <int K>
+__global__ void __launch_bounds__(NT) tile_scan_kernel(const BatchParams P, const TileTask *tasks,
+                                                       const uint32_t *n_tasks_ptr, uint32_t cap_tasks, TileHit *hits)
+{
+    __shared__ uint32_t hitbuf[4 * NT];
+    const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);        // written by flag_tiles on the same stream
+    const uint32_t n_threads = gridDim.x * blockDim.x;
+    for (uint32_t task = blockIdx.x * blockDim.x + threadIdx.x; task < n_tasks; task += n_threads) {
+        const TileTask T = tasks[task];
+        TileSweep<K> W;
+        W.setup(P, T, true);
+        // rows beyond the read's end sit below every real row, never feed one, and may exceed the real maximum
+        // when mismatch > 0: the exact maximum is taken over the real rows only (rowok)
+        int E = max(W.S, 1);                                     // cells below the tracked pair score cannot be maximal
+        uint32_t n_hit = 0;
+        const int t = W.t;
+        const uint32_t rowok = W.rowok;
+        W.run(P, (int)(T.rp_half & 1u), [&](int j, int cmax, const int (&H)[K]) {
+            if (cmax < E) return;
+            int vm = 0;
+#pragma unroll
+            for (int r = 0; r < K; ++r) vm = max(vm, ((rowok >> r) & 1u) ? H[r] : 0);
+            if (vm < E) return;
+            if (vm > E) { E = vm; n_hit = 0; }
+            uint32_t rm = 0;
+#pragma unroll
+            for (int r = 0; r < K; ++r) rm |= (H[r] == E) ? (1u << r) : 0u;
+            rm &= rowok;
+            while (rm) {
+                const int r = __ffs((int)rm) - 1;
+                rm &= rm - 1;
+                if (n_hit < 4) hitbuf[n_hit * NT + threadIdx.x] = ((uint32_t)(t * K + r + 1) << KEY_J_BITS) | (uint32_t)j;
+                ++n_hit;
+            }
+        });
+        if (n_hit && E > W.S) atomicMax(P.scores + W.pair, E);
+        TileHit o;
+        o.emax = n_hit ? E : 0; o.n = n_hit;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) o.code[h] = (uint32_t)h < n_hit ? hitbuf[h * NT + threadIdx.x] : 0u;
+        hits[task] = o;
+    }
+}
+
+template <int K>
+__global__ void __launch_bounds__(NT) tile_emit_kernel(const BatchParams P, const TileTask *tasks,
+                                                       const uint32_t *n_tasks_ptr, uint32_t cap_tasks, const TileHit *hits,
+                                                       uint64_t *keys, uint32_t cap, uint32_t *count)
+{
+    const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);
+    const int lane = threadIdx.x & 31;
+    const uint32_t n_threads = gridDim.x * blockDim.x;
+    const uint32_t iters = (n_tasks + n_threads - 1) / n_threads; // whole warps iterate together
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t task = it * n_threads + blockIdx.x * blockDim.x + threadIdx.x;
+        const bool live = task < n_tasks;
+        TileTask T = TileTask{0, 0, 0, 0};
+        TileHit h; h.emax = 0; h.n = 0;
+        uint64_t pkey = 0;
+        bool hot = false;
+        if (live) {
+            T = tasks[task];
+            h = hits[task];
+            const int read_idx = P.rp_reads[T.rp_half];
+            const int64_t ro = P.ref_orig[T.ref_sorted];
+            pkey = ((uint64_t)T.rp_half * (uint64_t)P.n_refs + (uint64_t)ro) << (KEY_J_BITS + KEY_I_BITS);
+            hot = h.n > 0 && h.emax == P.scores[ro * P.n_reads + read_idx];   // exact since the scan pass
+        }
+        const uint32_t mine = hot ? min(h.n, 4u) : 0u;
         uint32_t inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += v; }
@@ -407,18 +471,44 @@ __global__ void __launch_bounds__(NT) tile_locate_kernel(const BatchParams P, co
         uint32_t base = 0;
         if (lane == 31 && total) base = atomicAdd(count, total);
         base = __shfl_sync(0xffffffffu, base, 31) + inc - mine;
-        for (uint32_t h = 0; h < mine; ++h)
-            if (base + h < cap) keys[base + h] = (pkey << (KEY_J_BITS + KEY_I_BITS)) | hitbuf[h * NT + threadIdx.x];
+        if (hot && h.n <= 4) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if ((uint32_t)k < mine && base + k < cap) keys[base + k] = pkey | h.code[k];
+        } else if (hot) {
+            // tie-heavy tile: more cells than the scan could buffer -- recompute, one atomic per cell beyond the first four
+            TileSweep<K> W;
+            W.setup(P, T, true);
+            const int S = h.emax;
+            const int t = W.t;
+            const uint32_t rowok = W.rowok;
+            uint32_t seen = 0;
+            W.run(P, (int)(T.rp_half & 1u), [&](int j, int cmax, const int (&H)[K]) {
+                if (cmax < S) return;
+                uint32_t rm = 0;
+#pragma unroll
+                for (int r = 0; r < K; ++r) rm |= (H[r] == S) ? (1u << r) : 0u;
+                rm &= rowok;
+                while (rm) {
+                    const int r = __ffs((int)rm) - 1;
+                    rm &= rm - 1;
+                    const uint32_t k = seen < 4 ? base + seen : atomicAdd(count, 1u);
+                    ++seen;
+                    if (k < cap) keys[k] = pkey | ((uint32_t)(t * K + r + 1) << KEY_J_BITS) | (uint32_t)j;
+                }
+            });
+        }
     }
 }
 
 template <int K>
 cudaError_t launch_tile_locate_k(const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
-                                 uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st)
+                                 void *hits, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, int phase, cudaStream_t st)
 {
     // the task count is read on the device; size the grid for the capacity, capped at a few waves
     const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(((int64_t)cap_tasks + NT - 1) / NT, (int64_t)sm_count * 32));
-    tile_locate_kernel<K><<<(unsigned)ctas, NT, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count);
+    if (phase == 0) tile_scan_kernel<K><<<(unsigned)ctas, NT, 0, st>>>(P, tasks, n_tasks, cap_tasks, static_cast<TileHit *>(hits));
+    else tile_emit_kernel<K><<<(unsigned)ctas, NT, 0, st>>>(P, tasks, n_tasks, cap_tasks, static_cast<const TileHit *>(hits), keys, cap, count);
     return cudaGetLastError();
 }
 
@@ -458,18 +548,21 @@ bool tile_trace_ok(int match, int mismatch, int gap)
     return 2 * (smax - (int64_t)gap) + sabs < 250;
 }
 
+size_t locate_hit_bytes() { return sizeof(TileHit); }
+
+// phase 0: scan (exact tile maxima -> exact pair scores, buffered cells); phase 1: emit keys
 cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, const uint32_t *n_tasks,
-                          uint32_t cap_tasks, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
-                          cudaStream_t st)
+                          uint32_t cap_tasks, void *hits, uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count,
+                          int phase, cudaStream_t st)
 {
     switch (K) {
-        case 4:  return launch_tile_locate_k<4>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 8:  return launch_tile_locate_k<8>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 13: return launch_tile_locate_k<13>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 16: return launch_tile_locate_k<16>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 19: return launch_tile_locate_k<19>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 25: return launch_tile_locate_k<25>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
-        case 32: return launch_tile_locate_k<32>(P, tasks, n_tasks, cap_tasks, keys, cap, count, sm_count, st);
+        case 4:  return launch_tile_locate_k<4>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 8:  return launch_tile_locate_k<8>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 13: return launch_tile_locate_k<13>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 16: return launch_tile_locate_k<16>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 19: return launch_tile_locate_k<19>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 25: return launch_tile_locate_k<25>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 32: return launch_tile_locate_k<32>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
     }
     return cudaErrorInvalidValue;
 }
