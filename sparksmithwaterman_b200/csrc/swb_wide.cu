@@ -18,6 +18,7 @@
 #include "swb_internal.h"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace swb {
 
@@ -413,7 +414,9 @@ cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items
     if (n_items == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * 4);
+    static const int env_ctas = getenv("SWB_WIDE_CTAS_PER_SM") ? atoi(getenv("SWB_WIDE_CTAS_PER_SM")) : 0;
+    const int per_sm = env_ctas > 0 ? env_ctas : 4;
+    const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
     if (P.n_symbols <= 8) {
         const size_t smem = (size_t)4 * 8 * KL * WL * sizeof(int32_t);      // 4 warps x 8 codes x BH rows
         static bool attr_set = false;
