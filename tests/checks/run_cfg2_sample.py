@@ -5,7 +5,7 @@
   * the per-reference wrapping totals of that block,
   * complete results (cells, beginnings, both strings) of --full-pairs random pairs.
 
-    python tools/run_cfg2_sample.py [--reads 2048] [--score-reads 128] [--score-refs 1000] [--full-pairs 1500]
+    python tests/checks/run_cfg2_sample.py [--reads 2048] [--score-reads 128] [--score-refs 1000] [--full-pairs 1500]
 """
 import argparse
 import json
@@ -14,7 +14,7 @@ import random
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def main():

@@ -7,7 +7,7 @@ the 2-bit column string over the original sequences reproduces the score with ev
 positive; it ends in the reported max cell; `beginning` matches) and, for --oracle-pairs
 pairs, bit-exact equality with the CPU oracle (two-row score + 2-bit-plane traceback).
 
-    python tools/run_cfg3.py [--length 100000] [--pairs 10] [--oracle-pairs 1] [--out profiles/cfg3_r01.json]
+    python tests/checks/run_cfg3.py [--length 100000] [--pairs 10] [--oracle-pairs 1] [--out profiles/cfg3_r01.json]
 """
 import argparse
 import json
@@ -16,7 +16,7 @@ import random
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def mutate(rnd, s, sub, indel):

@@ -4,13 +4,13 @@ against its reference shard; per-pair results must be bit-exact vs the oracle on
 shard, and the merged best-hit records must be identical for every N (compared with the
 single-shard answer computed on rank 0).
 
-    torchrun --nproc-per-node N tools/run_cfg5_multigpu.py
+    torchrun --nproc-per-node N tests/checks/run_cfg5_multigpu.py
 """
 import json
 import os
 import sys
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 import numpy as np
 import torch

@@ -3,7 +3,7 @@
 writes one record per point: wall ms of swb_align (host buffers in, results out), GCUPS, max
 score; a sample of points is checked pair-by-pair against the CPU oracle.
 
-    python tools/run_engineer_sweeps.py [--out profiles/engineer_sweeps_r01.json] [--check-every 6]
+    python tests/checks/run_engineer_sweeps.py [--out profiles/engineer_sweeps_r01.json] [--check-every 6]
 """
 import argparse
 import json
@@ -11,7 +11,7 @@ import os
 import sys
 import time
 
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 
 
 def main():

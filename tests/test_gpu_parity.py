@@ -107,3 +107,19 @@ def test_large_scores_fall_back_to_the_group_traceback(engine):
     reads = [base[50:200], base[300:380] + "TT" + base[380:440], "ACGT" * 30, base[600:700][::-1], "A" * 20]
     for scores in ((100, -90, -30), (60, -50, -40), (90, 10, -80)):
         check_pairs(engine, refs, reads, scores, max_cells=200)
+
+
+def test_max_cell_at_every_tile_position(engine):
+    """The fill's tile maxima are subsampled (even rows x even steps + the tile's last row / step); the locate
+    stage must still find the exact score and every maximum cell.  Exact-substring reads put the unique maximum at
+    (m, j) for every j mod 16 and row parities / lane-final rows of the K = 4, 8, 13, 19 classes."""
+    rnd = random.Random(93)
+    base = "".join(rnd.choice("ACGT") for _ in range(420))
+    refs = [base, base[3:400]]
+    reads = []
+    for m in (3, 4, 5, 8, 9, 31, 32, 33, 37, 64, 65, 97, 104, 105, 149, 150, 151, 152):
+        for k in range(3):
+            j = 160 + ((7 * m + 5 * k) % 19)                   # end column: all residues mod 16 over the set
+            reads.append(base[j - m:j])
+    for scores in ((5, -3, -4), (10, -2, -7), (3, 1, -2)):     # the three fuzz score sets that take the subsampled fill
+        check_pairs(engine, refs, reads, scores, max_cells=50)
