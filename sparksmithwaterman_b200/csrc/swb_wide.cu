@@ -28,6 +28,14 @@ namespace {
 
 __device__ __forceinline__ int ld_cg(const int32_t *p) { return __ldcg(p); }
 __device__ __forceinline__ int ld_volatile(const int32_t *p) { return *reinterpret_cast<const volatile int32_t *>(p); }
+// progress counters: release store by the lane that wrote the band's bottom row, acquire load by the polling lane
+__device__ __forceinline__ void st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ int ld_acquire(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 struct WCtx {
     const uint8_t *ref;     // codes of this pair's reference
@@ -176,17 +184,18 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
             if (band > 0) {
                 const int need = min(C.n, s0 + 32);
                 if (seen < need) {
+                    // lane 0 acquires; the other lanes' boundary loads (ld.cg, L2) are issued after the loop's
+                    // branch has resolved on the acquired value, i.e. after the publisher's release
                     if (lane == 0) {
-                        int v = ld_volatile(prog_up);
-                        while (v < need) { __nanosleep(64); v = ld_volatile(prog_up); }
+                        int v = ld_acquire(prog_up);
+                        while (v < need) { __nanosleep(32); v = ld_acquire(prog_up); }
                         seen = v;
                     }
                     seen = __shfl_sync(0xffffffffu, seen, 0);
-                    __threadfence();
                 }
             }
             const int tbuf = top_prefetch(C, band, s0, lane);
-#pragma unroll 1
+#pragma unroll 4
             for (int u = 0; u < 32; ++u) {
                 const int s = s0 + u;
                 int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
@@ -228,9 +237,8 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                 diag = top;
             }
             cprev = ccur;
-            // publish: lane 31 has finished every column <= s0 + 1
-            __threadfence();
-            if (lane == WL - 1) *reinterpret_cast<volatile int32_t *>(prog_me) = min(C.n, max(0, s0 + 1));
+            // publish: lane 31 (the only writer of the bottom row) has finished every column <= s0 + 1
+            if (lane == WL - 1) st_release(prog_me, min(C.n, max(0, s0 + 1)));
             const int s_next = s0 + 32;
             if ((s_next % WCB) == 0) {
                 const int b = s_next / WCB;
@@ -252,8 +260,7 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                 bmax = max(bmax, tmax);
             }
         }
-        __threadfence();
-        if (lane == WL - 1) *reinterpret_cast<volatile int32_t *>(prog_me) = C.n;
+        if (lane == WL - 1) st_release(prog_me, C.n);
 #pragma unroll
         for (int o = 16; o; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
         if (lane == 0 && bmax > 0)
