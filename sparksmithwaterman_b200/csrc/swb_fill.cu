@@ -6,7 +6,7 @@
 // AlignmentScore.call (reference SmithWaterman.java:217-252, :277-280, :309-318) as
 // iterated by ScoreMatrix.call (:157-187).  Scores only: the tie rule of the ">="
 // cascade affects alignment types, never H, so the fill needs no direction state.
-// The traceback kernels (swb_trace.cu) restart from the checkpoints written here.
+// The locate / traceback kernels (swb_trace_tile.cu, swb_trace.cu) restart from the block records written here.
 //
 // Per cell pair (two reads packed in s16x2):  VIADDMNMX.RELU  x   = max(NW + s, 0)
 //                                             VIADDMNMX       pre = max(W + gap, x)

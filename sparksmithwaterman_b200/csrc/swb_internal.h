@@ -6,10 +6,12 @@
 //   * the 8 lanes form a skewed wavefront: at STEP s lane t computes column j = s - t + 1,
 //     the boundary row travels to lane t+1 with one __shfl_up_sync per step,
 //   * two reads are packed in the two s16 halves of every register (DPX s16x2 ops),
-//   * every CB steps the lanes' registers (K cells + the diagonal boundary) are written to
-//     HBM as a CHECKPOINT, together with the tile maximum of the last CB steps; the
-//     traceback kernels restart from a checkpoint and recompute only the blocks a path
-//     crosses, so no direction plane is ever written.
+//   * per block of CB steps and lane the fill writes one RECORD to HBM: the CHECKPOINT (the lane's
+//     K cells + the diagonal boundary at the block start) and the SEAM (the boundary row the
+//     lane receives at each of the CB steps), plus the lane's tile maximum.  A record is all a
+//     TILE (block, lane) = K rows x CB skewed columns needs to be recomputed on its own; the
+//     locate / traceback kernels recompute only the tiles that hold maximum cells or that a
+//     path crosses, so no direction plane is ever written.
 #pragma once
 
 #include <cstdint>

@@ -1,18 +1,17 @@
-// swb_trace.cu -- maximum-cell enumeration and traceback of the short-read path.
+// swb_trace.cu -- short-read path: tile flagging, the group-based traceback (fallback), small reductions.
 //
-// The fill (swb_fill.cu) leaves, per pair, the maximum score, per-(lane, block) tile
-// maxima and per-block register checkpoints.  Here:
-//   flag_tiles : tiles whose maximum equals the pair's maximum (and is > 0)
-//   locate     : (swb_trace_tile.cu) recompute each flagged tile from checkpoint + seam, emit every cell == max
-//                -> the reference's max-cell list (ScoreMatrix.call, SmithWaterman.java:176-185);
-//                keys (pair, i, j) are radix-sorted, which IS the row-major list order
-//   trace      : per max cell, GetAlignment.call (SmithWaterman.java:354-436): walk while
-//                the score is positive; the type of a positive cell is re-derived from the
-//                scores with the priority of the ">=" cascade (:228,:236,:245): alignment,
-//                then insertion, then deletion.  Blocks are recomputed lazily, right to
-//                left, each from its own checkpoint, so every H the walk reads is exact.
-// The recompute is unpacked int32 (DPX s32 ops); one 8-lane group per task, same lane/row/
-// step geometry as the fill so the checkpoints drop straight into registers.
+// The fill (swb_fill*.cu) leaves, per pair, the (tracked) maximum score, per-(block, lane) tile maxima and the
+// block records.  Here:
+//   flag_tiles : tiles whose maximum is within P.tmx_slack of the pair's tracked maximum (slack 0: equal to it)
+//   trace      : GROUP-based traceback, used when the byte tiles of the default kernel (swb_trace_tile.cu) cannot
+//                represent the score set (tile_trace_ok): per max cell, GetAlignment.call (SmithWaterman.java:
+//                354-436): walk while the score is positive; the type of a positive cell is re-derived from the
+//                scores with the priority of the ">=" cascade (:228,:236,:245): alignment, then insertion, then
+//                deletion.  Blocks are recomputed lazily, right to left, each from its own checkpoints (all 8
+//                lanes of the group), so every H the walk reads is exact.
+//   ref_totals, best_hits, cell_offsets, key sort: the per-call reductions of Distribution.MapRef (:424) and
+//                the best-hit records merged across GPUs.
+// Max-cell enumeration and the default traceback live in swb_trace_tile.cu.
 #include "swb_internal.h"
 #include "swb_device.cuh"
 
