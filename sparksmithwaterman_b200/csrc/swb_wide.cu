@@ -334,13 +334,32 @@ __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, co
 // Traceback: one warp per max cell.  Tile of the current (band, block):
 //   tile[c][lane][w], c = 0..WCB (c = 0: checkpointed column), w = 0: boundary row above the
 //   lane (row band*BH + lane*KL of the matrix), w = 1..KL: the lane's rows.
+// BYTE: the tile keeps only the low 8 bits of every score (12 bytes per lane and column instead of 36), which
+// quadruples the warps per SM.  That is enough because the walker carries the exact score of its cell (the pair
+// maximum minus the moves so far) and a candidate never lies 250 or more below H (tile_trace_ok): equality of the
+// low bytes is equality.  Other score sets use the int32 tile.
+template <bool BYTE>
 __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, const uint64_t *keys, uint32_t n_cells,
                                                          int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
                                                          int64_t ops_stride)
 {
-    extern __shared__ int32_t wtile[];                       // [WCB + 1][WL][KL + 1]
+    extern __shared__ int32_t wtile[];                       // [WCB + 1][WL][KL + 1] words, or [WCB + 1][WL][3] words of bytes
     const int lane = threadIdx.x;
-    constexpr int CW = WL * (KL + 1);
+    constexpr int LW = BYTE ? (KL + 1 + 3) / 4 : KL + 1;      // words per lane and column
+    constexpr int CW = WL * LW;
+    auto store_col = [&](int c, int top, const int (&Hc)[KL]) {
+        int32_t *col = wtile + c * CW + lane * LW;
+        if (BYTE) {
+            static_assert(KL == 8, "byte tile packing assumes 8 rows per lane");
+            col[0] = (int32_t)__byte_perm(__byte_perm((uint32_t)top, (uint32_t)Hc[0], 0x0040), __byte_perm((uint32_t)Hc[1], (uint32_t)Hc[2], 0x0040), 0x5410);
+            col[1] = (int32_t)__byte_perm(__byte_perm((uint32_t)Hc[3], (uint32_t)Hc[4], 0x0040), __byte_perm((uint32_t)Hc[5], (uint32_t)Hc[6], 0x0040), 0x5410);
+            col[2] = Hc[7] & 0xff;
+        } else {
+            col[0] = top;
+#pragma unroll
+            for (int r = 0; r < KL; ++r) col[r + 1] = Hc[r];
+        }
+    };
     for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
         const uint64_t key = keys[cell];
         const int pair = (int)wide_key_pair(key);
@@ -359,24 +378,14 @@ __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, cons
             load_rows(C, band, lane, rc, all_valid);
             int H[KL], diag;
             load_wide_state(C, band, blk, lane, H, diag);
-            {
-                int32_t *col = wtile + lane * (KL + 1);
-                col[0] = diag;
-#pragma unroll
-                for (int r = 0; r < KL; ++r) col[r + 1] = H[r];
-            }
+            store_col(0, diag, H);
             int cprev = code_prefetch(C, blk * WCB - 32, lane);
             for (int u0 = 0; u0 < WCB; u0 += 32) {
                 const int s0 = blk * WCB + u0;
                 const int tbuf = top_prefetch(C, band, s0, lane);
                 const int ccur = code_prefetch(C, s0, lane);
                 wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
-                           [&](int u, int top, const int (&Hc)[KL], bool, int) {
-                               int32_t *col = wtile + (u0 + u + 1) * CW + lane * (KL + 1);
-                               col[0] = top;
-#pragma unroll
-                               for (int r = 0; r < KL; ++r) col[r + 1] = Hc[r];
-                           });
+                           [&](int u, int top, const int (&Hc)[KL], bool, int) { store_col(u0 + u + 1, top, Hc); });
                 cprev = ccur;
             }
             __syncwarp();
@@ -387,13 +396,21 @@ __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, cons
                     const int r = (ci - 1) % KL + 1;                        // 1..KL
                     const int c = cj - (blk * WCB - tc);
                     if (c < 1 || c > WCB) break;
-                    const int32_t *lt = wtile + c * CW + tc * (KL + 1) + r;
-                    const int hw = lt[-CW], hn = lt[-1], hnw = lt[-CW - 1];
+                    int hw, hn, hnw;
+                    if (BYTE) {
+                        const uint8_t *lt = reinterpret_cast<const uint8_t *>(wtile + c * CW + tc * LW) + r;
+                        hw = lt[-CW * 4]; hn = lt[-1]; hnw = lt[-CW * 4 - 1];
+                    } else {
+                        const int32_t *lt = wtile + c * CW + tc * LW + r;
+                        hw = lt[-CW]; hn = lt[-1]; hnw = lt[-CW - 1];
+                    }
                     const int sc = (C.read[ci - 1] == C.ref[cj - 1]) ? C.match : C.mismatch;
-                    const bool eq_a = (hnw + sc == hcur), eq_i = (hn + C.gap == hcur), eq_d = (hw + C.gap == hcur);
+                    const int mask = BYTE ? 0xff : -1;
+                    const bool eq_a = ((hnw + sc - hcur) & mask) == 0, eq_i = ((hn + C.gap - hcur) & mask) == 0,
+                               eq_d = ((hw + C.gap - hcur) & mask) == 0;
                     const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
                     beginning = cj;
-                    hcur = op == 1u ? hnw : (op == 2u ? hn : hw);
+                    hcur -= (op == 1u) ? sc : C.gap;                      // exact score of the next cell
                     ci -= (op != 3u);
                     cj -= (op != 2u);
                     opword |= op << (2 * (int)(oplen & 15));
@@ -461,15 +478,19 @@ cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_
                               int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
 {
     if (n_cells == 0) return cudaSuccess;
-    const size_t smem = (size_t)(WCB + 1) * WL * (KL + 1) * sizeof(int32_t);
+    const bool bytes = tile_trace_ok(P.match, P.mismatch, P.gap);        // same bound as the short path's byte tiles
+    const size_t smem = (size_t)(WCB + 1) * WL * (bytes ? (KL + 1 + 3) / 4 : KL + 1) * sizeof(int32_t);
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)((size_t)(WCB + 1) * WL * (KL + 1) * sizeof(int32_t)));
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
-    const int64_t ctas = std::min<int64_t>(n_cells, (int64_t)sm_count * 3);
-    wide_trace_kernel<<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
+    const int per_sm = bytes ? 8 : 3;                                    // CTAs (warps) per SM that fit in shared memory
+    const int64_t ctas = std::min<int64_t>(n_cells, (int64_t)sm_count * per_sm);
+    if (bytes) wide_trace_kernel<true><<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
+    else       wide_trace_kernel<false><<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
     return cudaGetLastError();
 }
 
