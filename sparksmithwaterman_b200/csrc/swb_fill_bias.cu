@@ -252,11 +252,10 @@ static cudaError_t launch_fill_bias_k2(const BatchParams &P, uint32_t *work_coun
     {
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of
         // shared memory each) must be able to co-reside with this kernel's CTA on the same SM
-        static bool carve_set = false;
-        if (!carve_set) {
+        static PerDeviceOnce carve;
+        if (carve.need()) {
             e = cudaFuncSetAttribute(fill_bias_kernel<K, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (e != cudaSuccess) return e;
-            carve_set = true;
         }
     }
     if (smem > 48 * 1024) {

@@ -54,6 +54,20 @@ __host__ __device__ inline uint64_t key_pair(uint64_t k) { return k >> (KEY_J_BI
 __host__ __device__ inline uint32_t key_i(uint64_t k) { return (uint32_t)(k >> KEY_J_BITS) & ((1u << KEY_I_BITS) - 1); }
 __host__ __device__ inline uint32_t key_j(uint64_t k) { return (uint32_t)k & ((1u << KEY_J_BITS) - 1); }
 
+// cudaFuncSetAttribute is per device (context): a process may hold one swb_ctx per GPU (Spark local[N] over 8 GPUs
+// in one JVM), so "already set" is tracked per device.  need() is true the first time it is called on the current device.
+struct PerDeviceOnce {
+    bool done[64] = {};
+    bool need()
+    {
+        int d = 0;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 struct TileTask { uint32_t rp_half; uint32_t ref_sorted; uint32_t block; uint32_t lane; };   // one flagged tile
 
 // Everything the short-path kernels need for one batch of read pairs of one K class.

@@ -470,11 +470,10 @@ static cudaError_t launch_trace_k(const BatchParams &P, const uint64_t *keys, ui
     int warps = 4;
     while (warps > 1 && prof_bytes + per_group * 4 * warps + tail_bytes > 112 * 1024) --warps;   // two CTAs per SM
     const size_t smem = prof_bytes + per_group * 4 * warps + tail_bytes;
-    static bool attr_set[64] = {false};
-    if (!attr_set[K]) {
+    static PerDeviceOnce attr;                    // one per template instantiation (K)
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set[K] = true;
     }
     // chunks of the sorted cell list: several per SM for balance, each long enough to amortise its profile
     int chunk = (int)std::max<int64_t>(256, ((int64_t)n_cells + sm_count * 4 - 1) / (sm_count * 4));

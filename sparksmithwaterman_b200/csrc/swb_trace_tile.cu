@@ -519,12 +519,11 @@ cudaError_t launch_tile_trace_k(const BatchParams &P, const uint64_t *keys, uint
     using TG = TileGeo<K>;
     if (n_cells == 0) return cudaSuccess;
     const size_t smem = ((size_t)TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT) * sizeof(uint32_t) + (((size_t)GL * K + 15) / 16) * 16;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(tile_trace_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_trace_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     // chunks of the sorted cell list: many per SM for balance, each long enough to amortise its profile
     static const int env_div = getenv("SWB_TRACE_CHUNKS_PER_SM") ? atoi(getenv("SWB_TRACE_CHUNKS_PER_SM")) : 0;

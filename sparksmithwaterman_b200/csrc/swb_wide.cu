@@ -27,7 +27,6 @@ using namespace wide;
 namespace {
 
 __device__ __forceinline__ int ld_cg(const int32_t *p) { return __ldcg(p); }
-__device__ __forceinline__ int ld_volatile(const int32_t *p) { return *reinterpret_cast<const volatile int32_t *>(p); }
 // progress counters: release store by the lane that wrote the band's bottom row, acquire load by the polling lane
 __device__ __forceinline__ void st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int ld_acquire(const int32_t *p)
@@ -443,11 +442,10 @@ cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items
     const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
     if (P.n_symbols <= 8) {
         const size_t smem = (size_t)4 * 8 * KL * WL * sizeof(int32_t);      // 4 warps x 8 codes x BH rows
-        static bool attr_set = false;
-        if (!attr_set) {
+        static PerDeviceOnce attr;
+        if (attr.need()) {
             e = cudaFuncSetAttribute(wide_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             if (e != cudaSuccess) return e;
-            attr_set = true;
         }
         wide_fill_kernel<true><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
     } else {
@@ -480,12 +478,11 @@ cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_
     if (n_cells == 0) return cudaSuccess;
     const bool bytes = tile_trace_ok(P.match, P.mismatch, P.gap);        // same bound as the short path's byte tiles
     const size_t smem = (size_t)(WCB + 1) * WL * (bytes ? (KL + 1 + 3) / 4 : KL + 1) * sizeof(int32_t);
-    static bool attr_set = false;
-    if (!attr_set) {
+    static PerDeviceOnce attr;
+    if (attr.need()) {
         cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)((size_t)(WCB + 1) * WL * (KL + 1) * sizeof(int32_t)));
         if (e != cudaSuccess) return e;
-        attr_set = true;
     }
     const int per_sm = bytes ? 8 : 3;                                    // CTAs (warps) per SM that fit in shared memory
     const int64_t ctas = std::min<int64_t>(n_cells, (int64_t)sm_count * per_sm);
