@@ -121,3 +121,70 @@ def test_file_formats_mirror_inoutops(tmp_path):
     txt = inout.get_output_str(["ACGT"], (2, 1), 20, 7, [([">gi|1|a", "ACGT"], [(1, ["ACGT", "ACGT"])])])
     assert txt == ("Execution Time = 7 ms\n\n# Reference Sequences = 2\n# Reads = 1\n\nInput:\nACGT\n\n"
                    "Maximum alignment score = 20\nReference:\n>gi|1|a\nACGT\n\n\tIndex = 1\n\tACGT\n\tACGT\n\n")
+
+
+def _c_prototypes():
+    """name -> (return kind, [arg kinds]) from include/swb200.h; kinds: 'int' (32-bit), 'long' (64-bit), 'ptr', 'void'."""
+    with open(os.path.join(ROOT, "include", "swb200.h")) as f:
+        text = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    text = re.sub(r"#.*", "", text)
+
+    def kind(t):
+        t = t.strip()
+        if "*" in t:
+            return "ptr"
+        base = t.replace("const", "").split()
+        if not base or base == ["void"]:
+            return "void"
+        if base[0] in ("int64_t", "uint64_t"):
+            return "long"
+        assert base[0] in ("int", "int32_t", "uint32_t"), t
+        return "int"
+
+    out = {}
+    for m in re.finditer(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(swb_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text):
+        ret, name, args = m.group(1), m.group(2), m.group(3)
+        arglist = [a for a in (x.strip() for x in args.split(",")) if a and a != "void"]
+        # drop the parameter name: everything up to the last identifier
+        kinds = [kind(re.sub(r"\b[A-Za-z_][A-Za-z0-9_]*$", "", a) if not a.rstrip().endswith("*") else a) for a in arglist]
+        out[name] = (kind(ret), kinds)
+    return out
+
+
+def test_ctypes_and_java_bindings_match_the_header():
+    """No JDK exists here, so the Java layer cannot be compiled: at least its Panama descriptors (and the ctypes
+    signatures the tests run through) must agree with swb200.h argument by argument."""
+    import ctypes as C
+    protos = _c_prototypes()
+    assert len(protos) >= 30
+
+    def ckind(t):
+        if t is None:
+            return "void"
+        if t in (C.c_int, C.c_int32, C.c_uint32):
+            return "int"
+        if t in (C.c_int64, C.c_uint64, C.c_longlong):
+            return "long"
+        return "ptr"
+
+    for name, (restype, argtypes) in _ffi.SIGNATURES.items():
+        ret, args = protos[name]
+        assert [ckind(a) for a in argtypes] == args, (name, args)
+        assert ckind(restype) == ret, (name, ret)
+
+    with open(os.path.join(ROOT, "java", "sw", "NativeSW.java")) as f:
+        java = f.read()
+    jk = {"JAVA_INT": "int", "JAVA_LONG": "long", "ADDRESS": "ptr"}
+    found = 0
+    for m in re.finditer(r'h\(\s*"(swb_[a-z0-9_]+)"\s*,\s*FunctionDescriptor\.(ofVoid|of)\(([^)]*)\)', java):
+        name, how, desc = m.group(1), m.group(2), [x.strip() for x in m.group(3).split(",") if x.strip()]
+        ret, args = protos[name]
+        kinds = [jk[d] for d in desc]
+        if how == "of":
+            assert kinds[0] == ret, (name, kinds[0], ret)
+            kinds = kinds[1:]
+        else:
+            assert ret == "void", name
+        assert kinds == args, (name, kinds, args)
+        found += 1
+    assert found >= 12
