@@ -131,3 +131,25 @@ def test_distributed_sw_tie_mode(engine):
             exp = oracle.align(ref, read, *scores, tie_gt=True)
             got = op.call([ref, read], list(scores))
             assert got == (exp.score, [(b, [ra, qa]) for (b, ra, qa) in exp.sites]), (ref[:20], read[:20], scores)
+
+
+def test_scores_only_mode_is_exact(engine):
+    """SWB_F_SCORES_ONLY: no max-cell lists, no traceback -- but the scores must be the exact maxima.  With the
+    subsampled tile maxima of the default fill that needs the locate scan pass; other score sets take the exact fill."""
+    import numpy as np
+    rnd = random.Random(23)
+    base = "".join(rnd.choice("ACGT") for _ in range(3000))
+    refs = [base[:1200], base[1000:2500], "".join(rnd.choice("ACGT") for _ in range(700)), "AT" * 150, base[::-1][:900]]
+    reads = [base[100:250], base[1100:1181], base[2000:2140][::-1], "AT" * 40, base[500:533], base[1500:1800],
+             "".join(rnd.choice("ACGT") for _ in range(150))]
+    rs = engine.load_refset(refs)
+    for scores in ((5, -3, -4), (3, 1, -2), (2, -2, -2), (5, -9, -4)):
+        so = rs.align(reads, scores, scores_only=True)
+        full = rs.align(reads, scores)
+        exp = np.array([[oracle.align(r, q, *scores, max_cells=1).score for q in reads] for r in refs], dtype=np.int32)
+        assert (so.scores == exp).all(), scores
+        assert (full.scores == exp).all(), scores
+        assert (so.ref_totals == full.ref_totals).all()
+        assert (so.best_hits[:, :2] == full.best_hits[:, :2]).all()
+        so.free(); full.free()
+    rs.free()
