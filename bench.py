@@ -73,7 +73,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
         except OSError:
             self.proc = None
@@ -251,14 +251,16 @@ def main():
 
     # resident read batches (inputs in HBM before the timed region)
     resident = [rs.upload_reads(r) for r in step_reads]
+    # nvidia-smi takes ~0.1 s to start: launch the sampler before the warm-up so it is sampling (every 20 ms)
+    # throughout the timed region; warm-up samples are under the same load
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for k in range(W):
         res = step_resident(resident[k]); allgather_best(res); res.free()
     torch.cuda.synchronize()
     if dist:
         dist.barrier()
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     if dist:
