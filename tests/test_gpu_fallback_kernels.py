@@ -1,0 +1,41 @@
+"""GPU: the fallback kernels on the DEFAULT scores.  The engine picks its kernels from the score set (biased
+fill + subsampled tile maxima + byte-tile traceback for 5/-3/-4); environment switches force the other
+implementations -- unbiased fill (swb_fill.cu), exact tile maxima, group traceback (swb_trace.cu) -- so that every
+kernel is checked on the same workload.  The switches are read once per process: each case runs in a subprocess."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r"""
+import random, sys
+sys.path.insert(0, %r)
+import sparksmithwaterman_b200 as swb
+from tests.helpers import check_pairs
+rnd = random.Random(77)
+base = "".join(rnd.choice("ACGT") for _ in range(2600))
+refs = [base, base[300:1500], "".join(rnd.choice("ACGT") for _ in range(900)), "AT" * 220, base[::-1][:1300], "ACG" * 150]
+reads = [base[100:250], base[700:760] + "GG" + base[760:840], base[2000:2104][::-1], "AT" * 75, base[1200:1233],
+         "".join(rnd.choice("ACGT") for _ in range(150)), base[40:290], "ACG" * 40, base[5:12]]
+eng = swb.Engine(0)
+n = check_pairs(eng, refs, reads, (5, -3, -4), max_cells=400)
+n += check_pairs(eng, refs[:3], reads[:5], (5, -3, -4))
+eng.close()
+print("checked", n)
+""" % ROOT
+
+
+@pytest.mark.parametrize("switch", ["SWB_NO_BIAS_FILL", "SWB_NO_SUBSAMPLE", "SWB_NO_TILE_TRACE",
+                                    "SWB_NO_BIAS_FILL,SWB_NO_TILE_TRACE"])
+def test_forced_fallback_kernels_are_exact(switch):
+    env = dict(os.environ)
+    for s in switch.split(","):
+        env[s] = "1"
+    p = subprocess.run([sys.executable, "-c", SCRIPT], env=env, cwd=ROOT, capture_output=True, text=True, timeout=300)
+    assert p.returncode == 0, p.stdout[-2000:] + p.stderr[-4000:]
+    assert "checked" in p.stdout
