@@ -239,6 +239,9 @@ cudaError_t launch_fill(int K, const BatchParams &P, uint32_t *work_counter, int
 {
     switch (K) {
         case 4:  return launch_fill_k<4>(P, work_counter, sm_count, st);
+        case 5:  return launch_fill_k<5>(P, work_counter, sm_count, st);
+        case 7:  return launch_fill_k<7>(P, work_counter, sm_count, st);
+        case 10: return launch_fill_k<10>(P, work_counter, sm_count, st);
         case 8:  return launch_fill_k<8>(P, work_counter, sm_count, st);
         case 13: return launch_fill_k<13>(P, work_counter, sm_count, st);
         case 16: return launch_fill_k<16>(P, work_counter, sm_count, st);

@@ -29,8 +29,8 @@ constexpr int MAX_SHORT_ROWS = GL * 32;
 static_assert(CB == 16, "the fill kernels store one seam quad per 4 steps of a 16-step chunk");
 
 // rows-per-lane variants compiled for the short path
-constexpr int kNumK = 7;
-constexpr int kKList[kNumK] = {4, 8, 13, 16, 19, 25, 32};
+constexpr int kNumK = 10;
+constexpr int kKList[kNumK] = {4, 5, 7, 8, 10, 13, 16, 19, 25, 32};   // 8 K >= m: 36/50/75-80/100/125/150/200/250 bp reads fit with <= 7 % padding
 
 template <int K> struct Geo {
     static constexpr int KW = ((K + 1 + 3) / 4) * 4;            // checkpoint words per lane (K cells + diag)

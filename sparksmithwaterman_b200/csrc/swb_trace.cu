@@ -487,6 +487,9 @@ cudaError_t launch_trace(int K, const BatchParams &P, const uint64_t *keys, uint
 {
     switch (K) {
         case 4:  return launch_trace_k<4>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 5:  return launch_trace_k<5>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 7:  return launch_trace_k<7>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 10: return launch_trace_k<10>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 8:  return launch_trace_k<8>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 13: return launch_trace_k<13>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 16: return launch_trace_k<16>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);

@@ -556,6 +556,9 @@ cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, co
 {
     switch (K) {
         case 4:  return launch_tile_locate_k<4>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 5:  return launch_tile_locate_k<5>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 7:  return launch_tile_locate_k<7>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 10: return launch_tile_locate_k<10>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
         case 8:  return launch_tile_locate_k<8>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
         case 13: return launch_tile_locate_k<13>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
         case 16: return launch_tile_locate_k<16>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
@@ -571,6 +574,9 @@ cudaError_t launch_tile_trace(int K, const BatchParams &P, const uint64_t *keys,
 {
     switch (K) {
         case 4:  return launch_tile_trace_k<4>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 5:  return launch_tile_trace_k<5>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 7:  return launch_tile_trace_k<7>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 10: return launch_tile_trace_k<10>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 8:  return launch_tile_trace_k<8>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 13: return launch_tile_trace_k<13>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 16: return launch_tile_trace_k<16>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);

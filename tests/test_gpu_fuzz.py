@@ -30,7 +30,7 @@ def _workload(rnd):
     if rnd.random() < 0.3:
         ref_lens.append(rnd.randint(6000, 20000))
     refs = [_seq(rnd, n, alphabet) for n in ref_lens]
-    read_lens = [rnd.choice([0, 1, 3, 8, 31, 32, 33, 64, 100, 104, 105, 128, 150, 152, 153, 200, 255, 256])
+    read_lens = [rnd.choice([0, 1, 3, 8, 31, 32, 33, 36, 40, 41, 50, 56, 57, 64, 76, 80, 81, 100, 104, 105, 128, 150, 152, 153, 200, 255, 256])
                  for _ in range(rnd.randint(1, 8))]
     if rnd.random() < 0.25:
         read_lens.append(rnd.choice([257, 300, 513, 700]))
