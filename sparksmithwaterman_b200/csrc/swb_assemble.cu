@@ -55,19 +55,19 @@ __global__ void gather_cells_kernel(const BatchDesc *batches, int nb, uint32_t n
     words[k] = ((int64_t)len + 15) >> 4;
 }
 
-// one warp per cell: copy its packed columns into the dense buffer
+// eight lanes per cell (an alignment of ~170 columns is 11 words): copy its packed columns into the dense buffer
 __global__ void gather_ops_kernel(const BatchDesc *batches, int nb, uint32_t n_cells, const uint32_t *order,
                                   const int64_t *ops_off, uint32_t *ops_out)
 {
-    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
+    const uint32_t k = (blockIdx.x * blockDim.x + threadIdx.x) >> 3;
+    const int lane = threadIdx.x & 7;
     if (k >= n_cells) return;
     const uint32_t s = order[k];
     const BatchDesc &B = batches[find_batch(batches, nb, s)];
     const uint32_t *in = B.ops + (int64_t)(s - B.base) * B.ops_stride;
     uint32_t *out = ops_out + ops_off[k];
     const int64_t n = ops_off[k + 1] - ops_off[k];
-    for (int64_t w = lane; w < n; w += 32) out[w] = in[w];
+    for (int64_t w = lane; w < n; w += 8) out[w] = in[w];
 }
 
 // cell_off[p] = first sorted cell whose pair index >= p  (p = 0 .. n_pairs)
@@ -135,7 +135,7 @@ cudaError_t assemble_gather_ops(const BatchDesc *batches, int nb, uint32_t n_cel
 {
     if (n_cells == 0) return cudaSuccess;
     const int threads = 256;
-    const int64_t blocks = ((int64_t)n_cells * 32 + threads - 1) / threads;
+    const int64_t blocks = ((int64_t)n_cells * 8 + threads - 1) / threads;
     gather_ops_kernel<<<(unsigned)blocks, threads, 0, st>>>(batches, nb, n_cells, order, ops_off, ops_out);
     return cudaGetLastError();
 }
