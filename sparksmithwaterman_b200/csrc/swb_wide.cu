@@ -143,13 +143,13 @@ __device__ __forceinline__ void load_wide_state(const WCtx &C, int band, int blk
 // Fill.  PROF = true (alphabets of up to 8 symbols): the substitution score comes from a per-warp
 // shared-memory profile of the band ([code][KL/4][lane][4], conflict-free LDS.128) and the NW + s add is an
 // IMAD on the FMA pipe, leaving two DPX ops per cell on the integer pipe.  PROF = false: compare + select.
-template <bool PROF>
+template <bool PROF, int NC>
 __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, const int2 *items, int n_items,
                                                          uint32_t *ticket, int one)
 {
-    extern __shared__ __align__(16) int32_t wprof_all[];          // PROF: per warp [8 codes][KL/4][32 lanes][4]
+    extern __shared__ __align__(16) int32_t wprof_all[];          // PROF: per warp [NC codes][KL/4][32 lanes][4], NC = 4 or 8
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *wprof = wprof_all + warp * (8 * KL * WL);
+    int32_t *wprof = wprof_all + warp * (NC * KL * WL);
     for (;;) {
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(ticket, 1u);
@@ -159,10 +159,11 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
         const WCtx C = make_ctx(P, pair);
         int rc[KL]; bool all_valid;
         load_rows(C, band, lane, rc, all_valid);
+        const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
         if (PROF) {
             __syncwarp();
 #pragma unroll
-            for (int c = 0; c < 8; ++c)
+            for (int c = 0; c < NC; ++c)
 #pragma unroll
                 for (int r = 0; r < KL; ++r)
                     wprof[((c * (KL / 4) + (r >> 2)) * WL + lane) * 4 + (r & 3)] = (rc[r] == c) ? C.match : C.mismatch;
@@ -194,6 +195,37 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                 }
             }
             const int tbuf = top_prefetch(C, band, s0, lane);
+            if (PROF && warp_all_valid && s0 >= WL - 1 && s0 + 32 <= C.n) {
+                // interior chunk: every lane's 32 columns are inside the matrix and every row is a read row -> no
+                // per-step branches, so the unrolled steps overlap (profile loads of step u+1 under the chain of step u)
+#pragma unroll 8
+                for (int u = 0; u < 32; ++u) {
+                    int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
+                    const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
+                    if (lane == 0) top = t0;
+                    const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
+                    int sv[KL];
+                    const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & (NC - 1)) * (KL / 4) * WL + lane;
+#pragma unroll
+                    for (int q = 0; q < KL / 4; ++q) {
+                        const int4 v = pp[q * WL];
+                        sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
+                    }
+                    int nw = diag, nn = top;
+#pragma unroll
+                    for (int r = 0; r < KL; ++r) {
+                        const int tt = nw * one + sv[r];
+                        const int pre = __viaddmax_s32_relu(H[r], C.gap, tt);
+                        nw = H[r];
+                        H[r] = __viaddmax_s32(nn, C.gap, pre);
+                        nn = H[r];
+                    }
+                    if (lane == WL - 1) my_brow[s0 + u - lane + 1] = H[KL - 1];
+#pragma unroll
+                    for (int r = 0; r < KL; r += 2) tmax = __vimax3_s32(tmax, H[r], H[r + 1]);
+                    diag = top;
+                }
+            } else {
 #pragma unroll 4
             for (int u = 0; u < 32; ++u) {
                 const int s = s0 + u;
@@ -205,7 +237,7 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                 if ((j >= 1) && (j <= C.n)) {
                     int sv[KL];
                     if (PROF) {
-                        const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & 7) * (KL / 4) * WL + lane;
+                        const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & (NC - 1)) * (KL / 4) * WL + lane;
 #pragma unroll
                         for (int q = 0; q < KL / 4; ++q) {
                             const int4 v = pp[q * WL];
@@ -234,6 +266,7 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
                     }
                 }
                 diag = top;
+            }
             }
             cprev = ccur;
             // publish: lane 31 (the only writer of the bottom row) has finished every column <= s0 + 1
@@ -349,10 +382,16 @@ __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, cons
     auto store_col = [&](int c, int top, const int (&Hc)[KL]) {
         int32_t *col = wtile + c * CW + lane * LW;
         if (BYTE) {
-            static_assert(KL == 8, "byte tile packing assumes 8 rows per lane");
-            col[0] = (int32_t)__byte_perm(__byte_perm((uint32_t)top, (uint32_t)Hc[0], 0x0040), __byte_perm((uint32_t)Hc[1], (uint32_t)Hc[2], 0x0040), 0x5410);
-            col[1] = (int32_t)__byte_perm(__byte_perm((uint32_t)Hc[3], (uint32_t)Hc[4], 0x0040), __byte_perm((uint32_t)Hc[5], (uint32_t)Hc[6], 0x0040), 0x5410);
-            col[2] = Hc[7] & 0xff;
+#pragma unroll
+            for (int w = 0; w < LW; ++w) {
+                uint32_t v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * w + e;                       // byte k: 0 = boundary row, 1..KL = the lane's rows
+                    v[e] = k == 0 ? (uint32_t)top : (k <= KL ? (uint32_t)Hc[k - 1 < KL && k >= 1 ? k - 1 : 0] : 0u);
+                }
+                col[w] = (int32_t)__byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+            }
         } else {
             col[0] = top;
 #pragma unroll
@@ -438,18 +477,25 @@ cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
     static const int env_ctas = getenv("SWB_WIDE_CTAS_PER_SM") ? atoi(getenv("SWB_WIDE_CTAS_PER_SM")) : 0;
-    const int per_sm = env_ctas > 0 ? env_ctas : 4;
-    const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
     if (P.n_symbols <= 8) {
-        const size_t smem = (size_t)4 * 8 * KL * WL * sizeof(int32_t);      // 4 warps x 8 codes x BH rows
+        // profile of 4 or 8 codes; with 4 (DNA) seven 4-warp CTAs fit per SM: cfg3's 3,910 band items then run in ONE
+        // wave (4,144 warp slots) instead of 1.65 waves on 2,368 slots, whose second wave is 35 % idle
+        const int nc = P.n_symbols <= 4 ? 4 : 8;
+        const size_t smem = (size_t)4 * nc * KL * WL * sizeof(int32_t);      // 4 warps x codes x BH rows
+        const int per_sm = env_ctas > 0 ? env_ctas : (nc == 4 ? 7 : 4);
+        const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
         static PerDeviceOnce attr;
         if (attr.need()) {
-            e = cudaFuncSetAttribute(wide_fill_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            e = cudaFuncSetAttribute(wide_fill_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)((size_t)4 * 8 * KL * WL * sizeof(int32_t)));
             if (e != cudaSuccess) return e;
         }
-        wide_fill_kernel<true><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
+        if (nc == 4) wide_fill_kernel<true, 4><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
+        else         wide_fill_kernel<true, 8><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
     } else {
-        wide_fill_kernel<false><<<ctas, 128, 0, st>>>(P, items, n_items, ticket, 1);
+        const int per_sm = env_ctas > 0 ? env_ctas : 4;
+        const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
+        wide_fill_kernel<false, 8><<<ctas, 128, 0, st>>>(P, items, n_items, ticket, 1);
     }
     return cudaGetLastError();
 }
@@ -484,7 +530,7 @@ cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_
                                              (int)((size_t)(WCB + 1) * WL * (KL + 1) * sizeof(int32_t)));
         if (e != cudaSuccess) return e;
     }
-    const int per_sm = bytes ? 8 : 3;                                    // CTAs (warps) per SM that fit in shared memory
+    const int per_sm = std::max(1, std::min(16, (int)((220 * 1024) / (smem + 1024))));   // CTAs (warps) per SM that fit in shared memory
     const int64_t ctas = std::min<int64_t>(n_cells, (int64_t)sm_count * per_sm);
     if (bytes) wide_trace_kernel<true><<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
     else       wide_trace_kernel<false><<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
