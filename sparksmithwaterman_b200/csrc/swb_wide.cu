@@ -145,7 +145,7 @@ __device__ __forceinline__ void load_wide_state(const WCtx &C, int band, int blk
 // IMAD on the FMA pipe, leaving two DPX ops per cell on the integer pipe.  PROF = false: compare + select.
 template <bool PROF, int NC>
 __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, const int2 *items, int n_items,
-                                                         uint32_t *ticket, int one)
+                                                         uint32_t *ticket, int one, int lag_chunks)
 {
     extern __shared__ __align__(16) int32_t wprof_all[];          // PROF: per warp [NC codes][KL/4][32 lanes][4], NC = 4 or 8
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
         for (int s0 = 0; s0 < nsteps; s0 += 32) {
             const int ccur = code_prefetch(C, s0, lane);
             if (band > 0) {
-                const int need = min(C.n, s0 + 32);
+                const int need = min(C.n, s0 == 0 ? 32 * lag_chunks : s0 + 32);   // start with `lag_chunks` of slack: a late chunk above no longer stalls the whole cascade below
                 if (seen < need) {
                     // lane 0 acquires; the other lanes' boundary loads (ld.cg, L2) are issued after the loop's
                     // branch has resolved on the acquired value, i.e. after the publisher's release
@@ -476,6 +476,7 @@ cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items
     if (n_items == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
+    static const int lag = getenv("SWB_WIDE_LAG") ? std::max(1, atoi(getenv("SWB_WIDE_LAG"))) : 1;
     static const int env_ctas = getenv("SWB_WIDE_CTAS_PER_SM") ? atoi(getenv("SWB_WIDE_CTAS_PER_SM")) : 0;
     if (P.n_symbols <= 8) {
         // profile of 4 or 8 codes; with 4 (DNA) seven 4-warp CTAs fit per SM: cfg3's 3,910 band items then run in ONE
@@ -490,12 +491,12 @@ cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items
                                      (int)((size_t)4 * 8 * KL * WL * sizeof(int32_t)));
             if (e != cudaSuccess) return e;
         }
-        if (nc == 4) wide_fill_kernel<true, 4><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
-        else         wide_fill_kernel<true, 8><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
+        if (nc == 4) wide_fill_kernel<true, 4><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1, lag);
+        else         wide_fill_kernel<true, 8><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1, lag);
     } else {
         const int per_sm = env_ctas > 0 ? env_ctas : 4;
         const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
-        wide_fill_kernel<false, 8><<<ctas, 128, 0, st>>>(P, items, n_items, ticket, 1);
+        wide_fill_kernel<false, 8><<<ctas, 128, 0, st>>>(P, items, n_items, ticket, 1, lag);
     }
     return cudaGetLastError();
 }
