@@ -91,6 +91,29 @@ template <class Sink>
 __device__ __forceinline__ void wide_chunk(const WCtx &C, int s0, int lane, int tbuf, int cprev, int ccur,
                                            const int (&rc)[KL], int (&H)[KL], int &diag, Sink &&sink)
 {
+    if (s0 >= WL - 1 && s0 + 32 <= C.n) {
+        // interior chunk: every lane's 32 columns are inside the matrix -> no per-step branch, steps overlap.
+        // (Rows beyond the read's end compute garbage below the real rows, as in the general loop.)
+#pragma unroll 4
+        for (int u = 0; u < 32; ++u) {
+            int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
+            const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
+            if (lane == 0) top = t0;
+            const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
+            int nw = diag, nn = top;
+#pragma unroll
+            for (int r = 0; r < KL; ++r) {
+                const int sc = (rc[r] == c) ? C.match : C.mismatch;
+                const int pre = __viaddmax_s32_relu(H[r], C.gap, nw + sc);
+                nw = H[r];
+                H[r] = __viaddmax_s32(nn, C.gap, pre);
+                nn = H[r];
+            }
+            sink(u, top, H, true, s0 + u - lane + 1);
+            diag = top;
+        }
+        return;
+    }
 #pragma unroll 1
     for (int u = 0; u < 32; ++u) {
         const int s = s0 + u;
