@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define SWB_ABI_VERSION 1
+#define SWB_ABI_VERSION 2
 
 /* status codes */
 #define SWB_OK              0
@@ -105,7 +105,10 @@ const int32_t *swb_result_scores(const swb_result *res);
 /* ref_totals[r]: wrapping int32 sum over reads (Distribution.java:424) */
 const int32_t *swb_result_ref_totals(const swb_result *res);
 /* best_hits[4*q .. 4*q+3] = (score, ref index, i, j) of read q's best reference: highest
- * score, lowest ref index on ties, first max cell in row-major order ((0,0) if score 0). */
+ * score, lowest ref index on ties, first max cell in row-major order ((0,0) if score 0).
+ * The reference has no per-read best hit (it reduces per REFERENCE, Distribution.java:424); this
+ * record and its tie rule are this engine's definition (BASELINE north_star: "per-read (score,
+ * ref id, cell) best-hit records"). */
 const int32_t *swb_result_best_hits(const swb_result *res);
 
 /* cell_offsets[p] .. cell_offsets[p+1] index the materialised max cells of pair p.
@@ -147,6 +150,64 @@ int swb_result_device_ptr(const swb_result *res, int which, void **ptr, int64_t 
 /* The CUDA stream (cudaStream_t) every kernel and copy of this context is issued on, so a
  * host can bracket calls with its own events on that stream. */
 int swb_get_stream(swb_ctx *ctx, void **stream);
+
+/* ---- multi-GPU: the reference set sharded over devices, best hits merged over NVLink ----------------
+ * Replaces: the partition point of the reference's driver, `sc.parallelize(refs)` + map(MapRef)
+ * (Distribution.java:337-338): the pair set refs x reads is cut by REFERENCE, every device aligns
+ * all reads against its own shard (scores, max-cell lists, alignments and per-reference totals stay
+ * with the owning device), and only the per-read best-hit records (score, GLOBAL ref index, i, j)
+ * cross NVLink -- one ncclAllGather issued on each device's engine stream right after the best-hit
+ * kernel, followed by a merge kernel on the device.  The reference has no per-read best hit; the
+ * merge rule is this engine's own: highest score, then lowest global reference index (the running
+ * maximum with first-wins order of a single device scanning the references in index order).
+ * NCCL is loaded at run time (dlopen of libnccl.so.2, or $SWB_NCCL_LIB); a single device needs none.
+ *
+ * Two forms.  swb_multi_*: ONE process drives all devices (a JVM / Spark local[N] host) -- one host
+ * thread per device inside the call.  swb_comm_*: one process per device (torchrun, MPI); the host
+ * only carries the 128-byte NCCL id from rank 0 to the other ranks. */
+typedef struct swb_multi        swb_multi;         /* n devices: contexts, sharded reference set, NCCL communicators */
+typedef struct swb_multi_result swb_multi_result;
+typedef struct swb_comm         swb_comm;          /* one rank of a multi-process job */
+
+/* devices[n_devices] = CUDA device indices (n_devices >= 1); workspace as in swb_create, per device. */
+int  swb_multi_create(const int32_t *devices, int32_t n_devices, int64_t workspace_bytes, swb_multi **out);
+void swb_multi_destroy(swb_multi *m);
+int32_t swb_multi_device_count(const swb_multi *m);
+/* Context of shard d (borrowed; e.g. for swb_get_stream). */
+swb_ctx *swb_multi_ctx(swb_multi *m, int32_t d);
+
+/* Shard + load: references sorted by descending length (stable) and dealt in snake order
+ * (0..n-1, n-1..0, ...) so that every device holds the same number of bases to within one reference;
+ * shard d keeps its references in ascending global index.  Replaces an earlier set of this handle. */
+int  swb_multi_refset_load(swb_multi *m, int64_t n_refs, const char *bytes, const int64_t *offsets);
+int64_t swb_multi_ref_count(const swb_multi *m);
+/* global reference index -> (shard, index inside the shard) */
+int  swb_multi_ref_location(const swb_multi *m, int64_t global_ref, int32_t *shard, int64_t *local_ref);
+/* global indices of shard d's references, ascending; *n = their number */
+const int64_t *swb_multi_shard_refs(const swb_multi *m, int32_t d, int64_t *n);
+
+/* All reads against all shards (swb_align on every device, concurrently) + the best-hit merge. */
+int  swb_multi_align(swb_multi *m, int64_t n_reads, const char *read_bytes, const int64_t *read_offsets,
+                     int32_t match, int32_t mismatch, int32_t gap, uint32_t flags, swb_multi_result **out);
+void swb_multi_result_free(swb_multi_result *res);
+/* shard d's own result (borrowed; pair p = local_ref * n_reads + read): every swb_result_* accessor applies */
+swb_result *swb_multi_result_shard(swb_multi_result *res, int32_t d);
+/* merged[4*q .. 4*q+3] = (score, GLOBAL ref index, i, j) of read q over all shards */
+const int32_t *swb_multi_result_best_hits(const swb_multi_result *res);
+/* out[0] = wall ms of the call, out[1] = max over devices of the align's device ms, out[2] = allgather + merge ms */
+int  swb_multi_result_stats(const swb_multi_result *res, double *out, int n);
+
+/* multi-process form: rank 0 calls swb_comm_unique_id and ships the 128 bytes to every rank. */
+int  swb_comm_unique_id(char *id128);
+int  swb_comm_create(swb_ctx *ctx, const char *id128, int32_t rank, int32_t world, swb_comm **out);
+void swb_comm_destroy(swb_comm *c);
+/* Best hits of `res` (a result of this rank's shard, fetched or not) -> global ids through
+ * global_ids[n_local_refs] (host array) -> ncclAllGather on the context's stream -> merge kernel.
+ * merged_host (nullable) receives [n_reads * 4]; the merged records also stay on the device
+ * (swb_comm_merged_device_ptr) until the next call. */
+int  swb_comm_allgather_best(swb_comm *c, const swb_result *res, const int64_t *global_ids, int64_t n_local_refs,
+                             int32_t *merged_host);
+int  swb_comm_merged_device_ptr(swb_comm *c, void **ptr, int64_t *n_elems);
 
 /* Integer / DPX issue-rate microbenchmark (roofline denominator). */
 int swb_microbench_json(int device, int iters, char *buf, int buflen);

@@ -76,7 +76,7 @@ void swb_destroy(swb_ctx *c)
     for (int k = 0; k < 2; ++k) { c->ck2[k].release(); c->tmx2[k].release(); c->rp2[k].release(); }
     cudaStreamSynchronize(c->stream_fill);
     c->v_ref.release(); c->v_c0.release(); c->v_len.release(); c->v_skip.release(); c->v_end.release();
-    c->w_brow.release(); c->w_ck.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
+    c->w_brow.release(); c->w_rec.release(); c->w_wreads.release(); c->w_rpad.release(); c->w_rpad_off.release(); c->w_rpad_len.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
     c->w_pair_read.release(); c->w_band_off.release(); c->w_blk_off.release(); c->w_brow_off.release();
     c->w_items.release(); c->w_tasks.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);
@@ -337,7 +337,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                                  std::abs((int64_t)mismatch) <= 8000 && std::abs((int64_t)gap) <= 8000;
     auto read_is_short = [&](int32_t m) {
         return short_scores_ok && m <= MAX_SHORT_ROWS &&
-               (int64_t)std::max(match, 0) * std::min<int64_t>(m, rs->max_len) <= 16000;
+               (int64_t)std::max({match, mismatch, 0}) * std::min<int64_t>(m, rs->max_len) <= 16000;   // a positive mismatch scores too
     };
 
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
@@ -475,7 +475,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 P.match = match; P.mismatch = mismatch; P.gap = gap; P.tie_gt = (flags & SWB_F_TIE_GT) ? 1 : 0;
                 P.scores = res->d_scores.p; P.rec = ck.p; P.tmx = tmx.p;
                 uint32_t *d_work = ctx->counters.p + 4 + S.buf;
-                const bool biased = fill_bias_ok(match, mismatch, gap, (int64_t)std::max(match, 0) * std::min<int64_t>(S.m_max, rs->max_len));
+                const bool biased = fill_bias_ok(match, mismatch, gap, (int64_t)std::max({match, mismatch, 0}) * std::min<int64_t>(S.m_max, rs->max_len));
                 P.seam_bias = biased ? -gap : 0;               // the biased fill stores its seams biased
                 P.tmx_slack = biased ? fill_sub_slack(match, mismatch, gap) : 0;
                 const int sp_fill = tic(1, sF);

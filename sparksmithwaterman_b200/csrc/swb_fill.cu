@@ -220,10 +220,8 @@ static cudaError_t launch_fill_k(const BatchParams &P, uint32_t *work_counter, i
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of
         // shared memory each) must be able to co-reside with this kernel's CTA on the same SM
         static PerDeviceOnce carve;
-        if (carve.need()) {
-            e = cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-        }
+        e = carve.run([] { return cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); });
+        if (e != cudaSuccess) return e;
     }
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(fill_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -253,10 +253,8 @@ static cudaError_t launch_fill_bias_k2(const BatchParams &P, uint32_t *work_coun
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of
         // shared memory each) must be able to co-reside with this kernel's CTA on the same SM
         static PerDeviceOnce carve;
-        if (carve.need()) {
-            e = cudaFuncSetAttribute(fill_bias_kernel<K, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (e != cudaSuccess) return e;
-        }
+        e = carve.run([] { return cudaFuncSetAttribute(fill_bias_kernel<K, SUB>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared); });
+        if (e != cudaSuccess) return e;
     }
     if (smem > 48 * 1024) {
         e = cudaFuncSetAttribute(fill_bias_kernel<K, SUB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -310,7 +308,7 @@ bool fill_bias_ok(int match, int mismatch, int gap, int64_t max_score)
     if (gap >= 0) return false;
     const int ag = -gap;
     static const bool disabled = getenv("SWB_NO_BIAS_FILL") != nullptr;
-    return !disabled && match + ag >= 0 && mismatch + ag >= 0 && match + ag <= 4000 &&
+    return !disabled && match + ag >= 0 && mismatch + ag >= 0 && match + ag <= 4000 && mismatch + ag <= 4000 &&
            max_score + 32LL * ag <= 30000;
 }
 

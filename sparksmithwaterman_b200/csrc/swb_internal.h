@@ -16,6 +16,7 @@
 
 #include <cstdint>
 #include <cuda_runtime.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -57,14 +58,19 @@ __host__ __device__ inline uint32_t key_j(uint64_t k) { return (uint32_t)k & ((1
 // cudaFuncSetAttribute is per device (context): a process may hold one swb_ctx per GPU (Spark local[N] over 8 GPUs
 // in one JVM), so "already set" is tracked per device.  need() is true the first time it is called on the current device.
 struct PerDeviceOnce {
+    std::mutex mu;
     bool done[64] = {};
-    bool need()
+    // runs f() once per device, under a lock, and only records success: two contexts on one device (Spark local[N]
+    // threads of one JVM) can no longer skip an attribute that has not been set yet
+    template <class F> cudaError_t run(F &&f)
     {
         int d = 0;
-        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return true;
-        if (done[d]) return false;
-        done[d] = true;
-        return true;
+        if (cudaGetDevice(&d) != cudaSuccess || d < 0 || d >= 64) return f();
+        std::lock_guard<std::mutex> lk(mu);
+        if (done[d]) return cudaSuccess;
+        const cudaError_t e = f();
+        if (e == cudaSuccess) done[d] = true;
+        return e;
     }
 };
 
@@ -108,9 +114,15 @@ struct BatchParams {
 // ---- general ("wide") int32 path: bands of 32 lanes x KL rows, see swb_wide.cu ------------------
 namespace wide {
 constexpr int WL = 32;       // lanes per band (one warp)
-constexpr int KL = 8;        // rows per lane
-constexpr int BH = WL * KL;  // rows per band
-constexpr int WCB = 64;      // steps per checkpoint block
+constexpr int WCB = 32;      // steps per checkpoint block
+constexpr int kNumKL = 3;
+constexpr int kKLList[kNumKL] = {8, 16, 32};                  // rows per lane (band height 256 / 512 / 1024)
+template <int KL> struct WGeo {
+    static constexpr int BH = WL * KL;                        // rows per band
+    static constexpr int KW = ((KL + 1 + 3) / 4) * 4;         // checkpoint words per lane (KL cells + diag)
+    static constexpr int RW = KW + WCB;                       // record words per (band, block, lane): checkpoint + seam
+};
+constexpr int wide_rw(int kl) { return ((kl + 1 + 3) / 4) * 4 + WCB; }
 // key: local pair (21 bits) | i (21 bits) | j (22 bits)
 __host__ __device__ inline uint64_t wide_key(uint64_t pair, uint32_t i, uint32_t j) { return (pair << 43) | ((uint64_t)i << 22) | j; }
 __host__ __device__ inline uint64_t wide_key_pair(uint64_t k) { return k >> 43; }
@@ -118,7 +130,7 @@ __host__ __device__ inline uint32_t wide_key_i(uint64_t k) { return (uint32_t)(k
 __host__ __device__ inline uint32_t wide_key_j(uint64_t k) { return (uint32_t)k & ((1u << 22) - 1); }
 }  // namespace wide
 
-struct WideTask { int32_t pair, band, block; uint32_t lane_mask; };
+struct WideTask { int32_t pair, band, block; uint32_t lane; };   // one flagged tile
 
 struct WideParams {
     int32_t n_pairs;
@@ -126,16 +138,20 @@ struct WideParams {
     const int32_t *pair_read;    // [n_pairs] read index
     const uint8_t *ref_codes;    // 1 byte per base, original reference order
     const int64_t *ref_off;      // [n_refs + 1]
-    const uint8_t *read_codes;
-    const int64_t *read_off;
+    const uint8_t *rpad;         // read codes, each wide read 16-byte aligned and padded with 0xFE to a multiple of 1024 rows
+    const int64_t *rpad_off;     // [n_reads] offset of the read in rpad (reads of this call that take the wide path)
+    const int64_t *read_off;     // [n_reads + 1] offsets in the unpadded read codes (lengths)
     int32_t match, mismatch, gap;
     int32_t tie_gt;
     int32_t n_symbols;           // alphabet size of the reference set (codes 0 .. n_symbols-1)
     int64_t n_reads;
     const int64_t *band_off;     // [n_pairs + 1] prefix of bands
     const int64_t *blk_off;      // [n_pairs + 1] prefix of bands * blocks
-    const int64_t *brow_off;     // [n_pairs + 1] prefix of bands * (n + 1)
-    int32_t *brow, *ck, *tmx, *prog;
+    const int64_t *brow_off;     // [n_pairs + 1] prefix of bands * blocks * 32 (steps)
+    int32_t *brow;               // per band: lane 31's bottom row, indexed by step
+    int32_t *rec;                // block records [bands * blocks][32 lanes][RW]
+    int32_t *tmx;                // tile maxima   [bands * blocks][32 lanes]
+    int32_t *prog;               // per band: steps completed (release / acquire)
     int32_t *scores;
 };
 
@@ -161,13 +177,16 @@ cudaError_t assemble_gather_ops(const BatchDesc *batches, int nb, uint32_t n_cel
 cudaError_t assemble_offsets(const uint64_t *pair_sorted, uint32_t n_cells, int64_t n_pairs, int64_t *cell_off,
                              int32_t *best, int64_t n_reads, const int32_t *cells, cudaStream_t st);
 
-cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count,
+cudaError_t launch_wide_pad_reads(const uint8_t *codes, const int64_t *read_off, const int32_t *reads, int n_reads,
+                                  const int64_t *rpad_off, const int64_t *rpad_len, uint8_t *rpad, int64_t max_len,
+                                  cudaStream_t st);
+cudaError_t launch_wide_fill(int KL, const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count,
                              cudaStream_t st);
 cudaError_t launch_wide_flag(const WideParams &P, int64_t total_blocks, WideTask *tasks, uint32_t cap, uint32_t *count,
-                             cudaStream_t st);
-cudaError_t launch_wide_locate(const WideParams &P, const WideTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
+                             int sm_count, cudaStream_t st);
+cudaError_t launch_wide_locate(int KL, const WideParams &P, const WideTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
                                uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st);
-cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+cudaError_t launch_wide_trace(int KL, const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
                               int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st);
 
 // swb_fill.cu

@@ -471,8 +471,8 @@ static cudaError_t launch_trace_k(const BatchParams &P, const uint64_t *keys, ui
     while (warps > 1 && prof_bytes + per_group * 4 * warps + tail_bytes > 112 * 1024) --warps;   // two CTAs per SM
     const size_t smem = prof_bytes + per_group * 4 * warps + tail_bytes;
     static PerDeviceOnce attr;                    // one per template instantiation (K)
-    if (attr.need()) {
-        cudaError_t e = cudaFuncSetAttribute(trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const cudaError_t e = attr.run([&] { return cudaFuncSetAttribute(trace_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); });
         if (e != cudaSuccess) return e;
     }
     // chunks of the sorted cell list: several per SM for balance, each long enough to amortise its profile

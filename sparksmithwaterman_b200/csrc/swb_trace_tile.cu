@@ -520,9 +520,12 @@ cudaError_t launch_tile_trace_k(const BatchParams &P, const uint64_t *keys, uint
     if (n_cells == 0) return cudaSuccess;
     const size_t smem = ((size_t)TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT) * sizeof(uint32_t) + (((size_t)GL * K + 15) / 16) * 16;
     static PerDeviceOnce attr;
-    if (attr.need()) {
-        cudaError_t e = cudaFuncSetAttribute(tile_trace_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e == cudaSuccess) e = cudaFuncSetAttribute(tile_trace_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        const cudaError_t e = attr.run([&] {
+            cudaError_t e1 = cudaFuncSetAttribute(tile_trace_kernel<K, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e1 == cudaSuccess) e1 = cudaFuncSetAttribute(tile_trace_kernel<K, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            return e1;
+        });
         if (e != cudaSuccess) return e;
     }
     // chunks of the sorted cell list: many per SM for balance, each long enough to amortise its profile

@@ -1,20 +1,31 @@
 // swb_wide.cu -- the general ("wide") path: int32 scores, any read length, any scores that do
 // not overflow int32, 8-bit symbol codes (any alphabet).  Used for long pairs (BASELINE config 3:
-// 100 kbp x 100 kbp) and for every input outside the s16x2 short-read domain.
+// 100 kbp x 100 kbp), for reads longer than the s16x2 short path's 256 rows (the reference's own
+// read-length sweep goes to 500 bp, EngineerData.java:87-104) and for every score set outside
+// the s16x2 domain.
 //
-// Intra-pair parallelism: the matrix is cut in BANDS of BH = 32 lanes x KL rows.  One warp
-// sweeps a band along the reference as a 32-lane anti-diagonal wavefront (lane t computes
-// column s - t + 1 at step s; the boundary row moves down the lanes with __shfl_up_sync),
-// consecutive bands of a pair run concurrently on different warps, coupled through the
-// band's bottom row in HBM (brow) and a per-band progress counter: band b may compute a
-// 32-column chunk once band b-1 has published those columns.  Work is handed out by a global
-// ticket in (band, pair) order, so a warp only ever waits for a lower ticket, which is held by
-// a running warp: no deadlock, no cooperative launch.
-//
-// As in the short path the fill is score-only (SmithWaterman.java:157-187, :217-252) and leaves
-// register checkpoints every WCB steps + per-lane tile maxima; locate/trace recompute single
-// (band, block) tiles -- exact, because a tile's left edge is a checkpoint and its top edge is
-// the previous band's bottom row.  Traceback = GetAlignment.call (SmithWaterman.java:354-436).
+// Same design as the short path, in int32:
+//   * the matrix is cut in BANDS of 32 lanes x KL rows (KL = 8, 16 or 32, chosen per read); one
+//     warp sweeps a band along the reference as a 32-lane skewed wavefront (lane t computes column
+//     s - t + 1 at step s; the boundary row moves down the lanes with one __shfl_up_sync per step);
+//   * the cell costs one IMAD (NW + s, FMA pipe; s from a per-warp shared-memory profile) and two
+//     DPX ops (VIADDMNMX.RELU, VIADDMNMX) on the integer pipe -- SmithWaterman.java:217-252, :277-280,
+//     :309-318;
+//   * consecutive bands of a pair run concurrently on different warps, coupled through the band's
+//     bottom row in HBM (brow) and a per-band progress counter (release / acquire).  Work is handed
+//     out by a global ticket in (band, pair) order, so a warp only ever waits for a lower ticket,
+//     which is held by a running warp: no deadlock, no cooperative launch;
+//   * the fill is score-only and leaves, per (band, block of 32 steps, lane), one contiguous RECORD:
+//     the lane's CHECKPOINT (KL cells + the diagonal boundary at the block start) and its SEAM (the
+//     boundary row it receives at each of the 32 steps), plus the lane's tile maximum.  A record is
+//     all one THREAD needs to recompute the TILE (band, block, lane) = KL rows x 32 skewed columns;
+//   * locate: one thread per tile whose maximum equals the pair's score (ScoreMatrix.call's max-cell
+//     list, SmithWaterman.java:176-185; the radix sort of the keys gives its row-major order);
+//   * traceback (GetAlignment.call, SmithWaterman.java:354-436): tiles are recomputed into byte tiles
+//     in shared memory, one per thread.  G = 1: one thread per max cell (many cells, short walks).
+//     G = 32: one warp per max cell (few cells, long walks -- cfg3's 100k-column paths): the lanes
+//     recompute a CORRIDOR of 32 tiles along the predicted diagonal ahead of the walker, lane 0 walks
+//     through them until the path leaves the corridor; wrong predictions only cost another round.
 #include "swb_internal.h"
 
 #include <algorithm>
@@ -26,8 +37,8 @@ using namespace wide;
 
 namespace {
 
-__device__ __forceinline__ int ld_cg(const int32_t *p) { return __ldcg(p); }
-// progress counters: release store by the lane that wrote the band's bottom row, acquire load by the polling lane
+constexpr int PAD_NEG = -(1 << 29);          // profile score of a row beyond the read's end (gap < 0: stays below every real cell)
+
 __device__ __forceinline__ void st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ int ld_acquire(const int32_t *p)
 {
@@ -37,285 +48,243 @@ __device__ __forceinline__ int ld_acquire(const int32_t *p)
 }
 
 struct WCtx {
-    const uint8_t *ref;     // codes of this pair's reference
-    const uint8_t *read;    // codes of this pair's read
+    const uint8_t *ref;     // codes of this pair's reference (n bytes)
+    const uint8_t *read;    // codes of this pair's read in the padded buffer (16-byte aligned, 0xFE beyond m)
     int n, m;
     int match, mismatch, gap;
-    int n_blocks;           // blocks per band = ceil((n + 31) / WCB)
-    int32_t *brow;          // [bands][n + 1] bottom rows of this pair
-    int32_t *ck;            // [bands][n_blocks][KL + 1][32]
+    int n_blocks;           // blocks per band = ceil((n + 31) / 32)
+    int32_t *brow;          // [bands][n_blocks * 32] bottom row of lane 31, indexed by STEP
+    int32_t *rec;           // [bands][n_blocks][32 lanes][RW]
     int32_t *tmx;           // [bands][n_blocks][32]
 };
 
+template <int KL>
 __device__ __forceinline__ WCtx make_ctx(const WideParams &P, int pair)
 {
     WCtx C;
     const int ro = P.pair_ref[pair], rd = P.pair_read[pair];
     C.ref = P.ref_codes + P.ref_off[ro];
     C.n = (int)(P.ref_off[ro + 1] - P.ref_off[ro]);
-    C.read = P.read_codes + P.read_off[rd];
+    C.read = P.rpad + P.rpad_off[rd];
     C.m = (int)(P.read_off[rd + 1] - P.read_off[rd]);
     C.match = P.match; C.mismatch = P.mismatch; C.gap = P.gap;
     C.n_blocks = (C.n + WL - 1 + WCB - 1) / WCB;
-    if (C.n_blocks < 1) C.n_blocks = 1;
     C.brow = P.brow + P.brow_off[pair];
-    C.ck = P.ck + P.blk_off[pair] * (int64_t)((KL + 1) * WL);
+    C.rec = P.rec + P.blk_off[pair] * (int64_t)(WL * WGeo<KL>::RW);
     C.tmx = P.tmx + P.blk_off[pair] * (int64_t)WL;
     return C;
 }
 
-// read codes of this lane's rows in `band` (0x100 + r: matches nothing) and row validity
-__device__ __forceinline__ void load_rows(const WCtx &C, int band, int lane, int (&rc)[KL], bool &all_valid)
+// the KL read codes of lane-row T (rows T*KL .. T*KL+KL-1) from the padded read buffer
+template <int KL>
+__device__ __forceinline__ void load_row_codes(const uint8_t *read, int T, int (&rc)[KL])
 {
-    all_valid = true;
+    const uint2 *p = reinterpret_cast<const uint2 *>(read + (int64_t)T * KL);      // KL is a multiple of 8, the buffer 16-aligned
 #pragma unroll
-    for (int r = 0; r < KL; ++r) {
-        const int row = band * BH + lane * KL + r;          // 0-based
-        if (row < C.m) rc[r] = C.read[row];
-        else { rc[r] = 0x100 + r; all_valid = false; }
-    }
-}
-
-// One 32-step chunk of a band.  `tbuf` holds, in lane L, the top-boundary value of column
-// s0 + 1 + L (bottom row of the band above; 0 for band 0).  sink(u, top, H, valid, j).
-// Reference codes reach the lanes through registers, not per-step loads: lane L holds the code of
-// column s0 - 31 + L (cprev) and of column s0 + 1 + L (ccur); at step u lane t needs column
-// s0 + u - t + 1, i.e. ccur[u - t] if u >= t, else cprev[32 + u - t] -- one SEL + one SHFL.
-__device__ __forceinline__ int code_prefetch(const WCtx &C, int s0, int lane)
-{
-    const int j = s0 + 1 + lane;
-    return (j >= 1 && j <= C.n) ? (int)C.ref[j - 1] : 0x200;
-}
-
-template <class Sink>
-__device__ __forceinline__ void wide_chunk(const WCtx &C, int s0, int lane, int tbuf, int cprev, int ccur,
-                                           const int (&rc)[KL], int (&H)[KL], int &diag, Sink &&sink)
-{
-    if (s0 >= WL - 1 && s0 + 32 <= C.n) {
-        // interior chunk: every lane's 32 columns are inside the matrix -> no per-step branch, steps overlap.
-        // (Rows beyond the read's end compute garbage below the real rows, as in the general loop.)
-#pragma unroll 4
-        for (int u = 0; u < 32; ++u) {
-            int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
-            const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
-            if (lane == 0) top = t0;
-            const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
-            int nw = diag, nn = top;
+    for (int q = 0; q < KL / 8; ++q) {
+        const uint2 v = __ldg(p + q);
 #pragma unroll
-            for (int r = 0; r < KL; ++r) {
-                const int sc = (rc[r] == c) ? C.match : C.mismatch;
-                const int pre = __viaddmax_s32_relu(H[r], C.gap, nw + sc);
-                nw = H[r];
-                H[r] = __viaddmax_s32(nn, C.gap, pre);
-                nn = H[r];
-            }
-            sink(u, top, H, true, s0 + u - lane + 1);
-            diag = top;
+        for (int e = 0; e < 4; ++e) {
+            rc[8 * q + e] = (int)((v.x >> (8 * e)) & 0xffu);
+            rc[8 * q + 4 + e] = (int)((v.y >> (8 * e)) & 0xffu);
         }
-        return;
     }
-#pragma unroll 1
-    for (int u = 0; u < 32; ++u) {
-        const int s = s0 + u;
-        int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
-        const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
-        if (lane == 0) top = t0;
-        const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
-        const int j = s - lane + 1;
-        const bool valid = (j >= 1) && (j <= C.n);
-        if (valid) {
-            int nw = diag, nn = top;
-#pragma unroll
-            for (int r = 0; r < KL; ++r) {
-                const int sc = (rc[r] == c) ? C.match : C.mismatch;
-                const int pre = __viaddmax_s32_relu(H[r], C.gap, nw + sc);     // max(W+gap, NW+s, 0)
-                nw = H[r];
-                H[r] = __viaddmax_s32(nn, C.gap, pre);                          // max(N+gap, pre)
-                nn = H[r];
-            }
-        }
-        sink(u, top, H, valid, j);
-        diag = top;
-    }
-}
-
-__device__ __forceinline__ int top_prefetch(const WCtx &C, int band, int s0, int lane)
-{
-    if (band == 0) return 0;
-    const int j = s0 + 1 + lane;
-    return (j <= C.n) ? ld_cg(C.brow + (int64_t)(band - 1) * (C.n + 1) + j) : 0;
-}
-
-__device__ __forceinline__ void load_wide_state(const WCtx &C, int band, int blk, int lane, int (&H)[KL], int &diag)
-{
-    if (blk == 0) {
-#pragma unroll
-        for (int r = 0; r < KL; ++r) H[r] = 0;
-        diag = 0;
-        return;
-    }
-    const int32_t *p = C.ck + ((int64_t)band * C.n_blocks + blk) * ((KL + 1) * WL) + lane;
-#pragma unroll
-    for (int r = 0; r < KL; ++r) H[r] = p[r * WL];
-    diag = p[KL * WL];
 }
 
 }  // namespace
 
 // ---------------------------------------------------------------------------------------
-// Fill.  PROF = true (alphabets of up to 8 symbols): the substitution score comes from a per-warp
-// shared-memory profile of the band ([code][KL/4][lane][4], conflict-free LDS.128) and the NW + s add is an
-// IMAD on the FMA pipe, leaving two DPX ops per cell on the integer pipe.  PROF = false: compare + select.
-template <bool PROF, int NC>
-__global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, const int2 *items, int n_items,
-                                                         uint32_t *ticket, int one, int lag_chunks)
+// Fill.  NC = 4 / 8 (alphabets of up to NC symbols, gap < 0): substitution scores from a per-warp
+// shared-memory profile [code][KL/4][lane][4] (conflict-free LDS.128), NW + s as an IMAD on the FMA
+// pipe, two DPX ops per cell.  NC = 0: compare + select, row masks (any alphabet, any gap sign).
+template <int KL, int NC>
+__global__ void __launch_bounds__(128, KL >= 32 ? 3 : 4)
+wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *ticket, int one)
 {
-    extern __shared__ __align__(16) int32_t wprof_all[];          // PROF: per warp [NC codes][KL/4][32 lanes][4], NC = 4 or 8
+    using G = WGeo<KL>;
+    constexpr bool PROF = NC > 0;
+    constexpr int PW = PROF ? NC * KL * WL : 0;                   // profile words per warp
+    constexpr int SW = 2 * (WL + 16);                             // staging per warp: 2 x (32 top words + 64 code bytes)
+    extern __shared__ __align__(16) int32_t wsm[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int32_t *wprof = wprof_all + warp * (NC * KL * WL);
+    int32_t *wprof = wsm + warp * (PW + SW);
+    int32_t *stage = wprof + PW;
+    const int gap = P.gap;
+
     for (;;) {
         uint32_t it = 0;
         if (lane == 0) it = atomicAdd(ticket, 1u);
         it = __shfl_sync(0xffffffffu, it, 0);
         if (it >= (uint32_t)n_items) break;
         const int pair = items[it].x, band = items[it].y;
-        const WCtx C = make_ctx(P, pair);
-        int rc[KL]; bool all_valid;
-        load_rows(C, band, lane, rc, all_valid);
-        const bool warp_all_valid = __all_sync(0xffffffffu, all_valid);
+        const WCtx C = make_ctx<KL>(P, pair);
+        const int T = band * WL + lane;                           // this lane's lane-row
+        const int nvalid = min(KL, max(0, C.m - T * KL));         // real rows of this lane
+        int rc[KL];
+        load_row_codes<KL>(C.read, T, rc);
+        __syncwarp();
         if (PROF) {
-            __syncwarp();
 #pragma unroll
-            for (int c = 0; c < NC; ++c)
+            for (int c = 0; c < (PROF ? NC : 1); ++c)
 #pragma unroll
                 for (int r = 0; r < KL; ++r)
-                    wprof[((c * (KL / 4) + (r >> 2)) * WL + lane) * 4 + (r & 3)] = (rc[r] == c) ? C.match : C.mismatch;
-            __syncwarp();
+                    wprof[((c * (KL / 4) + (r >> 2)) * WL + lane) * 4 + (r & 3)] =
+                        r < nvalid ? ((rc[r] == c) ? C.match : C.mismatch) : PAD_NEG;
+        } else {
+#pragma unroll
+            for (int r = 0; r < KL; ++r) if (r >= nvalid) rc[r] = 0x100 + r;      // matches nothing
         }
         int H[KL], diag = 0;
 #pragma unroll
         for (int r = 0; r < KL; ++r) H[r] = 0;
         int tmax = 0, bmax = 0;
         const int nsteps = C.n + WL - 1;
-        int32_t *my_brow = C.brow + (int64_t)band * (C.n + 1);
+        const int nchunks = (nsteps + WCB - 1) / WCB;
+        int32_t *my_brow = C.brow + (int64_t)band * (C.n_blocks * WCB);
+        const int32_t *up_brow = my_brow - (int64_t)C.n_blocks * WCB;
         const int32_t *prog_up = band > 0 ? P.prog + P.band_off[pair] + band - 1 : nullptr;
         int32_t *prog_me = P.prog + P.band_off[pair] + band;
-        int seen = 0;                                             // columns of the band above known complete
-        int cprev = 0x200;
-        for (int s0 = 0; s0 < nsteps; s0 += 32) {
-            const int ccur = code_prefetch(C, s0, lane);
+        int32_t *recp = C.rec + (((int64_t)band * C.n_blocks) * WL + lane) * G::RW;     // record of block 0
+        int32_t *tmxp = C.tmx + ((int64_t)band * C.n_blocks) * WL + lane;
+        int seen = 0;                                             // steps of the band above known complete
+
+        // reference codes of a chunk: bytes s0-32 .. s0+31 (0-based columns) -> lane L fetches bytes L and L+32
+        auto fetch_codes = [&](int s0, int &c_lo, int &c_hi) {
+            const int j_lo = s0 - 32 + lane, j_hi = s0 + lane;
+            c_lo = (j_lo >= 0 && j_lo < C.n) ? (int)__ldg(C.ref + j_lo) : 0xFF;
+            c_hi = (j_hi >= 0 && j_hi < C.n) ? (int)__ldg(C.ref + j_hi) : 0xFF;
+        };
+        int c_lo, c_hi;
+        fetch_codes(0, c_lo, c_hi);
+
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const int s0 = ch * WCB;
+            int32_t *stg = stage + (ch & 1) * (WL + 16);
+            uint8_t *stg_codes = reinterpret_cast<uint8_t *>(stg + WL);
+            // ---- top boundary of lane 0: bottom row of the band above (column s0 + 1 + L = step s0 + 31 + L there)
+            int tval = 0;
             if (band > 0) {
-                const int need = min(C.n, s0 == 0 ? 32 * lag_chunks : s0 + 32);   // start with `lag_chunks` of slack: a late chunk above no longer stalls the whole cascade below
+                const int need = min(C.n, s0 + WCB) + WL - 1;    // steps the band above must have finished
                 if (seen < need) {
-                    // lane 0 acquires; the other lanes' boundary loads (ld.cg, L2) are issued after the loop's
-                    // branch has resolved on the acquired value, i.e. after the publisher's release
                     if (lane == 0) {
                         int v = ld_acquire(prog_up);
-                        while (v < need) { __nanosleep(32); v = ld_acquire(prog_up); }
+                        while (v < need) { __nanosleep(64); v = ld_acquire(prog_up); }
                         seen = v;
                     }
                     seen = __shfl_sync(0xffffffffu, seen, 0);
+                    __syncwarp();                                 // orders the other lanes' loads after lane 0's acquire
                 }
+                if (s0 + 1 + lane <= C.n) tval = __ldcg(up_brow + s0 + WL - 1 + lane);
             }
-            const int tbuf = top_prefetch(C, band, s0, lane);
-            if (PROF && warp_all_valid && s0 >= WL - 1 && s0 + 32 <= C.n) {
-                // interior chunk: every lane's 32 columns are inside the matrix and every row is a read row -> no
-                // per-step branches, so the unrolled steps overlap (profile loads of step u+1 under the chain of step u)
-#pragma unroll 8
-                for (int u = 0; u < 32; ++u) {
-                    int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
-                    const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
-                    if (lane == 0) top = t0;
-                    const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
-                    int sv[KL];
-                    const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & (NC - 1)) * (KL / 4) * WL + lane;
+            stg[lane] = tval;
+            stg_codes[lane] = (uint8_t)c_lo;
+            stg_codes[lane + 32] = (uint8_t)c_hi;
+            __syncwarp();
+            if (ch + 1 < nchunks) fetch_codes(s0 + WCB, c_lo, c_hi);             // prefetch: lands during this chunk
+            const uint8_t *cb = stg_codes + 32 - lane;            // code of step u: cb[u]  (column s0 + u - lane, 0-based)
+            int32_t *seam = recp + G::KW;
+
+            const bool interior = PROF && (s0 >= WL) && (s0 + WCB <= C.n);
+            if (interior) {
+                // every lane's 32 columns are inside the matrix: no per-step branch, steps overlap
+#pragma unroll 2
+                for (int q = 0; q < WCB / 4; ++q) {
+                    const int4 t4 = *reinterpret_cast<const int4 *>(stg + 4 * q);
+                    const int tq[4] = {t4.x, t4.y, t4.z, t4.w};
+                    int sm[4], bw[4];
 #pragma unroll
-                    for (int q = 0; q < KL / 4; ++q) {
-                        const int4 v = pp[q * WL];
-                        sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
-                    }
-                    int nw = diag, nn = top;
-#pragma unroll
-                    for (int r = 0; r < KL; ++r) {
-                        const int tt = nw * one + sv[r];
-                        const int pre = __viaddmax_s32_relu(H[r], C.gap, tt);
-                        nw = H[r];
-                        H[r] = __viaddmax_s32(nn, C.gap, pre);
-                        nn = H[r];
-                    }
-                    if (lane == WL - 1) my_brow[s0 + u - lane + 1] = H[KL - 1];
-#pragma unroll
-                    for (int r = 0; r < KL; r += 2) tmax = __vimax3_s32(tmax, H[r], H[r + 1]);
-                    diag = top;
-                }
-            } else {
-#pragma unroll 4
-            for (int u = 0; u < 32; ++u) {
-                const int s = s0 + u;
-                int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
-                const int t0 = __shfl_sync(0xffffffffu, tbuf, u);
-                if (lane == 0) top = t0;
-                const int c = __shfl_sync(0xffffffffu, lane <= u ? ccur : cprev, (u - lane) & 31);
-                const int j = s - lane + 1;
-                if ((j >= 1) && (j <= C.n)) {
-                    int sv[KL];
-                    if (PROF) {
+                    for (int e = 0; e < 4; ++e) {
+                        const int u = 4 * q + e;
+                        int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
+                        if (lane == 0) top = tq[e];
+                        const int c = cb[u];
                         const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & (NC - 1)) * (KL / 4) * WL + lane;
+                        int nw = diag, nn = top;
 #pragma unroll
-                        for (int q = 0; q < KL / 4; ++q) {
-                            const int4 v = pp[q * WL];
-                            sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
+                        for (int g4 = 0; g4 < KL / 4; ++g4) {
+                            const int4 v = pp[g4 * WL];
+                            const int sv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                            for (int x = 0; x < 4; ++x) {
+                                const int r = 4 * g4 + x;
+                                const int tt = nw * one + sv[x];                       // NW + s   (IMAD, FMA pipe)
+                                const int pre = __viaddmax_s32_relu(H[r], gap, tt);    // max(W + gap, NW + s, 0)
+                                nw = H[r];
+                                H[r] = __viaddmax_s32(nn, gap, pre);                   // max(N + gap, pre)
+                                nn = H[r];
+                            }
                         }
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < KL; ++r) sv[r] = (rc[r] == c) ? C.match : C.mismatch;
-                    }
-                    int nw = diag, nn = top;
-#pragma unroll
-                    for (int r = 0; r < KL; ++r) {
-                        const int tt = PROF ? nw * one + sv[r] : nw + sv[r];           // IMAD (FMA pipe) when PROF
-                        const int pre = __viaddmax_s32_relu(H[r], C.gap, tt);           // max(W+gap, NW+s, 0)
-                        nw = H[r];
-                        H[r] = __viaddmax_s32(nn, C.gap, pre);                          // max(N+gap, pre)
-                        nn = H[r];
-                    }
-                    if (lane == WL - 1) my_brow[j] = H[KL - 1];
-                    if (all_valid) {
 #pragma unroll
                         for (int r = 0; r < KL; r += 2) tmax = __vimax3_s32(tmax, H[r], H[r + 1]);
-                    } else {
-#pragma unroll
-                        for (int r = 0; r < KL; ++r) if (rc[r] < 0x100) tmax = max(tmax, H[r]);
+                        diag = top;
+                        sm[e] = top; bw[e] = H[KL - 1];
                     }
+                    *reinterpret_cast<int4 *>(seam + 4 * q) = make_int4(sm[0], sm[1], sm[2], sm[3]);
+                    if (lane == WL - 1) *reinterpret_cast<int4 *>(my_brow + s0 + 4 * q) = make_int4(bw[0], bw[1], bw[2], bw[3]);
                 }
-                diag = top;
-            }
-            }
-            cprev = ccur;
-            // publish: lane 31 (the only writer of the bottom row) has finished every column <= s0 + 1
-            if (lane == WL - 1) st_release(prog_me, min(C.n, max(0, s0 + 1)));
-            const int s_next = s0 + 32;
-            if ((s_next % WCB) == 0) {
-                const int b = s_next / WCB;
-                C.tmx[((int64_t)band * C.n_blocks + b - 1) * WL + lane] = tmax;
-                bmax = max(bmax, tmax);
-                tmax = 0;
-                if (s_next < nsteps) {
-                    int32_t *p = C.ck + ((int64_t)band * C.n_blocks + b) * ((KL + 1) * WL) + lane;
+            } else {
+#pragma unroll 1
+                for (int u = 0; u < WCB; ++u) {
+                    int top = __shfl_up_sync(0xffffffffu, H[KL - 1], 1);
+                    if (lane == 0) top = stg[u];
+                    const int c = cb[u];
+                    const int j = s0 + u - lane + 1;
+                    if (j >= 1 && j <= C.n) {
+                        int nw = diag, nn = top;
+                        if (PROF) {
+                            const int4 *pp = reinterpret_cast<const int4 *>(wprof) + (c & ((PROF ? NC : 1) - 1)) * (KL / 4) * WL + lane;
 #pragma unroll
-                    for (int r = 0; r < KL; ++r) p[r * WL] = H[r];
-                    p[KL * WL] = diag;
+                            for (int g4 = 0; g4 < KL / 4; ++g4) {
+                                const int4 v = pp[g4 * WL];
+                                const int sv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                                for (int x = 0; x < 4; ++x) {
+                                    const int r = 4 * g4 + x;
+                                    const int tt = nw * one + sv[x];
+                                    const int pre = __viaddmax_s32_relu(H[r], gap, tt);
+                                    nw = H[r];
+                                    H[r] = __viaddmax_s32(nn, gap, pre);
+                                    nn = H[r];
+                                }
+                            }
+#pragma unroll
+                            for (int r = 0; r < KL; r += 2) tmax = __vimax3_s32(tmax, H[r], H[r + 1]);
+                        } else {
+#pragma unroll
+                            for (int r = 0; r < KL; ++r) {
+                                const int sc = (rc[r] == c) ? C.match : C.mismatch;
+                                const int pre = __viaddmax_s32_relu(H[r], gap, nw + sc);
+                                nw = H[r];
+                                H[r] = __viaddmax_s32(nn, gap, pre);
+                                nn = H[r];
+                                if (r < nvalid) tmax = max(tmax, H[r]);          // rows beyond the read may exceed the real maximum when gap >= 0
+                            }
+                        }
+                    }
+                    diag = top;
+                    seam[u] = top;
+                    if (lane == WL - 1) my_brow[s0 + u] = H[KL - 1];
                 }
             }
-        }
-        {
-            const int s_end = ((nsteps + 31) >> 5) << 5;
-            if ((s_end % WCB) != 0) {
-                C.tmx[((int64_t)band * C.n_blocks + s_end / WCB) * WL + lane] = tmax;
-                bmax = max(bmax, tmax);
+            // ---- block boundary: tile maximum, next block's checkpoint, progress
+            tmxp[(int64_t)ch * WL] = tmax;
+            bmax = max(bmax, tmax);
+            tmax = 0;
+            recp += WL * G::RW;
+            if (ch + 1 < nchunks) {
+#pragma unroll
+                for (int q = 0; q < G::KW / 4; ++q) {
+                    int v[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int w = 4 * q + e;
+                        v[e] = w < KL ? H[w < KL ? w : 0] : (w == KL ? diag : 0);
+                    }
+                    *reinterpret_cast<int4 *>(recp + 4 * q) = make_int4(v[0], v[1], v[2], v[3]);
+                }
             }
+            if (lane == WL - 1) st_release(prog_me, ch + 1 < nchunks ? s0 + WCB : 0x7fffffff);
         }
-        if (lane == WL - 1) st_release(prog_me, C.n);
 #pragma unroll
         for (int o = 16; o; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
         if (lane == 0 && bmax > 0)
@@ -323,168 +292,283 @@ __global__ void __launch_bounds__(128) wide_fill_kernel(const WideParams P, cons
     }
 }
 
-// one thread per (pair, band, block): lanes whose tile maximum equals the pair's score
-__global__ void wide_flag_kernel(const WideParams P, int64_t total_blocks, WideTask *tasks, uint32_t cap, uint32_t *count)
+// copies the wide reads into the padded, 16-byte aligned code buffer (0xFE beyond the read's end)
+__global__ void wide_pad_reads_kernel(const uint8_t *codes, const int64_t *read_off, const int32_t *reads, int n_reads,
+                                      const int64_t *rpad_off, const int64_t *rpad_len, uint8_t *rpad)
 {
-    for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total_blocks;
-         idx += (int64_t)gridDim.x * blockDim.x) {
+    for (int k = blockIdx.y; k < n_reads; k += gridDim.y) {
+        const int rd = reads[k];
+        const int64_t src = read_off[rd], m = read_off[rd + 1] - src, dst = rpad_off[rd], len = rpad_len[k];
+        for (int64_t x = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; x < len; x += (int64_t)gridDim.x * blockDim.x)
+            rpad[dst + x] = x < m ? codes[src + x] : (uint8_t)0xFE;
+    }
+}
+
+// one warp per (pair, band, block): the lanes whose tile maximum equals the pair's score become tasks
+__global__ void __launch_bounds__(256) wide_flag_kernel(const WideParams P, int64_t total_blocks, WideTask *tasks,
+                                                         uint32_t cap, uint32_t *count)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+    for (int64_t idx = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5; idx < total_blocks; idx += n_warps) {
         int lo = 0, hi = P.n_pairs;
         while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (P.blk_off[mid] <= idx) lo = mid; else hi = mid; }
         const int pair = lo;
-        const int64_t rel = idx - P.blk_off[pair];
         const int ro = P.pair_ref[pair];
-        const int n = (int)(P.ref_off[ro + 1] - P.ref_off[ro]);
-        int nb = (n + WL - 1 + WCB - 1) / WCB; if (nb < 1) nb = 1;
-        const int band = (int)(rel / nb), blk = (int)(rel - (int64_t)band * nb);
         const int S = P.scores[(int64_t)ro * P.n_reads + P.pair_read[pair]];
         if (S <= 0) continue;
-        const int32_t *tm = P.tmx + idx * WL;
-        uint32_t mask = 0;
-        for (int l = 0; l < WL; ++l) if (tm[l] == S) mask |= 1u << l;
-        if (mask) {
-            const uint32_t k = atomicAdd(count, 1u);
-            if (k < cap) tasks[k] = WideTask{pair, band, blk, mask};
+        const bool hit = P.tmx[idx * WL + lane] == S;
+        const uint32_t mask = __ballot_sync(0xffffffffu, hit);
+        if (!mask) continue;
+        const int64_t rel = idx - P.blk_off[pair];
+        const int n = (int)(P.ref_off[ro + 1] - P.ref_off[ro]);
+        const int nb = (n + WL - 1 + WCB - 1) / WCB;
+        const int band = (int)(rel / nb), blk = (int)(rel - (int64_t)band * nb);
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(count, (uint32_t)__popc(mask));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (hit) {
+            const uint32_t k = base + (uint32_t)__popc(mask & ((1u << lane) - 1u));
+            if (k < cap) tasks[k] = WideTask{pair, band, blk, (uint32_t)lane};
         }
     }
 }
 
+namespace {
+
+// One tile (band, block, lane) recomputed by one thread from its record.
+template <int KL>
+struct WTile {
+    int H[KL], rc[KL];
+    int diag, j0;
+    const int32_t *rec;
+
+    __device__ __forceinline__ void load(const WCtx &C, int band, int t, int blk)
+    {
+        using G = WGeo<KL>;
+        rec = C.rec + (((int64_t)band * C.n_blocks + blk) * WL + t) * G::RW;
+        diag = 0;
+#pragma unroll
+        for (int r = 0; r < KL; ++r) H[r] = 0;
+        if (blk > 0) {
+#pragma unroll
+            for (int q = 0; q < G::KW / 4; ++q) {
+                const int4 a = __ldg(reinterpret_cast<const int4 *>(rec) + q);
+                const int v[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int w = 4 * q + e;
+                    if (w < KL) H[w < KL ? w : 0] = v[e];
+                    else if (w == KL) diag = v[e];
+                }
+            }
+        }
+        load_row_codes<KL>(C.read, band * WL + t, rc);
+        j0 = blk * WCB - t + 1;                                   // column of step u = j0 + u
+    }
+
+    // fn(u, top, H, real, j) after every step; the column is computed when it is inside the matrix
+    template <class Fn>
+    __device__ __forceinline__ void run(const WCtx &C, Fn &&fn)
+    {
+        const int gap = C.gap, match = C.match, mismatch = C.mismatch;
+        const int4 *sq = reinterpret_cast<const int4 *>(rec + WGeo<KL>::KW);
+#pragma unroll 1
+        for (int q = 0; q < WCB / 4; ++q) {
+            const int4 a = __ldg(sq + q);
+            const int tq[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = 4 * q + e, j = j0 + u;
+                const int top = tq[e];
+                const bool real = (j >= 1) && (j <= C.n);
+                if (real) {
+                    const int c = (int)__ldg(C.ref + j - 1);
+                    int nw = diag, nn = top;
+#pragma unroll
+                    for (int r = 0; r < KL; ++r) {
+                        const int sc = (rc[r] == c) ? match : mismatch;
+                        const int x = __viaddmax_s32_relu(nw, sc, 0);        // max(NW + s, 0)
+                        const int pre = __viaddmax_s32(H[r], gap, x);        // max(W + gap, .)
+                        nw = H[r];
+                        H[r] = __viaddmax_s32(nn, gap, pre);                 // max(N + gap, .)
+                        nn = H[r];
+                    }
+                }
+                fn(u, top, H, real, j);
+                diag = top;
+            }
+        }
+    }
+};
+
+}  // namespace
+
+// one thread per flagged tile: every cell of the tile that equals the pair's score becomes a key
+template <int KL>
 __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, const WideTask *tasks,
                                                            const uint32_t *n_tasks_ptr, uint32_t cap_tasks,
                                                            uint64_t *keys, uint32_t cap, uint32_t *count)
 {
     const uint32_t n_tasks = min(*n_tasks_ptr, cap_tasks);
-    const int lane = threadIdx.x & 31;
-    const uint32_t n_warps = gridDim.x * (blockDim.x >> 5);
-    for (uint32_t task = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; task < n_tasks; task += n_warps) {
+    const uint32_t n_threads = gridDim.x * blockDim.x;
+    for (uint32_t task = blockIdx.x * blockDim.x + threadIdx.x; task < n_tasks; task += n_threads) {
         const WideTask T = tasks[task];
-        const WCtx C = make_ctx(P, T.pair);
-        int rc[KL]; bool all_valid;
-        load_rows(C, T.band, lane, rc, all_valid);
-        int H[KL], diag;
-        load_wide_state(C, T.band, T.block, lane, H, diag);
+        const WCtx C = make_ctx<KL>(P, T.pair);
+        const int t = (int)T.lane;
         const int S = P.scores[(int64_t)P.pair_ref[T.pair] * P.n_reads + P.pair_read[T.pair]];
-        const bool mine = (T.lane_mask >> lane) & 1u;
-        int cprev = code_prefetch(C, T.block * WCB - 32, lane);
-        for (int u0 = 0; u0 < WCB; u0 += 32) {
-            const int s0 = T.block * WCB + u0;
-            const int tbuf = top_prefetch(C, T.band, s0, lane);
-            const int ccur = code_prefetch(C, s0, lane);
-            wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
-                       [&](int, int, const int (&Hc)[KL], bool valid, int j) {
-                           if (!(valid && mine)) return;
+        const int row0 = (T.band * WL + t) * KL;                  // 0-based first row of the tile
+        const int nvalid = min(KL, max(0, C.m - row0));
+        WTile<KL> W;
+        W.load(C, T.band, t, T.block);
 #pragma unroll
-                           for (int r = 0; r < KL; ++r) {
-                               const int i = T.band * BH + lane * KL + r + 1;
-                               if (Hc[r] == S && i <= C.m) {
-                                   const uint32_t k = atomicAdd(count, 1u);
-                                   if (k < cap) keys[k] = wide_key((uint64_t)T.pair, (uint32_t)i, (uint32_t)j);
-                               }
-                           }
-                       });
-            cprev = ccur;
-        }
+        for (int r = 0; r < KL; ++r) if (r >= nvalid) W.rc[r] = 0x100 + r;
+        W.run(C, [&](int, int, const int (&Hc)[KL], bool real, int j) {
+            if (!real) return;
+            uint32_t rm = 0;
+#pragma unroll
+            for (int r = 0; r < KL; ++r) rm |= (Hc[r] == S) ? (1u << r) : 0u;
+            if (nvalid < 32) rm &= (1u << nvalid) - 1u;
+            while (rm) {
+                const int r = __ffs((int)rm) - 1;
+                rm &= rm - 1;
+                const uint32_t k = atomicAdd(count, 1u);
+                if (k < cap) keys[k] = wide_key((uint64_t)T.pair, (uint32_t)(row0 + r + 1), (uint32_t)j);
+            }
+        });
     }
 }
 
-// Traceback: one warp per max cell.  Tile of the current (band, block):
-//   tile[c][lane][w], c = 0..WCB (c = 0: checkpointed column), w = 0: boundary row above the
-//   lane (row band*BH + lane*KL of the matrix), w = 1..KL: the lane's rows.
-// BYTE: the tile keeps only the low 8 bits of every score (12 bytes per lane and column instead of 36), which
-// quadruples the warps per SM.  That is enough because the walker carries the exact score of its cell (the pair
-// maximum minus the moves so far) and a candidate never lies 250 or more below H (tile_trace_ok): equality of the
-// low bytes is equality.  Other score sets use the int32 tile.
-template <bool BYTE>
-__global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, const uint64_t *keys, uint32_t n_cells,
+// ---------------------------------------------------------------------------------------
+// Traceback.  Tile in shared memory, one per thread, words interleaved over the CTA's threads
+// (word w of thread x at [w * NT + x]): column cc = 0 .. 32 (0 = the checkpointed column), element
+// rr = 0 .. KL (0 = the boundary row above the lane).
+// BYTE: only the low 8 bits of every score are kept.  That is enough because the walker carries the exact score
+// of its cell (the pair maximum minus the moves so far) and a candidate never lies 250 or more below H
+// (tile_trace_ok): equality of the low bytes is equality.  Other score sets use int32 tiles.
+template <int KL, int NT, int G, bool BYTE>
+__global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, const uint64_t *keys, uint32_t n_cells,
                                                          int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
                                                          int64_t ops_stride)
 {
-    extern __shared__ int32_t wtile[];                       // [WCB + 1][WL][KL + 1] words, or [WCB + 1][WL][3] words of bytes
-    const int lane = threadIdx.x;
-    constexpr int LW = BYTE ? (KL + 1 + 3) / 4 : KL + 1;      // words per lane and column
-    constexpr int CW = WL * LW;
-    auto store_col = [&](int c, int top, const int (&Hc)[KL]) {
-        int32_t *col = wtile + c * CW + lane * LW;
+    constexpr int ROWE = KL + 1;
+    constexpr int ROWW = BYTE ? (ROWE + 3) / 4 : ROWE;             // words per tile column
+    constexpr int TILE_WORDS = ROWW * (WCB + 1);
+    constexpr int HS = G / 2 > 0 ? G / 2 : 1;                      // lane-rows a corridor covers
+    extern __shared__ uint32_t tsm[];
+    int32_t *slot_blk = reinterpret_cast<int32_t *>(tsm + (size_t)TILE_WORDS * NT);     // [NT] block of the tile in each thread's slot
+    uint32_t *mytile = tsm + threadIdx.x;
+    const int gl = threadIdx.x % G;                                // lane in group
+    const int leader = threadIdx.x - gl;
+    const unsigned gmask = 0xffffffffu;
+    const uint32_t n_groups = gridDim.x * (NT / G);
+    const uint32_t gid = (blockIdx.x * NT + threadIdx.x) / G;
+    const int gap = P.gap, match = P.match, mismatch = P.mismatch;
+
+    auto store_col = [&](int cc, int top, const int (&Hc)[KL]) {
+        uint32_t *col = mytile + (size_t)cc * ROWW * NT;
         if (BYTE) {
 #pragma unroll
-            for (int w = 0; w < LW; ++w) {
+            for (int w = 0; w < ROWW; ++w) {
                 uint32_t v[4];
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * w + e;                       // byte k: 0 = boundary row, 1..KL = the lane's rows
-                    v[e] = k == 0 ? (uint32_t)top : (k <= KL ? (uint32_t)Hc[k - 1 < KL && k >= 1 ? k - 1 : 0] : 0u);
+                    const int k = 4 * w + e;                       // element k: 0 = boundary row, 1..KL = the lane's rows
+                    v[e] = k == 0 ? (uint32_t)top : (k <= KL ? (uint32_t)Hc[(k >= 1 && k <= KL) ? k - 1 : 0] : 0u);
                 }
-                col[w] = (int32_t)__byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                col[w * NT] = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
             }
         } else {
-            col[0] = top;
+            col[0] = (uint32_t)top;
 #pragma unroll
-            for (int r = 0; r < KL; ++r) col[r + 1] = Hc[r];
+            for (int r = 0; r < KL; ++r) col[(r + 1) * NT] = (uint32_t)Hc[r];
         }
     };
-    for (uint32_t cell = blockIdx.x; cell < n_cells; cell += gridDim.x) {
+    // element (rr, cc) of the tile in thread `slot`'s slot (low byte when BYTE)
+    auto at = [&](int slot, int rr, int cc) -> int {
+        if (BYTE)
+            return (int)reinterpret_cast<const uint8_t *>(tsm)[((size_t)(cc * ROWW + (rr >> 2)) * NT + slot) * 4 + (rr & 3)];
+        return (int)tsm[(size_t)(cc * ROWE + rr) * NT + slot];
+    };
+
+    for (uint32_t cell = gid; cell < n_cells; cell += n_groups) {            // group-uniform
         const uint64_t key = keys[cell];
         const int pair = (int)wide_key_pair(key);
         int ci = (int)wide_key_i(key), cj = (int)wide_key_j(key);
-        const WCtx C = make_ctx(P, pair);
+        const WCtx C = make_ctx<KL>(P, pair);
         int hcur = P.scores[(int64_t)P.pair_ref[pair] * P.n_reads + P.pair_read[pair]];
         int beginning = 0;
         int64_t oplen = 0;
         uint32_t opword = 0;
         uint32_t *myops = ops + (int64_t)cell * ops_stride;
-        while (hcur > 0) {                                     // warp-uniform: state is broadcast below
-            const int band = (ci - 1) / BH;
-            const int tl = ((ci - 1) % BH) / KL;
-            const int blk = (cj - 1 + tl) / WCB;
-            int rc[KL]; bool all_valid;
-            load_rows(C, band, lane, rc, all_valid);
-            int H[KL], diag;
-            load_wide_state(C, band, blk, lane, H, diag);
-            store_col(0, diag, H);
-            int cprev = code_prefetch(C, blk * WCB - 32, lane);
-            for (int u0 = 0; u0 < WCB; u0 += 32) {
-                const int s0 = blk * WCB + u0;
-                const int tbuf = top_prefetch(C, band, s0, lane);
-                const int ccur = code_prefetch(C, s0, lane);
-                wide_chunk(C, s0, lane, tbuf, cprev, ccur, rc, H, diag,
-                           [&](int u, int top, const int (&Hc)[KL], bool, int) { store_col(u0 + u + 1, top, Hc); });
-                cprev = ccur;
-            }
-            __syncwarp();
-            if (lane == 0) {
-                while (hcur > 0) {
-                    if ((ci - 1) / BH != band) break;                     // left the band upwards
-                    const int tc = ((ci - 1) % BH) / KL;
-                    const int r = (ci - 1) % KL + 1;                        // 1..KL
-                    const int c = cj - (blk * WCB - tc);
-                    if (c < 1 || c > WCB) break;
-                    int hw, hn, hnw;
-                    if (BYTE) {
-                        const uint8_t *lt = reinterpret_cast<const uint8_t *>(wtile + c * CW + tc * LW) + r;
-                        hw = lt[-CW * 4]; hn = lt[-1]; hnw = lt[-CW * 4 - 1];
-                    } else {
-                        const int32_t *lt = wtile + c * CW + tc * LW + r;
-                        hw = lt[-CW]; hn = lt[-1]; hnw = lt[-CW - 1];
-                    }
-                    const int sc = (C.read[ci - 1] == C.ref[cj - 1]) ? C.match : C.mismatch;
-                    const int mask = BYTE ? 0xff : -1;
-                    const bool eq_a = ((hnw + sc - hcur) & mask) == 0, eq_i = ((hn + C.gap - hcur) & mask) == 0,
-                               eq_d = ((hw + C.gap - hcur) & mask) == 0;
-                    const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
-                    beginning = cj;
-                    hcur -= (op == 1u) ? sc : C.gap;                      // exact score of the next cell
-                    ci -= (op != 3u);
-                    cj -= (op != 2u);
-                    opword |= op << (2 * (int)(oplen & 15));
-                    ++oplen;
-                    if ((oplen & 15) == 0) { myops[(oplen >> 4) - 1] = opword; opword = 0; }
+        while (hcur > 0) {                                         // group-uniform: the state is broadcast below
+            // ---- corridor: slot (k, d) = lane-row T0 - k, block b_k - d, b_k from the diagonal through (ci, cj)
+            const int T0 = (ci - 1) / KL;
+            const int k = gl >> 1, d = gl & 1;
+            const int Tk = T0 - k;
+            int myblk = -1;
+            if (Tk >= 0) {
+                const int t = Tk % WL;
+                const int di = k == 0 ? 0 : ci - (Tk * KL + KL);   // rows the path climbs to reach lane-row Tk
+                const int step = cj - di - 1 + t;
+                if (step >= 0) {
+                    const int b = step / WCB - d;
+                    if (b >= 0 && b < C.n_blocks) myblk = b;
                 }
             }
-            hcur = __shfl_sync(0xffffffffu, hcur, 0);
-            ci = __shfl_sync(0xffffffffu, ci, 0);
-            cj = __shfl_sync(0xffffffffu, cj, 0);
-            __syncwarp();
+            if (myblk >= 0) {
+                WTile<KL> W;
+                W.load(C, Tk / WL, Tk % WL, myblk);
+                store_col(0, W.diag, W.H);
+                W.run(C, [&](int u, int top, const int (&Hc)[KL], bool, int) { store_col(u + 1, top, Hc); });
+            }
+            slot_blk[threadIdx.x] = myblk;
+            if (G > 1) __syncwarp(gmask);
+            if (gl == 0) {
+                // ---- walk (SmithWaterman.java:380-409) through the corridor's tiles
+                for (;;) {
+                    const int T = (ci - 1) / KL;
+                    const int kk = T0 - T;
+                    if (kk >= HS) break;
+                    const int t = T % WL;
+                    const int step = cj - 1 + t;
+                    const int b = step / WCB;
+                    int slot = leader + 2 * kk;
+                    if (slot_blk[slot] != b) {
+                        if (G > 1 && slot_blk[slot + 1] == b) ++slot; else break;
+                    }
+                    int r = ci - T * KL;                           // 1..KL
+                    int c = step - b * WCB + 1;                    // 1..WCB
+                    const int cbase = cj - c;
+                    while (true) {
+                        const int hn = at(slot, r - 1, c), hw = at(slot, r, c - 1), hnw = at(slot, r - 1, c - 1);
+                        const int sc = (__ldg(C.read + ci - 1) == __ldg(C.ref + cj - 1)) ? match : mismatch;
+                        const int mask = BYTE ? 0xff : -1;
+                        const bool eq_a = ((hnw + sc - hcur) & mask) == 0, eq_i = ((hn + gap - hcur) & mask) == 0,
+                                   eq_d = ((hw + gap - hcur) & mask) == 0;
+                        const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
+                        beginning = cj;
+                        hcur -= (op == 1u) ? sc : gap;             // exact score of the next cell
+                        const int up = op != 3u, left = op != 2u;
+                        r -= up; ci -= up;
+                        c -= left; cj -= left;
+                        opword |= op << (2 * (int)(oplen & 15));
+                        ++oplen;
+                        if ((oplen & 15) == 0) { myops[(oplen >> 4) - 1] = opword; opword = 0; }
+                        if (hcur <= 0 || r == 0 || c == 0) break;  // done, or the path left this tile
+                    }
+                    (void)cbase;
+                    if (hcur <= 0) break;
+                }
+            }
+            if (G > 1) {
+                hcur = __shfl_sync(gmask, hcur, 0);
+                ci = __shfl_sync(gmask, ci, 0);
+                cj = __shfl_sync(gmask, cj, 0);
+                __syncwarp(gmask);
+            }
         }
-        if (lane == 0) {
+        if (gl == 0) {
             if (oplen & 15) myops[oplen >> 4] = opword;
             beginnings[cell] = beginning;
             op_lens[cell] = (int32_t)oplen;
@@ -493,72 +577,124 @@ __global__ void __launch_bounds__(32) wide_trace_kernel(const WideParams P, cons
 }
 
 // ---------------------------------------------------------------------------------------
-cudaError_t launch_wide_fill(const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count,
+namespace {
+
+template <int KL, int NC>
+cudaError_t launch_fill_k(const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count, cudaStream_t st)
+{
+    constexpr int PW = NC > 0 ? NC * KL * WL : 0, SW = 2 * (WL + 16);
+    const size_t smem = (size_t)4 * (PW + SW) * sizeof(int32_t);
+    static const int env_ctas = getenv("SWB_WIDE_CTAS_PER_SM") ? atoi(getenv("SWB_WIDE_CTAS_PER_SM")) : 0;
+    int per_sm = KL >= 32 ? 3 : 4;                                          // registers (__launch_bounds__)
+    per_sm = std::min<int>(per_sm, (int)((220 * 1024) / (smem + 1024)));    // shared memory
+    if (env_ctas > 0) per_sm = std::min(per_sm, env_ctas);
+    per_sm = std::max(per_sm, 1);
+    const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
+    cudaError_t e = cudaFuncSetAttribute(wide_fill_kernel<KL, NC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    wide_fill_kernel<KL, NC><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1);
+    return cudaGetLastError();
+}
+
+template <int KL>
+cudaError_t launch_fill_kl(const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count, cudaStream_t st)
+{
+    static const bool no_prof = getenv("SWB_WIDE_NO_PROFILE") != nullptr;
+    if (P.gap < 0 && P.n_symbols <= 4 && !no_prof) return launch_fill_k<KL, 4>(P, items, n_items, ticket, sm_count, st);
+    if (P.gap < 0 && P.n_symbols <= 8 && !no_prof) return launch_fill_k<KL, 8>(P, items, n_items, ticket, sm_count, st);
+    return launch_fill_k<KL, 0>(P, items, n_items, ticket, sm_count, st);
+}
+
+template <int KL, int NT, int G, bool BYTE>
+cudaError_t launch_trace_k(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+                           int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
+{
+    constexpr int ROWW = BYTE ? (KL + 1 + 3) / 4 : KL + 1;
+    const size_t smem = ((size_t)ROWW * (WCB + 1) * NT + NT) * sizeof(uint32_t);
+    cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel<KL, NT, G, BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const int per_sm = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));
+    const int64_t groups = ((int64_t)n_cells + (NT / G) - 1) / (NT / G);
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(groups, (int64_t)sm_count * per_sm));
+    wide_trace_kernel<KL, NT, G, BYTE><<<(unsigned)ctas, NT, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
+    return cudaGetLastError();
+}
+
+template <int KL>
+cudaError_t launch_trace_kl(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+                            int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
+{
+    const bool bytes = tile_trace_ok(P.match, P.mismatch, P.gap);        // same bound as the short path's byte tiles
+    static const int env_g = getenv("SWB_WIDE_TRACE_G") ? atoi(getenv("SWB_WIDE_TRACE_G")) : 0;
+    // one warp per cell while the cells cannot fill the machine with one thread each
+    const bool warp_mode = env_g ? env_g == 32 : (int64_t)n_cells < (int64_t)sm_count * 256;
+    constexpr int NTB = KL >= 32 ? 64 : 128;                              // byte tiles: 76 / 84 / 50 KB per CTA
+    if (bytes) {
+        if (warp_mode) return launch_trace_k<KL, NTB, 32, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        return launch_trace_k<KL, NTB, 1, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+    }
+    if (warp_mode) return launch_trace_k<KL, 32, 32, false>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+    return launch_trace_k<KL, 32, 1, false>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+}
+
+}  // namespace
+
+cudaError_t launch_wide_pad_reads(const uint8_t *codes, const int64_t *read_off, const int32_t *reads, int n_reads,
+                                  const int64_t *rpad_off, const int64_t *rpad_len, uint8_t *rpad, int64_t max_len,
+                                  cudaStream_t st)
+{
+    if (n_reads == 0) return cudaSuccess;
+    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>((max_len + 255) / 256, 256)), (unsigned)std::min(n_reads, 4096));
+    wide_pad_reads_kernel<<<grid, 256, 0, st>>>(codes, read_off, reads, n_reads, rpad_off, rpad_len, rpad);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wide_fill(int KL, const WideParams &P, const int2 *items, int n_items, uint32_t *ticket, int sm_count,
                              cudaStream_t st)
 {
     if (n_items == 0) return cudaSuccess;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(uint32_t), st);
     if (e != cudaSuccess) return e;
-    static const int lag = getenv("SWB_WIDE_LAG") ? std::max(1, atoi(getenv("SWB_WIDE_LAG"))) : 1;
-    static const int env_ctas = getenv("SWB_WIDE_CTAS_PER_SM") ? atoi(getenv("SWB_WIDE_CTAS_PER_SM")) : 0;
-    if (P.n_symbols <= 8) {
-        // profile of 4 or 8 codes; with 4 (DNA) seven 4-warp CTAs fit per SM: cfg3's 3,910 band items then run in ONE
-        // wave (4,144 warp slots) instead of 1.65 waves on 2,368 slots, whose second wave is 35 % idle
-        const int nc = P.n_symbols <= 4 ? 4 : 8;
-        const size_t smem = (size_t)4 * nc * KL * WL * sizeof(int32_t);      // 4 warps x codes x BH rows
-        const int per_sm = env_ctas > 0 ? env_ctas : (nc == 4 ? 7 : 4);
-        const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
-        static PerDeviceOnce attr;
-        if (attr.need()) {
-            e = cudaFuncSetAttribute(wide_fill_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)((size_t)4 * 8 * KL * WL * sizeof(int32_t)));
-            if (e != cudaSuccess) return e;
-        }
-        if (nc == 4) wide_fill_kernel<true, 4><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1, lag);
-        else         wide_fill_kernel<true, 8><<<ctas, 128, smem, st>>>(P, items, n_items, ticket, 1, lag);
-    } else {
-        const int per_sm = env_ctas > 0 ? env_ctas : 4;
-        const int ctas = (int)std::min<int64_t>(((int64_t)n_items + 3) / 4, (int64_t)sm_count * per_sm);
-        wide_fill_kernel<false, 8><<<ctas, 128, 0, st>>>(P, items, n_items, ticket, 1, lag);
+    switch (KL) {
+        case 8:  return launch_fill_kl<8>(P, items, n_items, ticket, sm_count, st);
+        case 16: return launch_fill_kl<16>(P, items, n_items, ticket, sm_count, st);
+        case 32: return launch_fill_kl<32>(P, items, n_items, ticket, sm_count, st);
     }
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_wide_flag(const WideParams &P, int64_t total_blocks, WideTask *tasks, uint32_t cap, uint32_t *count,
-                             cudaStream_t st)
+                             int sm_count, cudaStream_t st)
 {
     if (total_blocks == 0) return cudaSuccess;
-    const int threads = 128;
-    const int64_t blocks = std::min<int64_t>((total_blocks + threads - 1) / threads, 1 << 20);
-    wide_flag_kernel<<<(unsigned)blocks, threads, 0, st>>>(P, total_blocks, tasks, cap, count);
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>((total_blocks + 7) / 8, (int64_t)sm_count * 16));
+    wide_flag_kernel<<<(unsigned)ctas, 256, 0, st>>>(P, total_blocks, tasks, cap, count);
     return cudaGetLastError();
 }
 
-cudaError_t launch_wide_locate(const WideParams &P, const WideTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
+cudaError_t launch_wide_locate(int KL, const WideParams &P, const WideTask *tasks, const uint32_t *n_tasks, uint32_t cap_tasks,
                                uint64_t *keys, uint32_t cap, uint32_t *count, int sm_count, cudaStream_t st)
 {
-    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(((int64_t)cap_tasks + 3) / 4, (int64_t)sm_count * 8));
-    wide_locate_kernel<<<(unsigned)ctas, 128, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count);
+    const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(((int64_t)cap_tasks + 127) / 128, (int64_t)sm_count * 8));
+    switch (KL) {
+        case 8:  wide_locate_kernel<8><<<(unsigned)ctas, 128, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count); break;
+        case 16: wide_locate_kernel<16><<<(unsigned)ctas, 128, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count); break;
+        case 32: wide_locate_kernel<32><<<(unsigned)ctas, 128, 0, st>>>(P, tasks, n_tasks, cap_tasks, keys, cap, count); break;
+        default: return cudaErrorInvalidValue;
+    }
     return cudaGetLastError();
 }
 
-cudaError_t launch_wide_trace(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+cudaError_t launch_wide_trace(int KL, const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
                               int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
 {
     if (n_cells == 0) return cudaSuccess;
-    const bool bytes = tile_trace_ok(P.match, P.mismatch, P.gap);        // same bound as the short path's byte tiles
-    const size_t smem = (size_t)(WCB + 1) * WL * (bytes ? (KL + 1 + 3) / 4 : KL + 1) * sizeof(int32_t);
-    static PerDeviceOnce attr;
-    if (attr.need()) {
-        cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)((size_t)(WCB + 1) * WL * (KL + 1) * sizeof(int32_t)));
-        if (e != cudaSuccess) return e;
+    switch (KL) {
+        case 8:  return launch_trace_kl<8>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        case 16: return launch_trace_kl<16>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        case 32: return launch_trace_kl<32>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
     }
-    const int per_sm = std::max(1, std::min(16, (int)((220 * 1024) / (smem + 1024))));   // CTAs (warps) per SM that fit in shared memory
-    const int64_t ctas = std::min<int64_t>(n_cells, (int64_t)sm_count * per_sm);
-    if (bytes) wide_trace_kernel<true><<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
-    else       wide_trace_kernel<false><<<(unsigned)ctas, 32, smem, st>>>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
-    return cudaGetLastError();
+    return cudaErrorInvalidValue;
 }
 
 }  // namespace swb
