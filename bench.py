@@ -14,7 +14,11 @@ HBM: fill, every max cell, every traceback.  GCUPS = sum(m*n) / 1e9 / seconds.
           and D2H of scores, max-cell lists and packed alignments inside the timed region
   N > 1 : the reference set is sharded over the ranks (balanced by length), every rank
           aligns the same reads against its shard, and the per-read best-hit records are
-          merged with one NCCL all_gather per step (weak scaling: 10k refs per GPU).
+          merged with one ncclAllGather + a merge kernel per step, issued by libswb200 itself
+          on the engine's stream (swb_comm_*, the C ABI a JVM host binds; torch.distributed only
+          carries the 128-byte NCCL id and the timing reductions).  Weak scaling: 10k refs per GPU.
+          After the timed region the merged records of the last step are checked against an
+          independent torch reduction (max score, lowest global ref id).
 
 `--impl reference` times the reference's CPU path instead: the C restatement of
 SmithWaterman.java under oracle/ (no JVM exists in this image) on all host cores.
@@ -232,22 +236,41 @@ def main():
     ref_bases = rs.total_bases
     cells_per_step_local = ref_bases * READ_LEN * B
     stream = torch.cuda.ExternalStream(eng.stream_ptr, device=torch.device("cuda", local_rank))
-    my_ids_t = torch.tensor(my_ids, dtype=torch.int32, device="cuda")
+    my_ids_np = np.asarray(my_ids, dtype=np.int64)
+    comm = None
+    if dist:
+        # the data-path collective lives in libswb200 (swb_comm_*): NCCL id from rank 0, one communicator per rank
+        from sparksmithwaterman_b200 import multigpu
+        box = [multigpu.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = multigpu.Comm(eng, box[0], rank, world)
 
     def step_resident(rd, fetch=False):
         return rd.align(SCORES, scores_only=False, fetch=fetch)
 
-    def allgather_best(res):
+    def allgather_best(res, want_host=False):
+        """best hits -> global ref ids -> ncclAllGather -> merge kernel, all on the engine's stream (C ABI)."""
+        if not comm:
+            return None
+        return comm.allgather_best(res, my_ids_np, want_host=want_host)
+
+    def check_merge(res, merged):
+        """Independent check of the merged records of one step with torch collectives: score = max over ranks of
+        the local best score; ref = lowest global id among the ranks that reach it."""
         if not dist:
-            return
-        best = torch.as_tensor(res.device_array(2, (res.n_reads, 4)), device="cuda").clone()
-        best[:, 1] = my_ids_t[best[:, 1].long().clamp(min=0)]          # shard-local -> global ref id
-        out = [torch.empty_like(best) for _ in range(world)]
-        dist.all_gather(out, best)
-        allb = torch.stack(out)                                         # [world, B, 4]
-        key = allb[:, :, 0].long() * (1 << 32) - allb[:, :, 1].long()  # max score, then lowest ref id
-        win = key.argmax(dim=0)
-        return allb[win, torch.arange(allb.shape[1], device="cuda")]
+            return True
+        local = torch.from_numpy(res.best_hits.astype(np.int64)).cuda()
+        gid = torch.from_numpy(my_ids_np).cuda()[local[:, 1].clamp(min=0)]
+        smax = local[:, 0].clone()
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX)
+        cand = torch.where(local[:, 0] == smax, gid, torch.full_like(gid, 1 << 40))
+        dist.all_reduce(cand, op=dist.ReduceOp.MIN)
+        m = torch.from_numpy(merged.astype(np.int64)).cuda()
+        mine = (local[:, 0] == smax) & (gid == cand)                  # the winning rank also checks (i, j)
+        ok = bool((m[:, 0] == smax).all() and (m[:, 1] == cand).all() and (m[mine][:, 2:] == local[mine][:, 2:]).all())
+        t = torch.tensor([1 if ok else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return bool(t.item())
 
     # resident read batches (inputs in HBM before the timed region)
     resident = [rs.upload_reads(r) for r in step_reads]
@@ -306,15 +329,19 @@ def main():
     if dist:
         dist.barrier()
     t0 = time.perf_counter()
+    merged_last = None
     for k in range(W, W + K):
         res = rs.align(step_reads[k], SCORES)                     # H2D reads + compute + D2H of every result array
         if k == W + K - 1:
             last = res
-        allgather_best(res)
+        merged_last = allgather_best(res, want_host=True)         # merged best hits land on the host too
         if k != W + K - 1:
             res.free()
     torch.cuda.synchronize()
     e2e_ms = (time.perf_counter() - t0) * 1e3 / K
+    merge_ok = check_merge(last, merged_last) if dist else None
+    if dist and not merge_ok:
+        raise SystemExit("bench.py: merged best hits of the last step differ from the independent reduction")
     if dist:
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -328,6 +355,8 @@ def main():
     d2h = sc.nbytes + 4 * len(refs) + 16 * B + 8 * (sc.size + 1) + nc * (8 + 4 + 4 + 8) + 8 + 4 * words
     last.free()
 
+    if comm:
+        comm.close()
     if rank != 0:
         if dist:
             dist.destroy_process_group()
@@ -338,28 +367,37 @@ def main():
     # DPX roofline: 64 integer-pipe lane-ops/clk/SM (measured, profiles/dpx_microbench_r01.json),
     # 2 lane-ops per cell at the s16x2 minimum
     peak_gcups = sms * sm_max * 1e6 * 64 / 2 / 1e9
+    # what this kernel can reach at most on the integer pipe: 2 DPX ops per s16x2 cell PAIR (VIMNMX3 + VIADDMNMX,
+    # the add runs as IMAD on the FMA pipe) -> twice the SURVEY figure
+    alu_bound_gcups = sms * sm_max * 1e6 * 64 / 1e9
     fill_gcups = cells_per_step_local * K / 1e9 / (agg["fill_ms"] * 1e-3) if agg["fill_ms"] > 0 else 0.0
     run_clock = clocks.get("sm_mhz") or sm_max
-    # DRAM bytes of the fill kernel per launch, scaled from the committed ncu --set full capture
-    # (profiles/ncu_kernels_r01.json: one fill launch over a batch of `read_pairs_per_launch` read pairs of this refset)
-    traffic = None
-    try:
-        with open(os.path.join(ROOT, "profiles", "ncu_kernels_r01.json")) as f:
-            prof = json.load(f)
-        cap = next(k for k in prof["kernels"] if "fill_bias_kernel" in k["kernel"])
-        gb = float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])
-        rp_per_launch = (B / 2.0) / max(agg["batches"] / K, 1)
-        traffic = round(gb * 1e9 / float(prof["meta"]["read_pairs_per_launch"]) * rp_per_launch)
-    except Exception:
-        traffic = None
+    # DRAM bytes of the fill kernel per launch: NOT measured in this run -- scaled from the committed ncu --set full
+    # capture (one fill launch over `read_pairs_per_launch` read pairs of this refset) to this run's launch size
+    traffic, traffic_src = None, None
+    for prof_name in ("ncu_kernels_r02.json", "ncu_kernels_r01.json"):
+        try:
+            with open(os.path.join(ROOT, "profiles", prof_name)) as f:
+                prof = json.load(f)
+            cap = next(k for k in prof["kernels"] if "fill_bias_kernel" in k["kernel"])
+            gb = float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])
+            rp_per_launch = (B / 2.0) / max(agg["batches"] / K, 1)
+            traffic = round(gb * 1e9 / float(prof["meta"]["read_pairs_per_launch"]) * rp_per_launch)
+            traffic_src = f"scaled from profiles/{prof_name} (ncu --set full of the same kernel and refset), not measured in this run"
+            break
+        except Exception:
+            continue
     roofline = {"bound": "int_dpx", "kernel": "fill_bias_kernel<19>",
-                "note": "frac > 1 is real: the roofline unit is SURVEY 8d's 2 integer-pipe lane-ops per cell (4 per s16x2 "
-                        "cell pair); this kernel needs 2.5 per cell pair (one add runs as IMAD on the FMA pipe)", "achieved": round(fill_gcups, 1),
+                "note": "frac uses SURVEY 8d's unit (2 integer-pipe lane-ops per cell) and exceeds 1 because the kernel needs "
+                        "2.16 DPX ops per s16x2 cell PAIR; frac_alu_bound is the honest ceiling of this kernel design "
+                        "(2 DPX ops per cell pair, 64 lane-ops/clk/SM)",
+                "achieved": round(fill_gcups, 1),
                 "peak": round(peak_gcups, 1), "unit": "GCUPS", "frac": round(fill_gcups / peak_gcups, 4),
+                "frac_alu_bound": round(fill_gcups / alu_bound_gcups, 4), "alu_bound_peak": round(alu_bound_gcups, 1),
                 "peak_def": f"{sms} SMs x {sm_max:.0f} MHz ({peak_kind} sm_max_mhz) x 64 int lane-ops/clk/SM "
                             "(measured: profiles/dpx_microbench_r01.json) / 2 ops per s16x2 cell",
                 "frac_at_run_clock": round(fill_gcups / (peak_gcups * run_clock / sm_max), 4),
-                "traffic": traffic,
+                "traffic": traffic, "traffic_source": traffic_src,
                 "hbm": {"algorithmic_bytes_per_launch": agg["checkpoint_bytes"] / max(agg["batches"], 1),
                         "achieved_gbs": round(agg["checkpoint_bytes"] / 1e9 / (agg["fill_ms"] * 1e-3), 1)
                         if agg["fill_ms"] > 0 else 0.0,
@@ -377,6 +415,9 @@ def main():
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(e2e_ms, 3),
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(agg["launches"]), "max_cells_per_step": int(agg["max_cells"] / K)}
+    if world > 1:
+        line["collective"] = {"impl": "libswb200 swb_comm_allgather_best: ncclAllGather + merge kernel on the engine stream",
+                              "bytes_per_rank_per_step": 16 * B, "merged_equals_independent_reduction": merge_ok}
     if not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_leg(all_refs, reads_pool, os.cpu_count() or 1)

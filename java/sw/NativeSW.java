@@ -1,92 +1,89 @@
 package sw ;
 
-import java.lang.foreign.Arena ;
-import java.lang.foreign.FunctionDescriptor ;
-import java.lang.foreign.Linker ;
-import java.lang.foreign.MemorySegment ;
-import java.lang.foreign.SymbolLookup ;
-import java.lang.invoke.MethodHandle ;
 import java.nio.charset.StandardCharsets ;
-
-import static java.lang.foreign.ValueLayout.ADDRESS ;
-import static java.lang.foreign.ValueLayout.JAVA_BYTE ;
-import static java.lang.foreign.ValueLayout.JAVA_INT ;
-import static java.lang.foreign.ValueLayout.JAVA_LONG ;
+import java.util.List ;
 
 /**
- * Panama FFM (JDK 22+) binding of libswb200.so -- the C ABI declared in include/swb200.h.
- * NOT COMPILED OR RUN in the build environment (no JDK there); it shows the exact binding a
- * maintainer adds.  One process-wide context on CUDA device 0 (or -Dswb.device=N).
+ * JNI binding of libswb200 for the reference's own runtime (Java 1.8 / Spark 1.5.2, pom.xml:17-32):
+ * {@code System.loadLibrary("swbjni")} loads jni/swb_jni.c, which forwards every method below to the
+ * C ABI of include/swb200.h.  Handles are opaque {@code long}s; sequences cross as Latin-1 bytes plus
+ * {@code long[] offsets} (n + 1 entries); a native failure surfaces as an unchecked RuntimeException
+ * carrying swb_last_error(), because Function3.call declares no checked exception
+ * (reference SmithWaterman.java:62).
  *
- * Errors: every native call returns 0 or a negative code; this class turns a non-zero
- * code into an unchecked RuntimeException carrying swb_last_error(), because
- * Function3.call declares no checked exception (reference SmithWaterman.java:62).
+ * NOT COMPILED OR RUN in the build environment (no JDK there).  tests/test_abi_and_host.py checks that
+ * every {@code static native} method below has a {@code Java_sw_NativeSW_*} export with the same argument
+ * count in the compiled shim.  A Panama FFM (JDK 22+) binding of the same ABI is under java/ffm/.
  */
 final class NativeSW
 {
-	static final Linker LINKER = Linker.nativeLinker() ;
-	static final Arena ARENA = Arena.global() ;
-	static final SymbolLookup LIB = SymbolLookup.libraryLookup(
-			System.getProperty( "swb.library" , "libswb200.so" ) , ARENA ) ;
+	static { System.loadLibrary( System.getProperty( "swb.jni" , "swbjni" ) ) ; }
 
-	static MethodHandle h( String name , FunctionDescriptor fd )
+	private NativeSW() {}
+
+	// ---- context ------------------------------------------------------------------------
+	static native String lastError() ;
+	static native int deviceCount() ;
+	static native long create( int device , long workspaceBytes ) ;
+	static native void destroy( long ctx ) ;
+
+	// ---- reference set (HBM-resident, 2-bit packed) ----------------------------------------
+	static native long refsetLoad( long ctx , byte[] bytes , long[] offsets ) ;
+	static native void refsetFree( long refset ) ;
+
+	// ---- align all reads x all references of the set --------------------------------------
+	static native long align( long ctx , long refset , byte[] readBytes , long[] readOffsets , int match , int mismatch , int gap , int flags ) ;
+	static native void resultFree( long result ) ;
+
+	// ---- result arrays ---------------------------------------------------------------------
+	static native int[] scores( long result ) ;
+	static native int[] refTotals( long result ) ;
+	static native int[] bestHits( long result ) ;
+	static native long[] cellOffsets( long result ) ;
+	static native int[] cells( long result ) ;
+	static native int[] beginnings( long result ) ;
+	static native int[] opLens( long result ) ;
+	static native long pairCellCount( long result , long pair ) ;
+	static native int[] pairCell( long result , long pair , long k ) ;
+	static native byte[][] materialize( long result , long cell , int opLen , byte[] ref , byte[] read ) ;
+
+	// ---- multi-GPU (one JVM, several devices) -----------------------------------------------
+	static native long multiCreate( int[] devices , long workspaceBytes ) ;
+	static native void multiDestroy( long multi ) ;
+	static native void multiRefsetLoad( long multi , byte[] bytes , long[] offsets ) ;
+	static native long[] multiShardRefs( long multi , int shard ) ;
+	static native long multiAlign( long multi , byte[] readBytes , long[] readOffsets , int match , int mismatch , int gap , int flags ) ;
+	static native long multiShard( long multiResult , int shard ) ;
+	static native int[] multiBestHits( long multiResult , int nReads ) ;
+	static native void multiResultFree( long multiResult ) ;
+
+	static final int F_SCORES_ONLY = 1 , F_NO_FETCH = 2 , F_TIE_GT = 4 ;
+
+	/** process-wide engine context on CUDA device -Dswb.device (default 0); thread-safe on the native side */
+	private static long ctx = 0 ;
+	static synchronized long context()
 	{
-		return LINKER.downcallHandle( LIB.find(name).orElseThrow() , fd ) ;
-	}
-
-	static final MethodHandle LAST_ERROR  = h( "swb_last_error" , FunctionDescriptor.of(ADDRESS) ) ;
-	static final MethodHandle CREATE      = h( "swb_create" , FunctionDescriptor.of(JAVA_INT, JAVA_INT, JAVA_LONG, ADDRESS) ) ;
-	static final MethodHandle REFSET_LOAD = h( "swb_refset_load" , FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS) ) ;
-	static final MethodHandle REFSET_FREE = h( "swb_refset_free" , FunctionDescriptor.ofVoid(ADDRESS) ) ;
-	static final MethodHandle ALIGN       = h( "swb_align" , FunctionDescriptor.of(JAVA_INT, ADDRESS, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_INT, JAVA_INT, JAVA_INT, JAVA_INT, ADDRESS) ) ;
-	static final MethodHandle RESULT_FREE = h( "swb_result_free" , FunctionDescriptor.ofVoid(ADDRESS) ) ;
-	static final MethodHandle SCORES      = h( "swb_result_scores" , FunctionDescriptor.of(ADDRESS, ADDRESS) ) ;
-	static final MethodHandle REF_TOTALS  = h( "swb_result_ref_totals" , FunctionDescriptor.of(ADDRESS, ADDRESS) ) ;
-	static final MethodHandle CELL_OFFS   = h( "swb_result_cell_offsets" , FunctionDescriptor.of(ADDRESS, ADDRESS) ) ;
-	static final MethodHandle CELL_COUNT  = h( "swb_result_pair_cell_count" , FunctionDescriptor.of(JAVA_LONG, ADDRESS, JAVA_LONG) ) ;
-	static final MethodHandle PAIR_CELL   = h( "swb_result_pair_cell" , FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS) ) ;
-	static final MethodHandle MATERIALIZE = h( "swb_result_materialize" , FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, JAVA_LONG) ) ;
-
-	/** process-wide engine context (thread-safe on the native side) */
-	static final MemorySegment CTX = create() ;
-
-	private static MemorySegment create()
-	{
-		try( Arena a = Arena.ofConfined() )
+		if( ctx == 0 )
 		{
-			MemorySegment out = a.allocate( ADDRESS ) ;
-			check( (int) CREATE.invokeExact( Integer.getInteger("swb.device",0).intValue() , 0L , out ) ) ;
-			return out.get( ADDRESS , 0 ) ;
+			ctx = create( Integer.getInteger( "swb.device" , 0 ).intValue() , Long.getLong( "swb.workspace" , 0L ).longValue() ) ;
+			Runtime.getRuntime().addShutdownHook( new Thread() { public void run() { destroy( ctx ) ; } } ) ;
 		}
-		catch( RuntimeException e ) { throw e ; }
-		catch( Throwable t ) { throw new RuntimeException( t ) ; }
+		return ctx ;
 	}
 
-	static void check( int rc )
-	{
-		if( rc == 0 ) return ;
-		String msg ;
-		try { msg = ((MemorySegment) LAST_ERROR.invokeExact()).reinterpret(4096).getString(0) ; }
-		catch( Throwable t ) { msg = "?" ; }
-		throw new RuntimeException( "libswb200 error " + rc + ": " + msg ) ;
-	}
-
-	/** sequences -> (concatenated Latin-1 bytes, int64 offsets[n+1]) in native memory */
-	static MemorySegment[] pack( Arena a , java.util.List<String> seqs )
+	/** sequences -> concatenated Latin-1 bytes; offsets[k] .. offsets[k+1] delimit sequence k */
+	static byte[] pack( List<String> seqs , long[] offsets )
 	{
 		long total = 0 ;
-		for( String s : seqs ) total += s.length() ;
-		MemorySegment bytes = a.allocate( Math.max(total,1) ) ;
-		MemorySegment offs = a.allocate( JAVA_LONG , seqs.size() + 1L ) ;
-		long p = 0 ;
+		for( int k = 0 ; k < seqs.size() ; k++ ) { offsets[k] = total ; total += seqs.get(k).length() ; }
+		offsets[seqs.size()] = total ;
+		if( total > Integer.MAX_VALUE - 8 ) throw new RuntimeException( "sequence batch exceeds a Java array: split the call" ) ;
+		byte[] bytes = new byte[(int) total] ;
 		for( int k = 0 ; k < seqs.size() ; k++ )
 		{
-			offs.setAtIndex( JAVA_LONG , k , p ) ;
 			byte[] b = seqs.get(k).getBytes( StandardCharsets.ISO_8859_1 ) ;
-			MemorySegment.copy( b , 0 , bytes , JAVA_BYTE , p , b.length ) ;
-			p += b.length ;
+			System.arraycopy( b , 0 , bytes , (int) offsets[k] , b.length ) ;
 		}
-		offs.setAtIndex( JAVA_LONG , seqs.size() , p ) ;
-		return new MemorySegment[]{ bytes , offs } ;
+		return bytes ;
 	}
 }

@@ -4,25 +4,21 @@ import org.apache.spark.api.java.function.Function3 ;
 
 import scala.Tuple2 ;
 
-import java.lang.foreign.Arena ;
-import java.lang.foreign.MemorySegment ;
+import java.nio.charset.StandardCharsets ;
 import java.util.ArrayList ;
 import java.util.Collections ;
 import java.util.List ;
 
-import static java.lang.foreign.ValueLayout.ADDRESS ;
-import static java.lang.foreign.ValueLayout.JAVA_INT ;
-import static java.lang.foreign.ValueLayout.JAVA_LONG ;
-
 /**
- * Drop-in host layer for the reference's sw.SmithWaterman: same package, class, nested
- * public class and method signature; the body marshals to libswb200 (sm_100a CUDA) and
- * unmarshals the result into the reference's object graph.  Written fresh against
- * include/swb200.h; NOT COMPILED in the build environment (no JDK there).
+ * Drop-in host layer for the reference's sw.SmithWaterman (Java 1.8): same package, class, nested public
+ * class and method signature (reference SmithWaterman.java:35, 62); the body marshals to libswb200
+ * (hand-written sm_100a CUDA) through the JNI shim and rebuilds the reference's object graph
+ * {@code Tuple2<maxScore, ArrayList<Tuple2<beginning, {refAln, readAln}>>>} (SmithWaterman.java:91).
+ * Written fresh against include/swb200.h; NOT COMPILED in the build environment (no JDK there).
  *
- * Per-pair calls work but pay one native round trip each; the throughput path is
- * {@link #alignAll}, which a MapRef / DistributeReference integration calls once per
- * reference file (INTEGRATION.md).
+ * Per-pair calls are legal but pay one native round trip each; the throughput path is
+ * {@link #alignAll}, which the batched MapRef of java/sw/Distribution.java calls once per
+ * reference file (all references x all reads in one launch sequence).
  */
 @SuppressWarnings( "serial" )
 public class SmithWaterman
@@ -33,67 +29,57 @@ public class SmithWaterman
 		@Override
 		public Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>> call( String[] seqs , int[] alignScores , char[] alignTypes )
 		{
-			return alignAll( Collections.singletonList(seqs[0]) , Collections.singletonList(seqs[1]) , alignScores ).get(0).get(0) ;
+			return alignAll( Collections.singletonList(seqs[0]) , Collections.singletonList(seqs[1]) , alignScores , 0 ).get(0).get(0) ;
 		}
 	}
 
 	/** result.get(ref).get(read) = what OptAlignments.call returns for that pair. */
-	public static List<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>> alignAll( List<String> refs , List<String> reads , int[] alignScores )
+	public static List<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>> alignAll( List<String> refs , List<String> reads , int[] alignScores , int flags )
 	{
-		try( Arena a = Arena.ofConfined() )
+		long ctx = NativeSW.context() ;
+		long[] refOff = new long[refs.size() + 1] , readOff = new long[reads.size() + 1] ;
+		byte[] refBytes = NativeSW.pack( refs , refOff ) ;
+		byte[] readBytes = NativeSW.pack( reads , readOff ) ;
+		long refset = NativeSW.refsetLoad( ctx , refBytes , refOff ) ;
+		try
 		{
-			MemorySegment[] r = NativeSW.pack( a , refs ) ;
-			MemorySegment[] q = NativeSW.pack( a , reads ) ;
-			MemorySegment out = a.allocate( ADDRESS ) ;
-			NativeSW.check( (int) NativeSW.REFSET_LOAD.invokeExact( NativeSW.CTX , (long) refs.size() , r[0] , r[1] , out ) ) ;
-			MemorySegment refset = out.get( ADDRESS , 0 ) ;
-			try
-			{
-				NativeSW.check( (int) NativeSW.ALIGN.invokeExact( NativeSW.CTX , refset , (long) reads.size() , q[0] , q[1] ,
-						alignScores[0] , alignScores[1] , alignScores[2] , 0 , out ) ) ;
-				MemorySegment res = out.get( ADDRESS , 0 ) ;
-				try { return unmarshal( a , res , refs , reads ) ; }
-				finally { NativeSW.RESULT_FREE.invokeExact( res ) ; }
-			}
-			finally { NativeSW.REFSET_FREE.invokeExact( refset ) ; }
+			long res = NativeSW.align( ctx , refset , readBytes , readOff , alignScores[0] , alignScores[1] , alignScores[2] , flags ) ;
+			try { return unmarshal( res , refs , reads ) ; }
+			finally { NativeSW.resultFree( res ) ; }
 		}
-		catch( RuntimeException e ) { throw e ; }
-		catch( Throwable t ) { throw new RuntimeException( t ) ; }
+		finally { NativeSW.refsetFree( refset ) ; }
 	}
 
-	private static List<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>> unmarshal( Arena a , MemorySegment res , List<String> refs , List<String> reads ) throws Throwable
+	/** flat result arrays -> the reference's nested tuples; max cells in the reference's list order */
+	static List<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>> unmarshal( long res , List<String> refs , List<String> reads )
 	{
-		long nReads = reads.size() ;
-		MemorySegment scores = ((MemorySegment) NativeSW.SCORES.invokeExact( res )).reinterpret( 4L * refs.size() * nReads ) ;
-		MemorySegment offs = ((MemorySegment) NativeSW.CELL_OFFS.invokeExact( res )).reinterpret( 8L * (refs.size() * nReads + 1) ) ;
-		MemorySegment pi = a.allocate( JAVA_INT ) , pj = a.allocate( JAVA_INT ) , pb = a.allocate( JAVA_INT ) , pl = a.allocate( JAVA_INT ) ;
-		List<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>> all = new ArrayList<>( refs.size() ) ;
-		for( int ref = 0 ; ref < refs.size() ; ref++ )
+		int nReads = reads.size() ;
+		int[] scores = NativeSW.scores( res ) ;
+		long[] offs = NativeSW.cellOffsets( res ) ;
+		int[] cells = NativeSW.cells( res ) , begs = NativeSW.beginnings( res ) , lens = NativeSW.opLens( res ) ;
+		List<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>> all = new ArrayList<List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>>( refs.size() ) ;
+		byte[][] readBytes = new byte[nReads][] ;
+		for( int q = 0 ; q < nReads ; q++ ) readBytes[q] = reads.get(q).getBytes( StandardCharsets.ISO_8859_1 ) ;
+		for( int r = 0 ; r < refs.size() ; r++ )
 		{
-			List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>> row = new ArrayList<>( reads.size() ) ;
-			MemorySegment refBytes = a.allocateFrom( refs.get(ref) , java.nio.charset.StandardCharsets.ISO_8859_1 ) ;
-			for( int rd = 0 ; rd < reads.size() ; rd++ )
+			byte[] refBytes = refs.get(r).getBytes( StandardCharsets.ISO_8859_1 ) ;
+			List<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>> row = new ArrayList<Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>>( nReads ) ;
+			for( int q = 0 ; q < nReads ; q++ )
 			{
-				long pair = ref * nReads + rd ;
-				int score = scores.getAtIndex( JAVA_INT , pair ) ;
-				long count = (long) NativeSW.CELL_COUNT.invokeExact( res , pair ) ;      // m*n when score == 0
-				long base = offs.getAtIndex( JAVA_LONG , pair ) ;
-				ArrayList<Tuple2<Integer,String[]>> opt = new ArrayList<>( (int) count ) ;
-				MemorySegment readBytes = a.allocateFrom( reads.get(rd) , java.nio.charset.StandardCharsets.ISO_8859_1 ) ;
-				for( long k = 0 ; k < count ; k++ )
+				int pair = r * nReads + q ;
+				int score = scores[pair] ;
+				ArrayList<Tuple2<Integer,String[]>> opt = new ArrayList<Tuple2<Integer,String[]>>() ;
+				if( score == 0 )
 				{
-					NativeSW.check( (int) NativeSW.PAIR_CELL.invokeExact( res , pair , k , pi , pj , pb , pl ) ) ;
-					int len = pl.get( JAVA_INT , 0 ) ;
-					String[] aligned = { "" , "" } ;
-					if( score != 0 )
-					{
-						MemorySegment ra = a.allocate( len + 1L ) , qa = a.allocate( len + 1L ) ;
-						NativeSW.check( (int) NativeSW.MATERIALIZE.invokeExact( res , base + k , refBytes , (long) refs.get(ref).length() ,
-								readBytes , (long) reads.get(rd).length() , ra , qa , len + 1L ) ) ;
-						aligned[0] = ra.getString( 0 , java.nio.charset.StandardCharsets.ISO_8859_1 ) ;
-						aligned[1] = qa.getString( 0 , java.nio.charset.StandardCharsets.ISO_8859_1 ) ;
-					}
-					opt.add( new Tuple2<Integer,String[]>( pb.get(JAVA_INT,0) , aligned ) ) ;
+					// every cell ties at 0: m*n entries with beginning 0 and empty strings (SmithWaterman.java:180-185, :380)
+					long count = NativeSW.pairCellCount( res , pair ) ;
+					for( long k = 0 ; k < count ; k++ ) opt.add( new Tuple2<Integer,String[]>( 0 , new String[]{ "" , "" } ) ) ;
+				}
+				else for( long c = offs[pair] ; c < offs[pair + 1] ; c++ )
+				{
+					byte[][] aln = NativeSW.materialize( res , c , lens[(int) c] , refBytes , readBytes[q] ) ;
+					String[] strs = { new String( aln[0] , StandardCharsets.ISO_8859_1 ) , new String( aln[1] , StandardCharsets.ISO_8859_1 ) } ;
+					opt.add( new Tuple2<Integer,String[]>( begs[(int) c] , strs ) ) ;
 				}
 				row.add( new Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>>( score , opt ) ) ;
 			}

@@ -55,6 +55,27 @@ SIGNATURES = {
     "swb_result_device_ptr": (C.c_int, [_P, C.c_int, C.POINTER(_P), _I64P]),
     "swb_get_stream": (C.c_int, [_P, C.POINTER(_P)]),
     "swb_microbench_json": (C.c_int, [C.c_int, C.c_int, C.c_char_p, C.c_int]),
+    # multi-GPU (single process, n devices)
+    "swb_multi_create": (C.c_int, [_I32P, C.c_int32, C.c_int64, C.POINTER(_P)]),
+    "swb_multi_destroy": (None, [_P]),
+    "swb_multi_device_count": (C.c_int32, [_P]),
+    "swb_multi_ctx": (_P, [_P, C.c_int32]),
+    "swb_multi_refset_load": (C.c_int, [_P, C.c_int64, C.c_char_p, _I64P]),
+    "swb_multi_ref_count": (C.c_int64, [_P]),
+    "swb_multi_ref_location": (C.c_int, [_P, C.c_int64, _I32P, _I64P]),
+    "swb_multi_shard_refs": (_I64P, [_P, C.c_int32, _I64P]),
+    "swb_multi_align": (C.c_int, [_P, C.c_int64, C.c_char_p, _I64P, C.c_int32, C.c_int32, C.c_int32, C.c_uint32,
+                                  C.POINTER(_P)]),
+    "swb_multi_result_free": (None, [_P]),
+    "swb_multi_result_shard": (_P, [_P, C.c_int32]),
+    "swb_multi_result_best_hits": (_I32P, [_P]),
+    "swb_multi_result_stats": (C.c_int, [_P, C.POINTER(C.c_double), C.c_int]),
+    # multi-GPU (one process per device)
+    "swb_comm_unique_id": (C.c_int, [C.c_char_p]),
+    "swb_comm_create": (C.c_int, [_P, C.c_char_p, C.c_int32, C.c_int32, C.POINTER(_P)]),
+    "swb_comm_destroy": (None, [_P]),
+    "swb_comm_allgather_best": (C.c_int, [_P, _P, _I64P, C.c_int64, _I32P]),
+    "swb_comm_merged_device_ptr": (C.c_int, [_P, C.POINTER(_P), _I64P]),
 }
 
 _lib = None

@@ -17,7 +17,7 @@ BIN_DIR = os.path.join(HERE, "_bin")
 LIB = os.path.join(LIB_DIR, "libswb200.so")
 MICROBENCH = os.path.join(BIN_DIR, "dpx_microbench")
 
-SOURCES = ["swb_api.cu", "swb_fill.cu", "swb_fill_bias.cu", "swb_trace.cu", "swb_trace_tile.cu", "swb_wide.cu", "swb_wide_host.cu", "swb_assemble.cu", "dpx_microbench.cu"]
+SOURCES = ["swb_api.cu", "swb_fill.cu", "swb_fill_bias.cu", "swb_trace.cu", "swb_trace_tile.cu", "swb_wide.cu", "swb_wide_host.cu", "swb_multi.cu", "swb_assemble.cu", "dpx_microbench.cu"]
 HEADERS = ["swb_internal.h", "swb_device.cuh", "swb_host.h", os.path.join("..", "..", "include", "swb200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
@@ -48,7 +48,7 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
         for cmd, p in procs:
             if p.wait() != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
-        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
+        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs + ["-ldl"]
         subprocess.check_call(cmd)
     if force or not _newer(MICROBENCH, [os.path.join(CSRC, "dpx_microbench.cu")]):
         subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DSWB_MICROBENCH_MAIN", "-o", MICROBENCH,

@@ -80,6 +80,7 @@ struct swb_ctx {
     DevBuf<int32_t> w_brow, w_rec, w_tmx, w_prog, w_pair_ref, w_pair_read, w_wreads;
     DevBuf<uint8_t> w_rpad;                     // wide reads, aligned + padded (0xFE) to whole bands
     DevBuf<int64_t> w_rpad_off, w_rpad_len;
+    DevBuf<unsigned long long> w_dbg;
     DevBuf<int64_t> w_band_off, w_blk_off, w_brow_off;
     DevBuf<int2> w_items;
     DevBuf<WideTask> w_tasks;

@@ -148,11 +148,11 @@ struct WideParams {
     const int64_t *band_off;     // [n_pairs + 1] prefix of bands
     const int64_t *blk_off;      // [n_pairs + 1] prefix of bands * blocks
     const int64_t *brow_off;     // [n_pairs + 1] prefix of bands * blocks * 32 (steps)
-    int32_t *brow;               // per band: lane 31's bottom row, indexed by step
+    int32_t *brow;               // per band: lane 31's bottom row, indexed by step; -1 = not written yet (host memset)
     int32_t *rec;                // block records [bands * blocks][32 lanes][RW]
     int32_t *tmx;                // tile maxima   [bands * blocks][32 lanes]
-    int32_t *prog;               // per band: steps completed (release / acquire)
     int32_t *scores;
+    unsigned long long *dbg;     // optional counters (SWB_WIDE_DEBUG): [0] traceback rounds, [1] tiles walked, [2] tiles recomputed
 };
 
 // one batch of max cells as the assembly kernels see it (swb_assemble.cu)

@@ -39,12 +39,19 @@ namespace {
 
 constexpr int PAD_NEG = -(1 << 29);          // profile score of a row beyond the read's end (gap < 0: stays below every real cell)
 
-__device__ __forceinline__ void st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ int ld_acquire(const int32_t *p)
+// Band-to-band hand-off without fences: every word of a band's bottom row (brow) validates itself.  The host
+// fills brow with -1, scores are never negative, so a consumer that reads a value >= 0 has the producer's value
+// (relaxed, GPU-scope accesses of single 32-bit words: no ordering between different words is needed).
+__device__ __forceinline__ int ld_relaxed(const int32_t *p)
 {
     int v;
-    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+__device__ __forceinline__ void st_relaxed(int32_t *p, int v) { asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ void st_relaxed4(int32_t *p, int a, int b, int c, int d)
+{
+    asm volatile("st.relaxed.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 struct WCtx {
@@ -142,11 +149,15 @@ wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *t
         const int nchunks = (nsteps + WCB - 1) / WCB;
         int32_t *my_brow = C.brow + (int64_t)band * (C.n_blocks * WCB);
         const int32_t *up_brow = my_brow - (int64_t)C.n_blocks * WCB;
-        const int32_t *prog_up = band > 0 ? P.prog + P.band_off[pair] + band - 1 : nullptr;
-        int32_t *prog_me = P.prog + P.band_off[pair] + band;
+        const bool feeds_below = (int64_t)(band + 1) * G::BH < C.m;       // another band reads this band's bottom row
         int32_t *recp = C.rec + (((int64_t)band * C.n_blocks) * WL + lane) * G::RW;     // record of block 0
         int32_t *tmxp = C.tmx + ((int64_t)band * C.n_blocks) * WL + lane;
-        int seen = 0;                                             // steps of the band above known complete
+        // bottom row of the band above for lane 0: lane L holds column s0 + 1 + L = step s0 + 31 + L up there;
+        // requested one chunk ahead (the words validate themselves), re-polled while any is still -1
+        auto fetch_top = [&](int s0) -> int {
+            return (band > 0 && s0 + 1 + lane <= C.n) ? ld_relaxed(up_brow + s0 + WL - 1 + lane) : 0;
+        };
+        int tnext = fetch_top(0);
 
         // reference codes of a chunk: bytes s0-32 .. s0+31 (0-based columns) -> lane L fetches bytes L and L+32
         auto fetch_codes = [&](int s0, int &c_lo, int &c_hi) {
@@ -161,20 +172,14 @@ wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *t
             const int s0 = ch * WCB;
             int32_t *stg = stage + (ch & 1) * (WL + 16);
             uint8_t *stg_codes = reinterpret_cast<uint8_t *>(stg + WL);
-            // ---- top boundary of lane 0: bottom row of the band above (column s0 + 1 + L = step s0 + 31 + L there)
-            int tval = 0;
+            // ---- top boundary of lane 0
+            int tval = tnext;
             if (band > 0) {
-                const int need = min(C.n, s0 + WCB) + WL - 1;    // steps the band above must have finished
-                if (seen < need) {
-                    if (lane == 0) {
-                        int v = ld_acquire(prog_up);
-                        while (v < need) { __nanosleep(64); v = ld_acquire(prog_up); }
-                        seen = v;
-                    }
-                    seen = __shfl_sync(0xffffffffu, seen, 0);
-                    __syncwarp();                                 // orders the other lanes' loads after lane 0's acquire
+                while (__any_sync(0xffffffffu, tval < 0)) {
+                    __nanosleep(100);
+                    if (tval < 0) tval = ld_relaxed(up_brow + s0 + WL - 1 + lane);
                 }
-                if (s0 + 1 + lane <= C.n) tval = __ldcg(up_brow + s0 + WL - 1 + lane);
+                if (ch + 1 < nchunks) tnext = fetch_top(s0 + WCB);
             }
             stg[lane] = tval;
             stg_codes[lane] = (uint8_t)c_lo;
@@ -220,7 +225,7 @@ wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *t
                         sm[e] = top; bw[e] = H[KL - 1];
                     }
                     *reinterpret_cast<int4 *>(seam + 4 * q) = make_int4(sm[0], sm[1], sm[2], sm[3]);
-                    if (lane == WL - 1) *reinterpret_cast<int4 *>(my_brow + s0 + 4 * q) = make_int4(bw[0], bw[1], bw[2], bw[3]);
+                    if (feeds_below && lane == WL - 1) st_relaxed4(my_brow + s0 + 4 * q, bw[0], bw[1], bw[2], bw[3]);
                 }
             } else {
 #pragma unroll 1
@@ -263,7 +268,7 @@ wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *t
                     }
                     diag = top;
                     seam[u] = top;
-                    if (lane == WL - 1) my_brow[s0 + u] = H[KL - 1];
+                    if (feeds_below && lane == WL - 1) st_relaxed(my_brow + s0 + u, H[KL - 1]);
                 }
             }
             // ---- block boundary: tile maximum, next block's checkpoint, progress
@@ -283,7 +288,6 @@ wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *t
                     *reinterpret_cast<int4 *>(recp + 4 * q) = make_int4(v[0], v[1], v[2], v[3]);
                 }
             }
-            if (lane == WL - 1) st_release(prog_me, ch + 1 < nchunks ? s0 + WCB : 0x7fffffff);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) bmax = max(bmax, __shfl_xor_sync(0xffffffffu, bmax, o));
@@ -367,23 +371,33 @@ struct WTile {
         j0 = blk * WCB - t + 1;                                   // column of step u = j0 + u
     }
 
-    // fn(u, top, H, real, j) after every step; the column is computed when it is inside the matrix
+    // fn(u, top, H, code) after every step (code = 0xFD outside the matrix); the column is computed when it is
+    // inside the matrix.  The seam quad and the reference codes of the next four steps are requested one quad ahead.
     template <class Fn>
     __device__ __forceinline__ void run(const WCtx &C, Fn &&fn)
     {
         const int gap = C.gap, match = C.match, mismatch = C.mismatch;
         const int4 *sq = reinterpret_cast<const int4 *>(rec + WGeo<KL>::KW);
-#pragma unroll 1
-        for (int q = 0; q < WCB / 4; ++q) {
-            const int4 a = __ldg(sq + q);
-            const int tq[4] = {a.x, a.y, a.z, a.w};
+        auto codes4 = [&](int q, int (&cc)[4]) {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                const int u = 4 * q + e, j = j0 + u;
-                const int top = tq[e];
-                const bool real = (j >= 1) && (j <= C.n);
-                if (real) {
-                    const int c = (int)__ldg(C.ref + j - 1);
+                const int j = j0 + 4 * q + e;
+                cc[e] = (j >= 1 && j <= C.n) ? (int)__ldg(C.ref + j - 1) : 0xFD;
+            }
+        };
+        int4 a_nxt = __ldg(sq);
+        int c_nxt[4];
+        codes4(0, c_nxt);
+#pragma unroll 1
+        for (int q = 0; q < WCB / 4; ++q) {
+            const int tq[4] = {a_nxt.x, a_nxt.y, a_nxt.z, a_nxt.w};
+            const int cq[4] = {c_nxt[0], c_nxt[1], c_nxt[2], c_nxt[3]};
+            if (q + 1 < WCB / 4) { a_nxt = __ldg(sq + q + 1); codes4(q + 1, c_nxt); }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int u = 4 * q + e;
+                const int top = tq[e], c = cq[e];
+                if (c != 0xFD) {
                     int nw = diag, nn = top;
 #pragma unroll
                     for (int r = 0; r < KL; ++r) {
@@ -395,7 +409,7 @@ struct WTile {
                         nn = H[r];
                     }
                 }
-                fn(u, top, H, real, j);
+                fn(u, top, H, c);
                 diag = top;
             }
         }
@@ -421,10 +435,8 @@ __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, co
         const int nvalid = min(KL, max(0, C.m - row0));
         WTile<KL> W;
         W.load(C, T.band, t, T.block);
-#pragma unroll
-        for (int r = 0; r < KL; ++r) if (r >= nvalid) W.rc[r] = 0x100 + r;
-        W.run(C, [&](int, int, const int (&Hc)[KL], bool real, int j) {
-            if (!real) return;
+        W.run(C, [&](int u, int, const int (&Hc)[KL], int c) {
+            if (c == 0xFD) return;
             uint32_t rm = 0;
 #pragma unroll
             for (int r = 0; r < KL; ++r) rm |= (Hc[r] == S) ? (1u << r) : 0u;
@@ -433,40 +445,58 @@ __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, co
                 const int r = __ffs((int)rm) - 1;
                 rm &= rm - 1;
                 const uint32_t k = atomicAdd(count, 1u);
-                if (k < cap) keys[k] = wide_key((uint64_t)T.pair, (uint32_t)(row0 + r + 1), (uint32_t)j);
+                if (k < cap) keys[k] = wide_key((uint64_t)T.pair, (uint32_t)(row0 + r + 1), (uint32_t)(W.j0 + u));
             }
         });
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// Traceback.  Tile in shared memory, one per thread, words interleaved over the CTA's threads
-// (word w of thread x at [w * NT + x]): column cc = 0 .. 32 (0 = the checkpointed column), element
-// rr = 0 .. KL (0 = the boundary row above the lane).
+// Traceback.  Every thread owns one tile slot in shared memory (stride TW words, odd: the lanes' slots start in
+// different banks, so the lock-step column stores of a warp are conflict-free):
+//   elements [cc][rr], cc = 0 .. 32 (0 = the checkpointed column), rr = 0 .. KL (0 = the boundary row above the
+//   lane), then the lane-row's KL read codes and the reference codes of the tile's 32 steps.
+// A step up / left / diagonal in the matrix is a constant pointer decrement inside the slot.
 // BYTE: only the low 8 bits of every score are kept.  That is enough because the walker carries the exact score
 // of its cell (the pair maximum minus the moves so far) and a candidate never lies 250 or more below H
 // (tile_trace_ok): equality of the low bytes is equality.  Other score sets use int32 tiles.
+// The walker checks up to four diagonal moves per iteration ('>=' rule: an alignment move wins whenever
+// NW + s == H): all their loads are independent, so a run of matches costs one shared-memory latency per four
+// columns instead of one per column.
+template <int KL, bool BYTE> struct TraceGeo {
+    static constexpr int ES = BYTE ? 1 : 4;                         // bytes per element
+    static constexpr int ROWW = BYTE ? (KL + 1 + 3) / 4 : KL + 1;   // words per tile column
+    static constexpr int COLB = ROWW * 4;                           // bytes per tile column
+    static constexpr int CODE0 = ROWW * (WCB + 1);                  // first code word
+    static constexpr int TW = (CODE0 + KL / 4 + WCB / 4) | 1;       // slot stride in words (odd)
+    static constexpr int GUARD = 4 * (COLB + ES) / 4 + 4;           // words before slot 0: the diagonal look-ahead may reach below a slot
+    static size_t smem_bytes(int nt) { return ((size_t)nt + GUARD + (size_t)nt * TW) * 4; }
+};
+
 template <int KL, int NT, int G, bool BYTE>
 __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, const uint64_t *keys, uint32_t n_cells,
                                                          int32_t *beginnings, int32_t *op_lens, uint32_t *ops,
                                                          int64_t ops_stride)
 {
-    constexpr int ROWE = KL + 1;
-    constexpr int ROWW = BYTE ? (ROWE + 3) / 4 : ROWE;             // words per tile column
-    constexpr int TILE_WORDS = ROWW * (WCB + 1);
+    using TG = TraceGeo<KL, BYTE>;
+    constexpr int ES = TG::ES, ROWW = TG::ROWW, COLB = TG::COLB, TW = TG::TW;
+    constexpr int DG = COLB + ES;                                   // one diagonal step, in bytes
     constexpr int HS = G / 2 > 0 ? G / 2 : 1;                      // lane-rows a corridor covers
     extern __shared__ uint32_t tsm[];
-    int32_t *slot_blk = reinterpret_cast<int32_t *>(tsm + (size_t)TILE_WORDS * NT);     // [NT] block of the tile in each thread's slot
-    uint32_t *mytile = tsm + threadIdx.x;
+    int32_t *slot_blk = reinterpret_cast<int32_t *>(tsm);           // [NT] block of the tile in each thread's slot
+    uint32_t *slots = tsm + NT + TG::GUARD;
+    uint32_t *mytile = slots + (size_t)threadIdx.x * TW;
     const int gl = threadIdx.x % G;                                // lane in group
     const int leader = threadIdx.x - gl;
     const unsigned gmask = 0xffffffffu;
     const uint32_t n_groups = gridDim.x * (NT / G);
     const uint32_t gid = (blockIdx.x * NT + threadIdx.x) / G;
     const int gap = P.gap, match = P.match, mismatch = P.mismatch;
+    const bool tie_gt = P.tie_gt != 0;
+    constexpr int M = BYTE ? 0xff : -1;
 
     auto store_col = [&](int cc, int top, const int (&Hc)[KL]) {
-        uint32_t *col = mytile + (size_t)cc * ROWW * NT;
+        uint32_t *col = mytile + cc * ROWW;
         if (BYTE) {
 #pragma unroll
             for (int w = 0; w < ROWW; ++w) {
@@ -476,19 +506,16 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     const int k = 4 * w + e;                       // element k: 0 = boundary row, 1..KL = the lane's rows
                     v[e] = k == 0 ? (uint32_t)top : (k <= KL ? (uint32_t)Hc[(k >= 1 && k <= KL) ? k - 1 : 0] : 0u);
                 }
-                col[w * NT] = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
+                col[w] = __byte_perm(__byte_perm(v[0], v[1], 0x0040), __byte_perm(v[2], v[3], 0x0040), 0x5410);
             }
         } else {
             col[0] = (uint32_t)top;
 #pragma unroll
-            for (int r = 0; r < KL; ++r) col[(r + 1) * NT] = (uint32_t)Hc[r];
+            for (int r = 0; r < KL; ++r) col[r + 1] = (uint32_t)Hc[r];
         }
     };
-    // element (rr, cc) of the tile in thread `slot`'s slot (low byte when BYTE)
-    auto at = [&](int slot, int rr, int cc) -> int {
-        if (BYTE)
-            return (int)reinterpret_cast<const uint8_t *>(tsm)[((size_t)(cc * ROWW + (rr >> 2)) * NT + slot) * 4 + (rr & 3)];
-        return (int)tsm[(size_t)(cc * ROWE + rr) * NT + slot];
+    auto elem = [&](const uint8_t *p) -> int {
+        return BYTE ? (int)*p : *reinterpret_cast<const int32_t *>(p);
     };
 
     for (uint32_t cell = gid; cell < n_cells; cell += n_groups) {            // group-uniform
@@ -520,9 +547,19 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                 WTile<KL> W;
                 W.load(C, Tk / WL, Tk % WL, myblk);
                 store_col(0, W.diag, W.H);
-                W.run(C, [&](int u, int top, const int (&Hc)[KL], bool, int) { store_col(u + 1, top, Hc); });
+                uint32_t *cw = mytile + TG::CODE0;
+#pragma unroll
+                for (int q = 0; q < KL / 4; ++q)
+                    cw[q] = (uint32_t)W.rc[4 * q] | ((uint32_t)W.rc[4 * q + 1] << 8) | ((uint32_t)W.rc[4 * q + 2] << 16) | ((uint32_t)W.rc[4 * q + 3] << 24);
+                uint32_t cacc = 0;
+                W.run(C, [&](int u, int top, const int (&Hc)[KL], int c) {
+                    store_col(u + 1, top, Hc);
+                    cacc |= (uint32_t)c << (8 * (u & 3));
+                    if ((u & 3) == 3) { cw[KL / 4 + (u >> 2)] = cacc; cacc = 0; }
+                });
             }
             slot_blk[threadIdx.x] = myblk;
+            if (P.dbg) { if (gl == 0) atomicAdd(P.dbg, 1ull); if (myblk >= 0) atomicAdd(P.dbg + 2, 1ull); }
             if (G > 1) __syncwarp(gmask);
             if (gl == 0) {
                 // ---- walk (SmithWaterman.java:380-409) through the corridor's tiles
@@ -539,25 +576,52 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     }
                     int r = ci - T * KL;                           // 1..KL
                     int c = step - b * WCB + 1;                    // 1..WCB
-                    const int cbase = cj - c;
-                    while (true) {
-                        const int hn = at(slot, r - 1, c), hw = at(slot, r, c - 1), hnw = at(slot, r - 1, c - 1);
-                        const int sc = (__ldg(C.read + ci - 1) == __ldg(C.ref + cj - 1)) ? match : mismatch;
-                        const int mask = BYTE ? 0xff : -1;
-                        const bool eq_a = ((hnw + sc - hcur) & mask) == 0, eq_i = ((hn + gap - hcur) & mask) == 0,
-                                   eq_d = ((hw + gap - hcur) & mask) == 0;
-                        const uint32_t op = P.tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
-                        beginning = cj;
-                        hcur -= (op == 1u) ? sc : gap;             // exact score of the next cell
-                        const int up = op != 3u, left = op != 2u;
-                        r -= up; ci -= up;
-                        c -= left; cj -= left;
-                        opword |= op << (2 * (int)(oplen & 15));
-                        ++oplen;
-                        if ((oplen & 15) == 0) { myops[(oplen >> 4) - 1] = opword; opword = 0; }
+                    if (P.dbg) atomicAdd(P.dbg + 1, 1ull);
+                    const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
+                    const uint8_t *p = base + c * COLB + r * ES;   // element (r, c)
+                    const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);          // read code of row r
+                    const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);     // reference code of column c
+                    for (;;) {
+                        // everything a diagonal run of four and a single gap move can need; the loads are independent
+                        const int h1 = elem(p - DG), h2 = elem(p - 2 * DG), h3 = elem(p - 3 * DG), h4 = elem(p - 4 * DG);
+                        const int hn = elem(p - ES), hw = elem(p - COLB);
+                        const int s0 = (pr[0] == pq[0]) ? match : mismatch, s1 = (pr[-1] == pq[-1]) ? match : mismatch;
+                        const int s2 = (pr[-2] == pq[-2]) ? match : mismatch, s3 = (pr[-3] == pq[-3]) ? match : mismatch;
+                        const int lim = min(r, c);                 // cells (r - k, c - k), k < lim, lie inside this tile
+                        const int hc1 = hcur - s0, hc2 = hc1 - s1, hc3 = hc2 - s2, hc4 = hc3 - s3;
+                        const bool eq_a = ((h1 + s0 - hcur) & M) == 0;
+                        int L = 0;
+                        if (!tie_gt && eq_a) {
+                            const bool ok1 = lim > 1 && hc1 > 0 && ((h2 + s1 - hc1) & M) == 0;
+                            const bool ok2 = ok1 && lim > 2 && hc2 > 0 && ((h3 + s2 - hc2) & M) == 0;
+                            const bool ok3 = ok2 && lim > 3 && hc3 > 0 && ((h4 + s3 - hc3) & M) == 0;
+                            L = 1 + (int)ok1 + (int)ok2 + (int)ok3;
+                        }
+                        const uint32_t sh = 2u * ((uint32_t)oplen & 15u);
+                        if (L > 0) {
+                            hcur = L == 1 ? hc1 : (L == 2 ? hc2 : (L == 3 ? hc3 : hc4));
+                            beginning = cj - (L - 1);
+                            ci -= L; cj -= L; r -= L; c -= L;
+                            p -= L * DG; pr -= L; pq -= L;
+                            const unsigned long long acc = (unsigned long long)opword | ((unsigned long long)(0x55u >> (8 - 2 * L)) << sh);
+                            oplen += L;
+                            if (sh + 2u * (uint32_t)L >= 32u) { myops[(oplen >> 4) - 1] = (uint32_t)acc; opword = (uint32_t)(acc >> 32); }
+                            else opword = (uint32_t)acc;
+                        } else {
+                            const bool eq_i = ((hn + gap - hcur) & M) == 0, eq_d = ((hw + gap - hcur) & M) == 0;
+                            const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
+                            beginning = cj;
+                            hcur -= (op == 1u) ? s0 : gap;         // exact score of the next cell
+                            const int up = op != 3u, left = op != 2u;
+                            r -= up; ci -= up; pr -= up;
+                            c -= left; cj -= left; pq -= left;
+                            p -= up * ES + left * COLB;
+                            opword |= op << sh;
+                            ++oplen;
+                            if ((oplen & 15) == 0) { myops[(oplen >> 4) - 1] = opword; opword = 0; }
+                        }
                         if (hcur <= 0 || r == 0 || c == 0) break;  // done, or the path left this tile
                     }
-                    (void)cbase;
                     if (hcur <= 0) break;
                 }
             }
@@ -609,8 +673,7 @@ template <int KL, int NT, int G, bool BYTE>
 cudaError_t launch_trace_k(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
                            int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
 {
-    constexpr int ROWW = BYTE ? (KL + 1 + 3) / 4 : KL + 1;
-    const size_t smem = ((size_t)ROWW * (WCB + 1) * NT + NT) * sizeof(uint32_t);
+    const size_t smem = TraceGeo<KL, BYTE>::smem_bytes(NT);
     cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel<KL, NT, G, BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));

@@ -111,7 +111,6 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         CU(ctx->w_brow.reserve((size_t)nblk * WCB, st));
         CU(ctx->w_rec.reserve((size_t)nblk * WL * RW, st));
         CU(ctx->w_tmx.reserve((size_t)nblk * WL, st));
-        CU(ctx->w_prog.reserve((size_t)nbands, st));
         CU(ctx->counters.reserve(16, st));
         CU(cudaMemcpyAsync(ctx->w_pair_ref.p, pr.data() + k0, (size_t)np * 4, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->w_pair_read.p, pq.data() + k0, (size_t)np * 4, cudaMemcpyHostToDevice, st));
@@ -119,7 +118,7 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         CU(cudaMemcpyAsync(ctx->w_blk_off.p, blk_off.data(), blk_off.size() * 8, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->w_brow_off.p, brow_off.data(), brow_off.size() * 8, cudaMemcpyHostToDevice, st));
         CU(cudaMemcpyAsync(ctx->w_items.p, items.data(), items.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
-        CU(cudaMemsetAsync(ctx->w_prog.p, 0, (size_t)nbands * 4, st));
+        if (max_bands > 1) CU(cudaMemsetAsync(ctx->w_brow.p, 0xFF, (size_t)nblk * WCB * 4, st));   // -1: not written yet
 
         WideParams P;
         P.n_pairs = np; P.pair_ref = ctx->w_pair_ref.p; P.pair_read = ctx->w_pair_read.p;
@@ -127,8 +126,15 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         P.rpad = ctx->w_rpad.p; P.rpad_off = ctx->w_rpad_off.p; P.read_off = rd->off.p;
         P.match = match; P.mismatch = mismatch; P.gap = gap; P.n_reads = n_reads; P.n_symbols = rs->n_symbols; P.tie_gt = (flags & SWB_F_TIE_GT) ? 1 : 0;
         P.band_off = ctx->w_band_off.p; P.blk_off = ctx->w_blk_off.p; P.brow_off = ctx->w_brow_off.p;
-        P.brow = ctx->w_brow.p; P.rec = ctx->w_rec.p; P.tmx = ctx->w_tmx.p; P.prog = ctx->w_prog.p;
+        P.brow = ctx->w_brow.p; P.rec = ctx->w_rec.p; P.tmx = ctx->w_tmx.p;
         P.scores = res->d_scores.p;
+        static const bool wide_debug = getenv("SWB_WIDE_DEBUG") != nullptr;
+        P.dbg = nullptr;
+        if (wide_debug) {
+            CU(ctx->w_dbg.reserve(4, st));
+            CU(cudaMemsetAsync(ctx->w_dbg.p, 0, 32, st));
+            P.dbg = ctx->w_dbg.p;
+        }
         uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_ticket = ctx->counters.p + 2;
 
         CU(tic(1));
@@ -183,6 +189,12 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         ++*launches;
         CU(toc());
         CU(cudaStreamSynchronize(st));      // the host tables of this batch are reused by the next one
+        if (P.dbg) {
+            unsigned long long h[4];
+            CU(cudaMemcpy(h, P.dbg, 32, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[swb wide] KL=%d pairs=%d cells=%u: traceback rounds=%llu tiles walked=%llu tiles recomputed=%llu\n",
+                    KL, np, n_cells, h[0], h[1], h[2]);
+        }
         res->stats[8] += n_cells;
         res->batches.push_back(std::move(bo));
         k0 = k1;

@@ -143,15 +143,17 @@ STAT_NAMES = ("h2d_ms", "fill_ms", "locate_ms", "trace_ms", "d2h_ms", "device_ms
 
 
 class AlignResult:
-    def __init__(self, rs: RefSet, reads: List[bytes], h, scores_only: bool):
+    def __init__(self, rs: RefSet, reads: List[bytes], h, scores_only: bool, owned: bool = True):
         self.rs, self.reads, self.h, self.scores_only = rs, reads, h, scores_only
+        self._owned = owned                     # False: a shard of a MultiResult, freed with it
         self.lib = rs.eng.lib
         self.n_refs = int(self.lib.swb_result_n_refs(h))
         self.n_reads = int(self.lib.swb_result_n_reads(h))
 
     def free(self):
         if getattr(self, "h", None):
-            self.lib.swb_result_free(self.h)
+            if self._owned:
+                self.lib.swb_result_free(self.h)
             self.h = None
 
     def __del__(self):

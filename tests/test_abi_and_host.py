@@ -28,7 +28,7 @@ def test_header_symbols_all_exported(lib):
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in swb200.h but not exported"
     assert declared == set(_ffi.SIGNATURES), declared ^ set(_ffi.SIGNATURES)
-    assert lib.swb_abi_version() == 1
+    assert lib.swb_abi_version() == 2
 
 
 def test_product_does_not_touch_the_oracle():
@@ -172,7 +172,7 @@ def test_ctypes_and_java_bindings_match_the_header():
         assert [ckind(a) for a in argtypes] == args, (name, args)
         assert ckind(restype) == ret, (name, ret)
 
-    with open(os.path.join(ROOT, "java", "sw", "NativeSW.java")) as f:
+    with open(os.path.join(ROOT, "java", "ffm", "sw", "NativeSW.java")) as f:
         java = f.read()
     jk = {"JAVA_INT": "int", "JAVA_LONG": "long", "ADDRESS": "ptr"}
     found = 0
@@ -188,3 +188,35 @@ def test_ctypes_and_java_bindings_match_the_header():
         assert kinds == args, (name, kinds, args)
         found += 1
     assert found >= 12
+
+
+def test_jni_shim_compiles_and_matches_the_java_natives(tmp_path):
+    """The JDK-8 host layer (java/sw/NativeSW.java) binds jni/swb_jni.c.  No JDK exists here: the shim is compiled
+    against tests/jni_stub/jni.h and linked with libswb200; every `static native` method must have a
+    Java_sw_NativeSW_<name> export whose C parameter list is (JNIEnv*, jclass, <one per Java argument>)."""
+    import subprocess
+    so = tmp_path / "libswbjni_stub.so"
+    subprocess.check_call(["gcc", "-shared", "-fPIC", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "tests", "jni_stub"),
+                           "-I" + os.path.join(ROOT, "include"), os.path.join(ROOT, "jni", "swb_jni.c"),
+                           "-L" + os.path.dirname(_ffi.LIB_PATH), "-lswb200", "-o", str(so)])
+    exported = {l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", str(so)], text=True).splitlines()
+                if "Java_sw_NativeSW_" in l}
+    with open(os.path.join(ROOT, "java", "sw", "NativeSW.java")) as f:
+        java = f.read()
+    natives = re.findall(r"static\s+native\s+[\w\[\]]+\s+(\w+)\s*\(([^)]*)\)\s*;", java)
+    assert len(natives) >= 25
+    with open(os.path.join(ROOT, "jni", "swb_jni.c")) as f:
+        csrc = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    for name, args in natives:
+        sym = "Java_sw_NativeSW_" + name
+        assert sym in exported, sym
+        m = re.search(sym + r"\s*\(([^)]*)\)", csrc)
+        n_c = len([a for a in m.group(1).split(",") if a.strip()])
+        n_java = len([a for a in args.split(",") if a.strip()])
+        assert n_c == n_java + 2, (name, n_c, n_java)
+    assert len(exported) == len(natives)
+    # every swb_* symbol the shim calls is declared in the header (it compiled with -Werror) and exported by the library
+    undefined = {l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--undefined-only", str(so)], text=True).splitlines()
+                 if " swb_" in l}
+    lib_syms = {l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", _ffi.LIB_PATH], text=True).splitlines()}
+    assert undefined and undefined <= lib_syms

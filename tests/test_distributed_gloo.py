@@ -41,3 +41,20 @@ def test_allgather_merge_world2():
         k = max(range(n_refs), key=lambda x: (scores[x, q], -x))
         expect[q] = (scores[k, q], k, *cells[k, q])
     mp.spawn(_worker, args=(2, _free_port(), scores, cells, lengths, expect), nprocs=2, join=True)
+
+
+def _worker_empty(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # one reference, two ranks: rank 1's shard is empty and reports (0, -1, 0, 0) for every read
+    ids = multigpu.shard_refs([100], rank, world)
+    local = np.array([[7, 0, 3, 9], [0, 0, 0, 0]], np.int32) if ids else np.array([[0, -1, 0, 0], [0, -1, 0, 0]], np.int32)
+    merged = multigpu.allgather_best_hits(torch.from_numpy(multigpu.localize(local, ids)))
+    assert merged.numpy().tolist() == [[7, 0, 3, 9], [0, 0, 0, 0]], (rank, merged)      # never ref -1 for a score-0 read
+    dist.destroy_process_group()
+
+
+def test_empty_shard_never_wins_world2():
+    assert multigpu.merge_best_hits(np.array([[[0, -1, 0, 0]], [[0, 0, 0, 0]]])).tolist() == [[0, 0, 0, 0]]
+    mp.spawn(_worker_empty, args=(2, _free_port()), nprocs=2, join=True)
