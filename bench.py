@@ -113,6 +113,31 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power) if power else None}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Run this rank (and the pinned result buffers it allocates: first touch) on the CPU cores of the NUMA node the GPU
+    hangs off, so that 8 ranks pulling their results over PCIe do not cross the socket interconnect.  Best effort."""
+    try:
+        bus = subprocess.check_output(["nvidia-smi", "-i", str(index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                      text=True).strip().lower()
+        bus = bus[-12:] if len(bus) > 12 else bus                      # 00000000:1B:00.0 -> 0000:1b:00.0
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        pass
+    return None
+
+
 def shard_refs(refs, rank: int, world: int):
     """Length-balanced shard of the reference set."""
     from sparksmithwaterman_b200 import multigpu
@@ -216,6 +241,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if rank == 0:
         build_native()
     if dist:
@@ -416,6 +442,7 @@ def main():
                     "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
             "gpu_launches": int(agg["launches"]), "max_cells_per_step": int(agg["max_cells"] / K)}
     if world > 1:
+        line["host_affinity"] = numa
         line["collective"] = {"impl": "libswb200 swb_comm_allgather_best: ncclAllGather + merge kernel on the engine stream",
                               "bytes_per_rank_per_step": 16 * B, "merged_equals_independent_reduction": merge_ok}
     if not args.no_cpu_baseline:

@@ -58,7 +58,7 @@ const char *swb_last_error(void);
 int swb_device_count(void);
 
 /* Context for CUDA device `device`.  workspace_bytes bounds the HBM scratch used for
- * fill checkpoints (0 = default 8 GiB, clamped to free memory). */
+ * fill's block records (0 = default: 45 % of the free HBM, at most 64 GiB; always clamped to half the free memory). */
 int  swb_create(int device, int64_t workspace_bytes, swb_ctx **out);
 void swb_destroy(swb_ctx *ctx);
 

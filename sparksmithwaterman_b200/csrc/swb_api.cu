@@ -15,6 +15,69 @@ std::string &last_error()
 }
 }  // namespace swbh
 
+// ---- device-side ingest: validate, case-fold, encode and 2-bit pack on the GPU (the reference's strings come from
+// InOutOps.GetRefSeqs / GetReads, InOutOps.java:60-88, :100-169; here they arrive as raw ASCII bytes) ------------
+namespace {
+
+// which byte values occur (after upper-casing): 128-bit presence mask + a non-ASCII flag
+__global__ void seq_scan_kernel(const uint8_t *raw, int64_t n, uint32_t *present, uint32_t *bad)
+{
+    uint32_t m[4] = {0, 0, 0, 0};
+    uint32_t b = 0;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t c = raw[k];
+        if (c >= 128) { b = 1; continue; }
+        if (c >= 'a' && c <= 'z') c -= 32;
+        m[c >> 5] |= 1u << (c & 31);
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w) {
+        uint32_t v = m[w];
+        for (int o = 16; o; o >>= 1) v |= __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0 && v) atomicOr(present + w, v);
+    }
+    if (b) atomicOr(bad, 1u);
+}
+
+// raw ASCII -> symbol codes (code_of[upper(byte)], 0xFF = symbol absent from the reference set)
+__global__ void seq_encode_kernel(const uint8_t *raw, int64_t n, const uint8_t *code_of, uint8_t *codes, uint32_t *bad)
+{
+    __shared__ uint8_t tab[128];
+    if (threadIdx.x < 128) tab[threadIdx.x] = code_of[threadIdx.x];
+    __syncthreads();
+    uint32_t b = 0;
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t c = raw[k];
+        if (c >= 128) { b = 1; c = 0; }
+        if (c >= 'a' && c <= 'z') c -= 32;
+        codes[k] = tab[c];
+    }
+    if (b && bad) atomicOr(bad, 1u);
+}
+
+// 2-bit pack, 16 codes per word, references in the device (descending-length) order: one thread per output word
+__global__ void ref_pack_kernel(const uint8_t *codes8, const int64_t *src_off, const int32_t *len, const uint32_t *word_off,
+                                int64_t n_refs, uint64_t n_words, uint32_t *words)
+{
+    for (uint64_t w = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; w < n_words; w += (uint64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = n_refs;                              // last reference whose first word is <= w
+        while (hi - lo > 1) { const int64_t mid = (lo + hi) >> 1; if ((uint64_t)word_off[mid] <= w) lo = mid; else hi = mid; }
+        const int64_t c0 = (int64_t)(w - word_off[lo]) * 16;
+        const int64_t n = len[lo];
+        const uint8_t *src = codes8 + src_off[lo] + c0;
+        uint32_t v = 0;
+        for (int k = 0; k < 16 && c0 + k < n; ++k) v |= (uint32_t)(src[k] & 3u) << (2 * k);
+        words[w] = v;
+    }
+}
+
+int grid_for(int64_t n, int threads, int sm_count)
+{
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)sm_count * 16));
+}
+
+}  // namespace
+
 extern "C" {
 
 int swb_abi_version(void) { return SWB_ABI_VERSION; }
@@ -42,12 +105,16 @@ int swb_create(int device, int64_t workspace_bytes, swb_ctx **out)
     cudaDeviceProp p;
     CU(cudaGetDeviceProperties(&p, device));
     if (p.major < 9) return fail(SWB_E_UNSUPPORTED, "swb_create: DPX kernels need sm_90+ (built for sm_100a)");
-    swb_ctx *c = new swb_ctx();
+    // owned until *out is set: a failing call below releases the streams / events created so far
+    std::unique_ptr<swb_ctx, void (*)(swb_ctx *)> guard(new swb_ctx(), swb_destroy);
+    swb_ctx *c = guard.get();
     c->device = device;
     c->sm_count = p.multiProcessorCount;
     size_t free_b = 0, total_b = 0;
     CU(cudaMemGetInfo(&free_b, &total_b));
-    int64_t ws = workspace_bytes > 0 ? workspace_bytes : (int64_t)8 << 30;
+    // default: 45 % of the free HBM, at most 64 GiB (a B200 has 180 GB: the number every published figure uses).  The
+    // block records of one batch live here; a larger workspace means fewer, larger batches (cfg3 needs 27 GB for one).
+    int64_t ws = workspace_bytes > 0 ? workspace_bytes : std::min<int64_t>((int64_t)64 << 30, (int64_t)(free_b / 100 * 45));
     ws = std::min<int64_t>(ws, (int64_t)(free_b / 2));
     c->ws_bytes = ws;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
@@ -62,13 +129,22 @@ int swb_create(int device, int64_t workspace_bytes, swb_ctx **out)
     CU(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = UINT64_MAX;                                    // keep freed blocks in the pool
     CU(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    *out = c;
+    *out = guard.release();
     return SWB_OK;
+}
+
+// Handles (reference sets, read batches, results) point into their context and release device memory on its
+// streams: a context destroyed while handles are alive (Python __del__ order at interpreter exit, a JVM's global
+// arena) only marks itself; the last handle's *_free finishes the destruction.
+static void ctx_handle_released(swb_ctx *c)
+{
+    if (c->live.fetch_sub(1) == 1 && c->dying.load()) swb_destroy(c);
 }
 
 void swb_destroy(swb_ctx *c)
 {
     if (!c) return;
+    if (c->live.load() > 0) { c->dying.store(true); return; }
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     c->ck.release(); c->tmx.release(); c->counters.release(); c->rp.release(); c->slot.release();
@@ -121,7 +197,7 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
     rs->ctx = ctx;
     rs->n_refs = n_refs;
     rs->len_orig.resize((size_t)n_refs);
-    bool present[128] = {false};
+    cudaStream_t st = ctx->stream;
     for (int64_t k = 0; k < n_refs; ++k) {
         const int64_t n = offsets[k + 1] - offsets[k];
         if (n >= ((int64_t)1 << KEY_J_BITS))
@@ -129,15 +205,25 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         rs->len_orig[(size_t)k] = (int32_t)n;
         rs->total_bases += n;
         rs->max_len = std::max<int32_t>(rs->max_len, (int32_t)n);
-        const unsigned char *p = (const unsigned char *)bytes + offsets[k];
-        for (int64_t c = 0; c < n; ++c) {
-            if (p[c] >= 128) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: non-ASCII byte in a reference");
-            present[upper(p[c])] = true;
-        }
     }
+    // ---- raw bytes to the device; symbols present and the non-ASCII check there ----------------------
+    const int64_t total = rs->total_bases;
+    DevBuf<uint8_t> d_raw, d_tab;
+    DevBuf<uint32_t> d_flags;                                      // [0..3] presence mask, [4] non-ASCII seen
+    CU(d_raw.alloc((size_t)total + 16, st));
+    CU(d_flags.alloc(8, st));
+    CU(d_tab.alloc(128, st));
+    CU(cudaMemsetAsync(d_flags.p, 0, 32, st));
+    if (total) CU(cudaMemcpyAsync(d_raw.p, bytes + offsets[0], (size_t)total, cudaMemcpyHostToDevice, st));
+    if (total) seq_scan_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw.p, total, d_flags.p, d_flags.p + 4);
+    CU(cudaGetLastError());
+    uint32_t h_flags[8] = {0};
+    CU(cudaMemcpyAsync(h_flags, d_flags.p, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_flags[4]) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: non-ASCII byte in a reference");
     memset(rs->code_of, 0xFF, sizeof rs->code_of);
     for (int c = 0; c < 128; ++c)
-        if (present[c]) rs->code_of[c] = (uint8_t)rs->n_symbols++;
+        if ((h_flags[c >> 5] >> (c & 31)) & 1u) rs->code_of[c] = (uint8_t)rs->n_symbols++;
     rs->two_bit_ok = rs->n_symbols <= 4;       // otherwise only the 8-bit int32 path can hold the set
 
     // length buckets: descending length, stable
@@ -147,7 +233,7 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
                      [&](int32_t a, int32_t b) { return rs->len_orig[(size_t)a] > rs->len_orig[(size_t)b]; });
     std::vector<int32_t> sorted_of((size_t)n_refs), len_sorted((size_t)n_refs);
     std::vector<uint32_t> word_off((size_t)n_refs);
-    std::vector<int64_t> blk_off((size_t)n_refs + 1);
+    std::vector<int64_t> blk_off((size_t)n_refs + 1), src_off((size_t)n_refs), o8((size_t)n_refs + 1);
     uint64_t words_total = 0;
     int64_t blocks = 0;
     for (int64_t s = 0; s < n_refs; ++s) {
@@ -156,55 +242,47 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         sorted_of[(size_t)o] = (int32_t)s;
         len_sorted[(size_t)s] = n;
         word_off[(size_t)s] = (uint32_t)words_total;
+        src_off[(size_t)s] = offsets[o] - offsets[0];
         words_total += (uint64_t)(n + 15) / 16;
         blk_off[(size_t)s] = blocks;
         blocks += (n + GL - 1 + CB - 1) / CB > 0 ? (n + GL - 1 + CB - 1) / CB : 1;
     }
     blk_off[(size_t)n_refs] = blocks;
+    for (int64_t k = 0; k <= n_refs; ++k) o8[(size_t)k] = offsets[k] - offsets[0];
     rs->len_sorted = len_sorted;
     rs->blocks_per_rp = blocks;
     if (words_total >= ((uint64_t)1 << 32)) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference set too large");
-    std::vector<uint32_t> words((size_t)words_total + 1, 0u);
-    for (int64_t s = 0; s < n_refs; ++s) {
-        const int32_t o = order[(size_t)s];
-        const unsigned char *p = (const unsigned char *)bytes + offsets[o];
-        uint32_t *w = words.data() + word_off[(size_t)s];
-        const int32_t n = len_sorted[(size_t)s];
-        if (rs->two_bit_ok)
-            for (int32_t c = 0; c < n; ++c) w[c >> 4] |= (uint32_t)rs->code_of[upper(p[c])] << (2 * (c & 15));
-    }
-    // 8-bit codes in the caller's order for the wide path
-    {
-        std::vector<uint8_t> c8((size_t)rs->total_bases + 1);
-        std::vector<int64_t> o8((size_t)n_refs + 1);
-        int64_t pos = 0;
-        for (int64_t k = 0; k < n_refs; ++k) {
-            o8[(size_t)k] = pos;
-            const unsigned char *p = (const unsigned char *)bytes + offsets[k];
-            for (int32_t c = 0; c < rs->len_orig[(size_t)k]; ++c) c8[(size_t)pos++] = rs->code_of[upper(p[c])];
-        }
-        o8[(size_t)n_refs] = pos;
-        CU(rs->codes8.alloc(c8.size(), ctx->stream));
-        CU(rs->off8.alloc(o8.size(), ctx->stream));
-        CU(cudaStreamSynchronize(ctx->stream));
-        CU(cudaMemcpy(rs->codes8.p, c8.data(), c8.size(), cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(rs->off8.p, o8.data(), o8.size() * 8, cudaMemcpyHostToDevice));
-    }
-    CU(rs->words.alloc(words.size(), ctx->stream));
-    CU(rs->word_off.alloc((size_t)n_refs, ctx->stream));
-    CU(rs->len.alloc((size_t)n_refs, ctx->stream));
-    CU(rs->orig.alloc((size_t)n_refs, ctx->stream));
-    CU(rs->sorted_of.alloc((size_t)n_refs, ctx->stream));
-    CU(rs->blk_off.alloc((size_t)n_refs + 1, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
-    CU(cudaMemcpy(rs->words.p, words.data(), words.size() * 4, cudaMemcpyHostToDevice));
+
+    // ---- encode (8-bit codes, caller's order: wide path) and 2-bit pack (sorted order: short path) on the device ----
+    DevBuf<int64_t> d_src_off;
+    CU(rs->codes8.alloc((size_t)total + 16, st));
+    CU(rs->off8.alloc(o8.size(), st));
+    CU(rs->words.alloc((size_t)words_total + 1, st));
+    CU(rs->word_off.alloc((size_t)n_refs, st));
+    CU(rs->len.alloc((size_t)n_refs, st));
+    CU(rs->orig.alloc((size_t)n_refs, st));
+    CU(rs->sorted_of.alloc((size_t)n_refs, st));
+    CU(rs->blk_off.alloc((size_t)n_refs + 1, st));
+    CU(d_src_off.alloc((size_t)n_refs, st));
+    CU(cudaMemcpyAsync(d_tab.p, rs->code_of, 128, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(rs->off8.p, o8.data(), o8.size() * 8, cudaMemcpyHostToDevice, st));
     if (n_refs) {
-        CU(cudaMemcpy(rs->word_off.p, word_off.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(rs->len.p, len_sorted.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(rs->orig.p, order.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
-        CU(cudaMemcpy(rs->sorted_of.p, sorted_of.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice));
+        CU(cudaMemcpyAsync(rs->word_off.p, word_off.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(rs->len.p, len_sorted.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(rs->orig.p, order.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(rs->sorted_of.p, sorted_of.data(), (size_t)n_refs * 4, cudaMemcpyHostToDevice, st));
+        CU(cudaMemcpyAsync(d_src_off.p, src_off.data(), (size_t)n_refs * 8, cudaMemcpyHostToDevice, st));
     }
-    CU(cudaMemcpy(rs->blk_off.p, blk_off.data(), ((size_t)n_refs + 1) * 8, cudaMemcpyHostToDevice));
+    CU(cudaMemcpyAsync(rs->blk_off.p, blk_off.data(), ((size_t)n_refs + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (total) seq_encode_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw.p, total, d_tab.p, rs->codes8.p, nullptr);
+    CU(cudaMemsetAsync(rs->words.p + words_total, 0, 4, st));
+    if (words_total && rs->two_bit_ok)
+        ref_pack_kernel<<<grid_for((int64_t)words_total, 256, ctx->sm_count), 256, 0, st>>>(rs->codes8.p, d_src_off.p, rs->len.p, rs->word_off.p,
+                                                                                             n_refs, words_total, rs->words.p);
+    else if (words_total) CU(cudaMemsetAsync(rs->words.p, 0, (size_t)words_total * 4, st));
+    CU(cudaGetLastError());
+    CU(cudaStreamSynchronize(st));                 // the host tables above are locals
+    ctx->live.fetch_add(1);
     *out = rs.release();
     return SWB_OK;
 }
@@ -212,8 +290,10 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
 void swb_refset_free(swb_refset *rs)
 {
     if (!rs) return;
-    cudaSetDevice(rs->ctx->device);
+    swb_ctx *c = rs->ctx;
+    cudaSetDevice(c->device);
     delete rs;
+    ctx_handle_released(c);
 }
 int64_t swb_refset_count(const swb_refset *rs) { return rs ? rs->n_refs : 0; }
 int64_t swb_refset_total_bases(const swb_refset *rs) { return rs ? rs->total_bases : 0; }
@@ -242,20 +322,26 @@ int swb_reads_upload(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const 
         total += m;
     }
     off[(size_t)n_reads] = total;
-    std::vector<uint8_t> codes((size_t)total + 1);
-    for (int64_t k = 0; k < n_reads; ++k) {
-        const unsigned char *p = (const unsigned char *)bytes + offsets[k];
-        uint8_t *c = codes.data() + off[(size_t)k];
-        for (int32_t x = 0; x < rd->len[(size_t)k]; ++x) {
-            if (p[x] >= 128) return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: non-ASCII byte in a read");
-            c[x] = rs->code_of[upper(p[x])];
-        }
-    }
-    CU(rd->codes.alloc(codes.size(), ctx->stream));
-    CU(rd->off.alloc(off.size(), ctx->stream));
-    CU(cudaMemcpyAsync(rd->codes.p, codes.data(), codes.size(), cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaMemcpyAsync(rd->off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
-    CU(cudaStreamSynchronize(ctx->stream));
+    // raw bytes up, case-fold + encode against the set's alphabet on the device
+    cudaStream_t st = ctx->stream;
+    DevBuf<uint8_t> d_raw, d_tab;
+    DevBuf<uint32_t> d_bad;
+    CU(d_raw.alloc((size_t)total + 16, st));
+    CU(d_tab.alloc(128, st));
+    CU(d_bad.alloc(1, st));
+    CU(rd->codes.alloc((size_t)total + 16, st));
+    CU(rd->off.alloc(off.size(), st));
+    CU(cudaMemsetAsync(d_bad.p, 0, 4, st));
+    CU(cudaMemcpyAsync(d_tab.p, rs->code_of, 128, cudaMemcpyHostToDevice, st));
+    if (total) CU(cudaMemcpyAsync(d_raw.p, bytes + offsets[0], (size_t)total, cudaMemcpyHostToDevice, st));
+    CU(cudaMemcpyAsync(rd->off.p, off.data(), off.size() * 8, cudaMemcpyHostToDevice, st));
+    if (total) seq_encode_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw.p, total, d_tab.p, rd->codes.p, d_bad.p);
+    CU(cudaGetLastError());
+    uint32_t h_bad = 0;
+    CU(cudaMemcpyAsync(&h_bad, d_bad.p, 4, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_bad) return fail(SWB_E_UNSUPPORTED, "swb_reads_upload: non-ASCII byte in a read");
+    ctx->live.fetch_add(1);
     *out = rd.release();
     return SWB_OK;
 }
@@ -263,8 +349,10 @@ int swb_reads_upload(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const 
 void swb_reads_free(swb_reads *rd)
 {
     if (!rd) return;
-    cudaSetDevice(rd->ctx->device);
+    swb_ctx *c = rd->ctx;
+    cudaSetDevice(c->device);
     delete rd;
+    ctx_handle_released(c);
 }
 int64_t swb_reads_count(const swb_reads *rd) { return rd ? rd->n_reads : 0; }
 
@@ -343,7 +431,10 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    std::unique_ptr<swb_result> res(new swb_result());
+    // a result counts as a live handle of its context from here on (released by swb_result_free, also on the error paths)
+    auto res_del = [](swb_result *r) { swb_result_free(r); };
+    std::unique_ptr<swb_result, decltype(res_del)> res(new swb_result(), res_del);
+    ctx->live.fetch_add(1);
     res->ctx = ctx; res->n_refs = n_refs; res->n_reads = n_reads; res->flags = flags;
     res->ref_len = rs->len_orig; res->read_len = rd->len;
     const size_t n_pairs = (size_t)(n_refs * n_reads);
@@ -754,12 +845,14 @@ int swb_result_fetch(swb_result *res)
 void swb_result_free(swb_result *res)
 {
     if (!res) return;
-    cudaSetDevice(res->ctx->device);
+    swb_ctx *c = res->ctx;
+    cudaSetDevice(c->device);
     {
-        std::lock_guard<std::recursive_mutex> lk(res->ctx->mu);
-        for (auto &b : res->pins) res->ctx->pin_put(b);
+        std::lock_guard<std::recursive_mutex> lk(c->mu);
+        for (auto &b : res->pins) c->pin_put(b);
     }
     delete res;
+    ctx_handle_released(c);
 }
 
 int64_t swb_result_n_refs(const swb_result *r) { return r ? r->n_refs : 0; }

@@ -3,6 +3,7 @@
 #include "swb_internal.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -68,6 +69,8 @@ struct swb_ctx {
     DevBuf<int32_t> rp2[2];
     cudaEvent_t ev[2] = {nullptr, nullptr};
     std::recursive_mutex mu;
+    std::atomic<int> live{0};                   // handles (refsets, read batches, results) that still point here
+    std::atomic<bool> dying{false};             // swb_destroy was called while handles were alive: the last free destroys
     // grow-only scratch reused by every align call on this context
     DevBuf<uint32_t> ck, tmx, counters;
     DevBuf<int32_t> rp, slot;

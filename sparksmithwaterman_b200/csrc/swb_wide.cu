@@ -481,8 +481,11 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
     using TG = TraceGeo<KL, BYTE>;
     constexpr int ES = TG::ES, ROWW = TG::ROWW, COLB = TG::COLB, TW = TG::TW;
     constexpr int DG = COLB + ES;                                   // one diagonal step, in bytes
-    constexpr int HS = G / 2 > 0 ? G / 2 : 1;                      // lane-rows a corridor covers
+    constexpr int DB = G >= 128 ? 4 : (G > 1 ? 2 : 1);             // blocks per lane-row of the corridor
+    constexpr int HS = G / DB;                                     // lane-rows a corridor covers
+    static_assert(G == 1 || G == 32 || G == NT, "a group is a thread, a warp or the whole CTA");
     extern __shared__ uint32_t tsm[];
+    __shared__ int bc_state[3];                                    // CTA-wide groups: the walker's state for the next round
     int32_t *slot_blk = reinterpret_cast<int32_t *>(tsm);           // [NT] block of the tile in each thread's slot
     uint32_t *slots = tsm + NT + TG::GUARD;
     uint32_t *mytile = slots + (size_t)threadIdx.x * TW;
@@ -530,18 +533,17 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
         uint32_t *myops = ops + (int64_t)cell * ops_stride;
         while (hcur > 0) {                                         // group-uniform: the state is broadcast below
             // ---- corridor: slot (k, d) = lane-row T0 - k, block b_k - d, b_k from the diagonal through (ci, cj)
+            // (DB = 2: blocks b_k, b_k - 1; DB = 4: b_k + 1 .. b_k - 2 -- a path with many gaps drifts off the diagonal)
             const int T0 = (ci - 1) / KL;
-            const int k = gl >> 1, d = gl & 1;
+            const int k = gl / DB, d = gl % DB;
             const int Tk = T0 - k;
             int myblk = -1;
             if (Tk >= 0) {
                 const int t = Tk % WL;
                 const int di = k == 0 ? 0 : ci - (Tk * KL + KL);   // rows the path climbs to reach lane-row Tk
                 const int step = cj - di - 1 + t;
-                if (step >= 0) {
-                    const int b = step / WCB - d;
-                    if (b >= 0 && b < C.n_blocks) myblk = b;
-                }
+                const int b = (step >= 0 ? step / WCB : -1) + (DB == 4 ? 1 : 0) - d;
+                if (b >= 0 && b < C.n_blocks) myblk = b;
             }
             if (myblk >= 0) {
                 WTile<KL> W;
@@ -560,9 +562,10 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             }
             slot_blk[threadIdx.x] = myblk;
             if (P.dbg) { if (gl == 0) atomicAdd(P.dbg, 1ull); if (myblk >= 0) atomicAdd(P.dbg + 2, 1ull); }
-            if (G > 1) __syncwarp(gmask);
-            if (gl == 0) {
-                // ---- walk (SmithWaterman.java:380-409) through the corridor's tiles
+            if (G == 32) __syncwarp(gmask);
+            else if (G > 32) __syncthreads();
+            if (G == 1) {
+                // ---- walk (SmithWaterman.java:380-409): one thread per max cell
                 for (;;) {
                     const int T = (ci - 1) / KL;
                     const int kk = T0 - T;
@@ -570,9 +573,12 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     const int t = T % WL;
                     const int step = cj - 1 + t;
                     const int b = step / WCB;
-                    int slot = leader + 2 * kk;
+                    int slot = leader + DB * kk;
                     if (slot_blk[slot] != b) {
-                        if (G > 1 && slot_blk[slot + 1] == b) ++slot; else break;
+                        int dd = 1;
+                        while (dd < DB && slot_blk[slot + dd] != b) ++dd;
+                        if (dd == DB) break;
+                        slot += dd;
                     }
                     int r = ci - T * KL;                           // 1..KL
                     int c = step - b * WCB + 1;                    // 1..WCB
@@ -625,11 +631,94 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     if (hcur <= 0) break;
                 }
             }
-            if (G > 1) {
-                hcur = __shfl_sync(gmask, hcur, 0);
-                ci = __shfl_sync(gmask, ci, 0);
-                cj = __shfl_sync(gmask, cj, 0);
-                __syncwarp(gmask);
+            if (G > 1 && gl < 32) {
+                // ---- walk (SmithWaterman.java:380-409), all 32 lanes of the group's first warp in lock step.  Every lane
+                // keeps the whole walker state (no shuffles); lane k probes the diagonal cell (r - k, c - k): it is an
+                // alignment move iff NW + s == H (the '>=' cascade's first choice), so one ballot finds a whole run of
+                // alignment moves; the gap move that ends the run is decided in the same iteration.
+                const int wl = gl;
+                const int big = max(abs(match), abs(mismatch));
+                auto push = [&](uint32_t op, int n) {               // n columns of the same op
+                    const uint32_t pattern = op * 0x55555555u;
+                    while (n > 0) {
+                        const int used = (int)(oplen & 15);
+                        const int take = min(n, 16 - used);
+                        const uint32_t bits = take == 16 ? pattern : (pattern & ((1u << (2 * take)) - 1u));
+                        opword |= bits << (2 * used);
+                        oplen += take; n -= take;
+                        if ((oplen & 15) == 0) { if (wl == 0) myops[(oplen >> 4) - 1] = opword; opword = 0; }
+                    }
+                };
+                for (;;) {
+                    const int T = (ci - 1) / KL;
+                    const int kk = T0 - T;
+                    if (kk >= HS) break;
+                    const int t = T % WL;
+                    const int step = cj - 1 + t;
+                    const int b = step / WCB;
+                    int slot = leader + DB * kk;
+                    if (slot_blk[slot] != b) {
+                        int dd = 1;
+                        while (dd < DB && slot_blk[slot + dd] != b) ++dd;
+                        if (dd == DB) break;
+                        slot += dd;
+                    }
+                    int r = ci - T * KL;                           // 1..KL
+                    int c = step - b * WCB + 1;                    // 1..WCB
+                    if (P.dbg && wl == 0) atomicAdd(P.dbg + 1, 1ull);
+                    const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
+                    const uint8_t *p = base + c * COLB + r * ES;   // element (r, c)
+                    const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);          // read code of row r
+                    const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);     // reference code of column c
+                    for (;;) {
+                        const int lim = min(r, c);                 // cells (r - k, c - k), k < lim, lie inside this tile
+                        const bool inside = wl < lim;
+                        const uint8_t *pk = p - wl * DG;
+                        const int hk = inside ? elem(pk) : 0, hnwk = inside ? elem(pk - DG) : 1;
+                        const bool is_m = inside && pr[-wl] == pq[-wl];
+                        const int sck = is_m ? match : mismatch;
+                        const bool okk = inside && (((hnwk + sck - hk) & M) == 0);
+                        const unsigned okm = __ballot_sync(0xffffffffu, okk), mm = __ballot_sync(0xffffffffu, is_m);
+                        const int run = tie_gt ? 0 : (okm == 0xffffffffu ? 32 : __ffs((int)~okm) - 1);
+                        // a cell is only visited while its score is positive: exact along the run unless the walk is about
+                        // to end -- then advance one cell at a time
+                        const int L = (hcur > 32 * big) ? run : min(run, 1);
+                        if (L > 0) {
+                            const unsigned lm = L >= 32 ? 0xffffffffu : ((1u << L) - 1u);
+                            const int nm = __popc(mm & lm);
+                            hcur -= nm * match + (L - nm) * mismatch;
+                            beginning = cj - (L - 1);
+                            ci -= L; cj -= L; r -= L; c -= L;
+                            p -= L * DG; pr -= L; pq -= L;
+                            push(1u, L);
+                        }
+                        if (hcur <= 0 || r == 0 || c == 0) break;  // done, or the path left this tile
+                        if (L == run && run < lim) {
+                            // the cell here is known not to take the alignment move ('>=' rule), or the rule is '>'
+                            const int hn = elem(p - ES), hw = elem(p - COLB);
+                            const bool eq_i = ((hn + gap - hcur) & M) == 0, eq_d = ((hw + gap - hcur) & M) == 0;
+                            const int s0 = (pr[0] == pq[0]) ? match : mismatch;
+                            const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
+                            beginning = cj;
+                            hcur -= (op == 1u) ? s0 : gap;
+                            const int up = op != 3u, left = op != 2u;
+                            r -= up; ci -= up; pr -= up;
+                            c -= left; cj -= left; pq -= left;
+                            p -= up * ES + left * COLB;
+                            push(op, 1);
+                            if (hcur <= 0 || r == 0 || c == 0) break;
+                        }
+                    }
+                    if (hcur <= 0) break;
+                }
+            }
+            if (G == 32) {
+                __syncwarp(gmask);                                 // every lane walked: the state is already uniform
+            } else if (G > 32) {
+                if (gl == 0) { bc_state[0] = hcur; bc_state[1] = ci; bc_state[2] = cj; }
+                __syncthreads();
+                hcur = bc_state[0]; ci = bc_state[1]; cj = bc_state[2];
+                __syncthreads();
             }
         }
         if (gl == 0) {
@@ -689,14 +778,16 @@ cudaError_t launch_trace_kl(const WideParams &P, const uint64_t *keys, uint32_t 
 {
     const bool bytes = tile_trace_ok(P.match, P.mismatch, P.gap);        // same bound as the short path's byte tiles
     static const int env_g = getenv("SWB_WIDE_TRACE_G") ? atoi(getenv("SWB_WIDE_TRACE_G")) : 0;
-    // one warp per cell while the cells cannot fill the machine with one thread each
-    const bool warp_mode = env_g ? env_g == 32 : (int64_t)n_cells < (int64_t)sm_count * 256;
-    constexpr int NTB = KL >= 32 ? 64 : 128;                              // byte tiles: 76 / 84 / 50 KB per CTA
+    // lanes per max cell: a whole CTA (corridor of 32 lane-rows x 4 blocks) while there are fewer cells than SMs, a warp
+    // (16 x 2) while the cells cannot fill the machine with one thread each, else one thread per cell
+    const int g = env_g ? env_g : ((int64_t)n_cells <= (int64_t)sm_count ? 128 : ((int64_t)n_cells < (int64_t)sm_count * 256 ? 32 : 1));
+    constexpr int NTB = KL >= 32 ? 64 : 128;                              // byte tiles: 80 / 91 / 56 KB per CTA
     if (bytes) {
-        if (warp_mode) return launch_trace_k<KL, NTB, 32, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        if (g >= 128) return launch_trace_k<KL, 128, 128, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        if (g == 32) return launch_trace_k<KL, NTB, 32, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
         return launch_trace_k<KL, NTB, 1, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
     }
-    if (warp_mode) return launch_trace_k<KL, 32, 32, false>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+    if (g >= 32) return launch_trace_k<KL, 32, 32, false>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
     return launch_trace_k<KL, 32, 1, false>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
 }
 

@@ -58,8 +58,18 @@ def main():
             got = res.pair(lk, q)
             assert got[0] == exp.score and got[1] == exp.cells and got[2] == exp.sites, (gk, q)
             checked += 1; cells += len(exp.cells)
+    # the merge through the C ABI's own collective (swb_comm_*: ncclAllGather + merge kernel), and, as a cross-check,
+    # through torch.distributed
     best = torch.from_numpy(multigpu.localize(res.best_hits, ids)).cuda()
-    merged = multigpu.allgather_best_hits(best) if world > 1 else best
+    if world > 1:
+        box = [multigpu.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        comm = multigpu.Comm(eng, box[0], rank, world)
+        merged = torch.from_numpy(comm.allgather_best(res, np.asarray(ids, dtype=np.int64)))
+        assert (merged.numpy() == multigpu.allgather_best_hits(best).cpu().numpy()).all()
+        comm.close()
+    else:
+        merged = best
     # single-shard reference answer from the oracle
     expect = np.zeros((len(reads), 4), np.int32)
     for q, read in enumerate(reads):
