@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Companion of tools/pin_oracle_with_jdk.sh: emits the pinning cases (every known-answer vector of
+"""Companion of oracle/pin_with_jdk.sh: emits the pinning cases (every known-answer vector of
 tests/golden/kat.json + N seeded random pairs over several score sets) as TSV for the Java driver, and compares the
 Java operator's answers with the C oracle's (oracle/sw_oracle.c).  The oracle side runs anywhere (gcc only)."""
 import argparse

@@ -1,5 +1,5 @@
 #!/bin/bash
-# pin_oracle_with_jdk.sh -- turn "parity unpinned" into a one-command check on any host that has a JDK (>= 8).
+# pin_with_jdk.sh -- turn "parity unpinned" into a one-command check on any host that has a JDK (>= 8).
 #
 # The reference's operator file src/sw/SmithWaterman.java imports only three foreign types
 # (org.apache.spark.api.java.function.Function2 / Function3 and scala.Tuple2, SmithWaterman.java:3-6), so it
@@ -7,11 +7,11 @@
 #   1. writes the stubs + a small driver into a temp dir,
 #   2. compiles the UNMODIFIED reference file from where it lies (never copied into this repo),
 #   3. runs the Java operator over every known-answer vector of tests/golden/kat.json and over --random N seeded
-#      random pairs (the same generator as tools/pin_oracle_pairs.py prints),
+#      random pairs (the same generator as oracle/pin_pairs.py prints),
 #   4. diffs score / max-cell count / beginnings / both alignment strings against the C oracle's committed answers.
 # Exit code 0 = the oracle (and with it every GPU parity test) is pinned to the real Java implementation.
 #
-#   tools/pin_oracle_with_jdk.sh [/path/to/reference] [--random 200]
+#   oracle/pin_with_jdk.sh [/path/to/reference] [--random 200]
 #
 # NOT RUNNABLE in the build image (no JDK, no network); committed so that a maintainer can.
 set -euo pipefail
@@ -69,6 +69,6 @@ public class Pin {
 }
 J
 javac -nowarn -d "$W/out" $(find "$W/src" -name '*.java') "$REF/src/sw/SmithWaterman.java"
-python3 "$ROOT/tools/pin_oracle_pairs.py" --random "$RANDOM_N" --emit-cases > "$W/cases.tsv"
+python3 "$ROOT/oracle/pin_pairs.py" --random "$RANDOM_N" --emit-cases > "$W/cases.tsv"
 java -Xss512m -cp "$W/out" pin.Pin < "$W/cases.tsv" > "$W/java.tsv"
-python3 "$ROOT/tools/pin_oracle_pairs.py" --random "$RANDOM_N" --compare "$W/java.tsv"
+python3 "$ROOT/oracle/pin_pairs.py" --random "$RANDOM_N" --compare "$W/java.tsv"

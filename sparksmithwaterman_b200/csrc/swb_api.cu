@@ -119,6 +119,7 @@ int swb_create(int device, int64_t workspace_bytes, swb_ctx **out)
     c->ws_bytes = ws;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     CU(cudaStreamCreateWithFlags(&c->stream_fill, cudaStreamNonBlocking));
+    CU(cudaStreamCreateWithFlags(&c->stream_copy, cudaStreamNonBlocking));
     // Two-stream pipelining (fill of batch k+1 beside the traceback of batch k) is OFF by default: measured on
     // B200 the persistent fill warps keep the integer pipe ~94 % busy and starve co-resident kernels (locate
     // 0.55 -> 5.5 ms), so the overlap buys nothing (62.0 vs 61.1 ms per step).  SWB_PIPELINE=1 enables it.
@@ -160,6 +161,7 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
     if (c->stream_fill) cudaStreamDestroy(c->stream_fill);
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -183,48 +185,27 @@ static int check_offsets(const char *who, int64_t n, const char *bytes, const in
     return SWB_OK;
 }
 
-int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64_t *offsets, swb_refset **out)
+// One packed set over references [0, n_refs) of `offsets`, whose raw bytes already sit on the device at d_raw
+// (d_raw[0] = byte offsets[0]); the alphabet is the caller's.  Encodes (8-bit codes, caller's order: wide path) and
+// 2-bit packs (descending-length order: short path) on the device.
+static int build_leaf(swb_ctx *ctx, int64_t n_refs, const int64_t *offsets, const uint8_t *d_raw, const uint8_t *code_of,
+                      int n_symbols, swb_refset **out)
 {
-    if (!ctx || !out) return fail(SWB_E_INVALID, "swb_refset_load: null argument");
-    *out = nullptr;
-    int rc = check_offsets("swb_refset_load", n_refs, bytes, offsets);
-    if (rc) return rc;
-    if (n_refs > (int64_t)1 << 30) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: more than 2^30 references");
-    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
-    CU(cudaSetDevice(ctx->device));
-
+    cudaStream_t st = ctx->stream;
     std::unique_ptr<swb_refset> rs(new swb_refset());
     rs->ctx = ctx;
     rs->n_refs = n_refs;
     rs->len_orig.resize((size_t)n_refs);
-    cudaStream_t st = ctx->stream;
     for (int64_t k = 0; k < n_refs; ++k) {
         const int64_t n = offsets[k + 1] - offsets[k];
-        if (n >= ((int64_t)1 << KEY_J_BITS))
-            return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference longer than 4,194,303 bases");
         rs->len_orig[(size_t)k] = (int32_t)n;
         rs->total_bases += n;
         rs->max_len = std::max<int32_t>(rs->max_len, (int32_t)n);
     }
-    // ---- raw bytes to the device; symbols present and the non-ASCII check there ----------------------
     const int64_t total = rs->total_bases;
-    DevBuf<uint8_t> d_raw, d_tab;
-    DevBuf<uint32_t> d_flags;                                      // [0..3] presence mask, [4] non-ASCII seen
-    CU(d_raw.alloc((size_t)total + 16, st));
-    CU(d_flags.alloc(8, st));
-    CU(d_tab.alloc(128, st));
-    CU(cudaMemsetAsync(d_flags.p, 0, 32, st));
-    if (total) CU(cudaMemcpyAsync(d_raw.p, bytes + offsets[0], (size_t)total, cudaMemcpyHostToDevice, st));
-    if (total) seq_scan_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw.p, total, d_flags.p, d_flags.p + 4);
-    CU(cudaGetLastError());
-    uint32_t h_flags[8] = {0};
-    CU(cudaMemcpyAsync(h_flags, d_flags.p, 32, cudaMemcpyDeviceToHost, st));
-    CU(cudaStreamSynchronize(st));
-    if (h_flags[4]) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: non-ASCII byte in a reference");
-    memset(rs->code_of, 0xFF, sizeof rs->code_of);
-    for (int c = 0; c < 128; ++c)
-        if ((h_flags[c >> 5] >> (c & 31)) & 1u) rs->code_of[c] = (uint8_t)rs->n_symbols++;
-    rs->two_bit_ok = rs->n_symbols <= 4;       // otherwise only the 8-bit int32 path can hold the set
+    memcpy(rs->code_of, code_of, sizeof rs->code_of);
+    rs->n_symbols = n_symbols;
+    rs->two_bit_ok = n_symbols <= 4;           // otherwise only the 8-bit int32 path can hold the set
 
     // length buckets: descending length, stable
     std::vector<int32_t> order((size_t)n_refs);
@@ -253,8 +234,9 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
     rs->blocks_per_rp = blocks;
     if (words_total >= ((uint64_t)1 << 32)) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference set too large");
 
-    // ---- encode (8-bit codes, caller's order: wide path) and 2-bit pack (sorted order: short path) on the device ----
     DevBuf<int64_t> d_src_off;
+    DevBuf<uint8_t> d_tab;
+    CU(d_tab.alloc(128, st));
     CU(rs->codes8.alloc((size_t)total + 16, st));
     CU(rs->off8.alloc(o8.size(), st));
     CU(rs->words.alloc((size_t)words_total + 1, st));
@@ -274,7 +256,7 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         CU(cudaMemcpyAsync(d_src_off.p, src_off.data(), (size_t)n_refs * 8, cudaMemcpyHostToDevice, st));
     }
     CU(cudaMemcpyAsync(rs->blk_off.p, blk_off.data(), ((size_t)n_refs + 1) * 8, cudaMemcpyHostToDevice, st));
-    if (total) seq_encode_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw.p, total, d_tab.p, rs->codes8.p, nullptr);
+    if (total) seq_encode_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw, total, d_tab.p, rs->codes8.p, nullptr);
     CU(cudaMemsetAsync(rs->words.p + words_total, 0, 4, st));
     if (words_total && rs->two_bit_ok)
         ref_pack_kernel<<<grid_for((int64_t)words_total, 256, ctx->sm_count), 256, 0, st>>>(rs->codes8.p, d_src_off.p, rs->len.p, rs->word_off.p,
@@ -282,8 +264,89 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
     else if (words_total) CU(cudaMemsetAsync(rs->words.p, 0, (size_t)words_total * 4, st));
     CU(cudaGetLastError());
     CU(cudaStreamSynchronize(st));                 // the host tables above are locals
-    ctx->live.fetch_add(1);
     *out = rs.release();
+    return SWB_OK;
+}
+
+// how many parts a set of `total_bases` is cut into: a part should hold about 96 read pairs' block records
+// (74 bytes per base and read pair) in the workspace, so that a typical call is one batch per part
+static int part_count(const swb_ctx *ctx, int64_t total_bases, int64_t n_refs)
+{
+    static const int env_parts = getenv("SWB_REF_PARTS") ? atoi(getenv("SWB_REF_PARTS")) : 0;
+    if (env_parts > 0) return (int)std::min<int64_t>(env_parts, std::max<int64_t>(n_refs, 1));
+    const double part_bases = (double)ctx->ws_bytes / (74.0 * 96.0);
+    const int s = (int)((double)total_bases / std::max(part_bases, 1.0) + 0.5);
+    return (int)std::min<int64_t>(std::max(1, std::min(s, 8)), std::max<int64_t>(n_refs, 1));
+}
+
+int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64_t *offsets, swb_refset **out)
+{
+    if (!ctx || !out) return fail(SWB_E_INVALID, "swb_refset_load: null argument");
+    *out = nullptr;
+    int rc = check_offsets("swb_refset_load", n_refs, bytes, offsets);
+    if (rc) return rc;
+    if (n_refs > (int64_t)1 << 30) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: more than 2^30 references");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    for (int64_t k = 0; k < n_refs; ++k)
+        if (offsets[k + 1] - offsets[k] >= ((int64_t)1 << KEY_J_BITS))
+            return fail(SWB_E_UNSUPPORTED, "swb_refset_load: reference longer than 4,194,303 bases");
+    // ---- raw bytes to the device; symbols present and the non-ASCII check there ----------------------
+    const int64_t total = offsets[n_refs] - offsets[0];
+    DevBuf<uint8_t> d_raw;
+    DevBuf<uint32_t> d_flags;                                      // [0..3] presence mask, [4] non-ASCII seen
+    CU(d_raw.alloc((size_t)total + 16, st));
+    CU(d_flags.alloc(8, st));
+    CU(cudaMemsetAsync(d_flags.p, 0, 32, st));
+    if (total) CU(cudaMemcpyAsync(d_raw.p, bytes + offsets[0], (size_t)total, cudaMemcpyHostToDevice, st));
+    if (total) seq_scan_kernel<<<grid_for(total, 256, ctx->sm_count), 256, 0, st>>>(d_raw.p, total, d_flags.p, d_flags.p + 4);
+    CU(cudaGetLastError());
+    uint32_t h_flags[8] = {0};
+    CU(cudaMemcpyAsync(h_flags, d_flags.p, 32, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    if (h_flags[4]) return fail(SWB_E_UNSUPPORTED, "swb_refset_load: non-ASCII byte in a reference");
+    uint8_t code_of[128];
+    int n_symbols = 0;
+    memset(code_of, 0xFF, sizeof code_of);
+    for (int c = 0; c < 128; ++c)
+        if ((h_flags[c >> 5] >> (c & 31)) & 1u) code_of[c] = (uint8_t)n_symbols++;
+
+    const int S = part_count(ctx, total, n_refs);
+    swb_refset *rs = nullptr;
+    if (S <= 1) {
+        rc = build_leaf(ctx, n_refs, offsets, d_raw.p, code_of, n_symbols, &rs);
+        if (rc) return rc;
+    } else {
+        // parts of equal base counts, cut at reference boundaries
+        std::unique_ptr<swb_refset> parent(new swb_refset());
+        parent->ctx = ctx; parent->n_refs = n_refs; parent->total_bases = total;
+        parent->n_symbols = n_symbols; parent->two_bit_ok = n_symbols <= 4;
+        memcpy(parent->code_of, code_of, sizeof code_of);
+        parent->len_orig.resize((size_t)n_refs);
+        for (int64_t k = 0; k < n_refs; ++k) {
+            parent->len_orig[(size_t)k] = (int32_t)(offsets[k + 1] - offsets[k]);
+            parent->max_len = std::max(parent->max_len, parent->len_orig[(size_t)k]);
+        }
+        auto drop = [&] { for (swb_refset *q : parent->parts) delete q; parent->parts.clear(); };
+        int64_t r0 = 0;
+        for (int k = 0; k < S && r0 < n_refs; ++k) {
+            const int64_t goal = offsets[0] + (total * (k + 1)) / S;
+            int64_t r1 = r0 + 1;
+            while (r1 < n_refs && (k == S - 1 || offsets[r1] < goal)) ++r1;
+            if (k == S - 1) r1 = n_refs;
+            swb_refset *leaf = nullptr;
+            rc = build_leaf(ctx, r1 - r0, offsets + r0, d_raw.p + (offsets[r0] - offsets[0]), code_of, n_symbols, &leaf);
+            if (rc) { drop(); return rc; }
+            leaf->parent = parent.get();
+            parent->parts.push_back(leaf);
+            parent->part_first.push_back(r0);
+            r0 = r1;
+        }
+        rs = parent.release();
+    }
+    ctx->live.fetch_add(1);
+    *out = rs;
     return SWB_OK;
 }
 
@@ -292,6 +355,7 @@ void swb_refset_free(swb_refset *rs)
     if (!rs) return;
     swb_ctx *c = rs->ctx;
     cudaSetDevice(c->device);
+    for (swb_refset *q : rs->parts) delete q;
     delete rs;
     ctx_handle_released(c);
 }
@@ -402,12 +466,14 @@ static int pick_k(int m)
     return 0;
 }
 
-int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, int32_t match, int32_t mismatch,
-                       int32_t gap, uint32_t flags, swb_result **out)
+// One packed set (a whole small set, or one part of a large one).  ext_scores / ext_totals: rows of the parent's
+// score matrix / totals this part writes into (nullptr: own arrays).
+static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, int32_t match, int32_t mismatch,
+                      int32_t gap, uint32_t flags, int32_t *ext_scores, int32_t *ext_totals, swb_result **out)
 {
     if (!ctx || !rs || !rd || !out) return fail(SWB_E_INVALID, "swb_align: null argument");
     *out = nullptr;
-    if (rd->rs != rs) return fail(SWB_E_INVALID, "swb_align: reads were encoded against a different reference set");
+    if (rd->rs != rs && rd->rs != rs->parent) return fail(SWB_E_INVALID, "swb_align: reads were encoded against a different reference set");
     if (rs->ctx != ctx || rd->ctx != ctx) return fail(SWB_E_INVALID, "swb_align: handles belong to another context");
     const int64_t n_refs = rs->n_refs, n_reads = rd->n_reads;
     if (n_refs * n_reads >= ((int64_t)1 << 33)) return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^33 pairs per call");
@@ -438,8 +504,8 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     res->ctx = ctx; res->n_refs = n_refs; res->n_reads = n_reads; res->flags = flags;
     res->ref_len = rs->len_orig; res->read_len = rd->len;
     const size_t n_pairs = (size_t)(n_refs * n_reads);
-    CU(res->d_scores.alloc(n_pairs, st));
-    CU(res->d_totals.alloc((size_t)n_refs, st));
+    if (ext_scores) res->d_scores.view(ext_scores, n_pairs); else CU(res->d_scores.alloc(n_pairs, st));
+    if (ext_totals) res->d_totals.view(ext_totals, (size_t)n_refs); else CU(res->d_totals.alloc((size_t)n_refs, st));
     CU(res->d_best.alloc((size_t)n_reads * 4, st));
     CU(cudaMemsetAsync(res->d_scores.p, 0, std::max<size_t>(n_pairs, 1) * 4, st));
 
@@ -499,17 +565,28 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
             std::stable_sort(idx.begin(), idx.end(),
                              [&](int32_t a, int32_t b) { return rd->len[(size_t)a] > rd->len[(size_t)b]; });
             const int64_t n_rp_total = ((int64_t)idx.size() + 1) / 2;
-            Segments segs;
-            make_segments(rs, K, match, mismatch, gap, n_rp_total, ctx->sm_count, segs);
-            const size_t nv = segs.ref.size();
-            CU(ctx->v_ref.reserve(nv, st)); CU(ctx->v_c0.reserve(nv, st)); CU(ctx->v_len.reserve(nv, st));
-            CU(ctx->v_skip.reserve(nv, st)); CU(ctx->v_end.reserve(nv, st));
-            CU(cudaMemcpyAsync(ctx->v_ref.p, segs.ref.data(), nv * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(ctx->v_c0.p, segs.c0.data(), nv * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(ctx->v_len.p, segs.len.data(), nv * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(ctx->v_skip.p, segs.skip.data(), nv * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaMemcpyAsync(ctx->v_end.p, segs.end.data(), nv * 4, cudaMemcpyHostToDevice, st));
-            CU(cudaStreamSynchronize(st));         // segs is a local
+            // the segment tables only depend on (K, scores, few-items flag): built once per reference set and kept on the device
+            const bool few_items = n_rp_total * ((rs->n_refs + 3) / 4) < (int64_t)ctx->sm_count * 24;
+            const swb_refset::SegKey skey{K, match, mismatch, gap, few_items ? 1 : 0};
+            auto sit = rs->seg_cache.find(skey);
+            if (sit == rs->seg_cache.end()) {
+                Segments segs;
+                make_segments(rs, K, match, mismatch, gap, n_rp_total, ctx->sm_count, segs);
+                auto sc = std::make_shared<swb_refset::SegTables>();
+                sc->nv = segs.ref.size();
+                CU(sc->ref.alloc(sc->nv, st)); CU(sc->c0.alloc(sc->nv, st)); CU(sc->len.alloc(sc->nv, st));
+                CU(sc->skip.alloc(sc->nv, st)); CU(sc->end.alloc(sc->nv, st));
+                CU(cudaMemcpyAsync(sc->ref.p, segs.ref.data(), sc->nv * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(sc->c0.p, segs.c0.data(), sc->nv * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(sc->len.p, segs.len.data(), sc->nv * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(sc->skip.p, segs.skip.data(), sc->nv * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaMemcpyAsync(sc->end.p, segs.end.data(), sc->nv * 4, cudaMemcpyHostToDevice, st));
+                CU(cudaStreamSynchronize(st));         // segs is a local
+                if (rs->seg_cache.size() >= 16) rs->seg_cache.clear();
+                sit = rs->seg_cache.emplace(skey, sc).first;
+            }
+            const std::shared_ptr<swb_refset::SegTables> segt = sit->second;
+            const size_t nv = segt->nv;
             // ---- batches of read pairs, two-stage pipeline on two streams -----------------------------
             // stage F (ctx->stream_fill): fill of batch k+1;  stage T (ctx->stream): flag/locate/sort/trace of
             // batch k.  The fill saturates the integer pipe, the traceback is latency-bound: run together they
@@ -559,8 +636,8 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
                 P.ref_words = rs->words.p; P.ref_word_off = rs->word_off.p; P.ref_len = rs->len.p;
                 P.ref_orig = rs->orig.p; P.ref_sorted_of = rs->sorted_of.p; P.ref_blk_off = rs->blk_off.p;
                 P.n_refs = (int32_t)n_refs; P.blocks_per_rp = rs->blocks_per_rp;
-                P.v_ref = ctx->v_ref.p; P.v_c0 = ctx->v_c0.p; P.v_len = ctx->v_len.p; P.v_skip = ctx->v_skip.p;
-                P.v_end = ctx->v_end.p; P.n_vrefs = (int32_t)nv;
+                P.v_ref = segt->ref.p; P.v_c0 = segt->c0.p; P.v_len = segt->len.p; P.v_skip = segt->skip.p;
+                P.v_end = segt->end.p; P.n_vrefs = (int32_t)nv;
                 P.read_codes = rd->codes.p; P.read_off = rd->off.p; P.rp_reads = rpb.p; P.read_slot = nullptr;
                 P.n_rp = S.n_rp; P.n_reads = n_reads;
                 P.match = match; P.mismatch = mismatch; P.gap = gap; P.tie_gt = (flags & SWB_F_TIE_GT) ? 1 : 0;
@@ -776,6 +853,185 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     return SWB_OK;
 }
 
+namespace {
+
+__global__ void add_base_kernel(int64_t *a, int64_t n, int64_t base)
+{
+    for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < n; k += (int64_t)gridDim.x * blockDim.x) a[k] += base;
+}
+
+// best = better(best, part's best with its reference index moved to the global numbering): highest score, lowest reference
+__global__ void fold_best_kernel(int32_t *best, const int32_t *part, int64_t n_reads, int32_t first, int is_first)
+{
+    const int64_t q = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (q >= n_reads) return;
+    int4 b = reinterpret_cast<const int4 *>(part)[q];
+    if (b.y >= 0) b.y += first;
+    if (!is_first) {
+        const int4 a = reinterpret_cast<const int4 *>(best)[q];
+        if (a.y >= 0 && (b.y < 0 || a.x >= b.x)) b = a;            // parts come in ascending reference order: ties keep the earlier
+    }
+    reinterpret_cast<int4 *>(best)[q] = b;
+}
+
+// grows a pinned host array, keeping its first `used` bytes (the parts copied so far)
+int pin_ensure(swb_ctx *ctx, swb_ctx::PinBuf &b, size_t need, size_t used, size_t want)
+{
+    if (b.p && b.bytes >= need) return SWB_OK;
+    if (used) CU(cudaStreamSynchronize(ctx->stream_copy));
+    swb_ctx::PinBuf nb = ctx->pin_get(std::max<size_t>(std::max(need, want), 16));
+    if (!nb.p) return fail(SWB_E_NOMEM, "swb_align: pinned host allocation failed");
+    if (used && b.p) memcpy(nb.p, b.p, used);
+    ctx->pin_put(b);
+    b = nb;
+    return SWB_OK;
+}
+
+// part k of a multi-part result -> its segment of the host arrays, on the copy stream (the compute stream goes on)
+int copy_part(swb_result *res, size_t k)
+{
+    swb_ctx *ctx = res->ctx;
+    swb_result *sub = res->subs[k];
+    cudaStream_t sc = ctx->stream_copy;
+    const size_t S = res->subs.size();
+    const int64_t first = res->sub_first[k];
+    const size_t np_k = (size_t)(sub->n_refs * sub->n_reads), N_k = sub->total_cells;
+    const size_t n_pairs = (size_t)(res->n_refs * res->n_reads);
+    const size_t cb = (size_t)res->cells_done, wb = (size_t)res->words_done;
+    // capacity guess after the first part: the parts hold equal base counts
+    const size_t wantN = (size_t)((double)(cb + N_k) * (double)S / (double)(k + 1) * 1.15) + 1024;
+    const size_t wantW = (size_t)((double)(wb + (size_t)sub->total_words) * (double)S / (double)(k + 1) * 1.15) + 1024;
+    int rc;
+    if ((rc = pin_ensure(ctx, res->h_cell_off, (n_pairs + 1) * 8, 0, 0))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_cells, (cb + N_k) * 8, cb * 8, wantN * 8))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_beg, (cb + N_k) * 4, cb * 4, wantN * 4))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_len, (cb + N_k) * 4, cb * 4, wantN * 4))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_ops_off, (cb + N_k + 1) * 8, cb * 8, (wantN + 1) * 8))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_ops, (wb + (size_t)sub->total_words) * 4, wb * 4, wantW * 4))) return rc;
+    cudaEvent_t ev;
+    CU(ctx->next_event(&ev));
+    CU(cudaEventRecord(ev, ctx->stream));
+    CU(cudaStreamWaitEvent(sc, ev, 0));
+    if (np_k) {
+        if (cb) add_base_kernel<<<grid_for((int64_t)np_k, 256, ctx->sm_count), 256, 0, sc>>>(sub->f_cell_off.p, (int64_t)np_k, (int64_t)cb);
+        CU(cudaMemcpyAsync((int64_t *)res->h_cell_off.p + (size_t)first * (size_t)res->n_reads, sub->f_cell_off.p, np_k * 8, cudaMemcpyDeviceToHost, sc));
+    }
+    if (N_k) {
+        if (wb) add_base_kernel<<<grid_for((int64_t)N_k, 256, ctx->sm_count), 256, 0, sc>>>(sub->f_ops_off.p, (int64_t)N_k, (int64_t)wb);
+        CU(cudaMemcpyAsync((int32_t *)res->h_cells.p + cb * 2, sub->f_cells.p, N_k * 8, cudaMemcpyDeviceToHost, sc));
+        CU(cudaMemcpyAsync((int32_t *)res->h_beg.p + cb, sub->f_beg.p, N_k * 4, cudaMemcpyDeviceToHost, sc));
+        CU(cudaMemcpyAsync((int32_t *)res->h_len.p + cb, sub->f_len.p, N_k * 4, cudaMemcpyDeviceToHost, sc));
+        CU(cudaMemcpyAsync((int64_t *)res->h_ops_off.p + cb, sub->f_ops_off.p, N_k * 8, cudaMemcpyDeviceToHost, sc));
+        if (sub->total_words)
+            CU(cudaMemcpyAsync((uint32_t *)res->h_ops.p + wb, sub->f_ops.p, (size_t)sub->total_words * 4, cudaMemcpyDeviceToHost, sc));
+    }
+    CU(cudaGetLastError());
+    res->cells_done += N_k;
+    res->words_done += sub->total_words;
+    res->sub_copied[k] = 1;
+    return SWB_OK;
+}
+
+// the arrays that are only complete after the last part, the closing entries, and the host views
+int finish_parts_fetch(swb_result *res)
+{
+    swb_ctx *ctx = res->ctx;
+    cudaStream_t sc = ctx->stream_copy;
+    const bool full = !(res->flags & SWB_F_SCORES_ONLY);
+    const size_t n_pairs = (size_t)(res->n_refs * res->n_reads);
+    int rc;
+    if (full)
+        for (size_t k = 0; k < res->subs.size(); ++k)
+            if (!res->sub_copied[k] && (rc = copy_part(res, k))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_scores, std::max<size_t>(n_pairs, 1) * 4, 0, 0))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_totals, std::max<size_t>((size_t)res->n_refs, 1) * 4, 0, 0))) return rc;
+    if ((rc = pin_ensure(ctx, res->h_best, std::max<size_t>((size_t)res->n_reads, 1) * 16, 0, 0))) return rc;
+    cudaEvent_t ev;
+    CU(ctx->next_event(&ev));
+    CU(cudaEventRecord(ev, ctx->stream));
+    CU(cudaStreamWaitEvent(sc, ev, 0));
+    CU(cudaEventRecord(ctx->ev[0], sc));
+    if (n_pairs) CU(cudaMemcpyAsync(res->h_scores.p, res->d_scores.p, n_pairs * 4, cudaMemcpyDeviceToHost, sc));
+    if (res->n_refs) CU(cudaMemcpyAsync(res->h_totals.p, res->d_totals.p, (size_t)res->n_refs * 4, cudaMemcpyDeviceToHost, sc));
+    if (res->n_reads) CU(cudaMemcpyAsync(res->h_best.p, res->d_best.p, (size_t)res->n_reads * 16, cudaMemcpyDeviceToHost, sc));
+    CU(cudaEventRecord(ctx->ev[1], sc));
+    CU(cudaStreamSynchronize(sc));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]);
+    res->stats[4] = ms;                                           // what was left to copy after the last part's compute
+    res->scores = (const int32_t *)res->h_scores.p; res->totals = (const int32_t *)res->h_totals.p;
+    res->best = (const int32_t *)res->h_best.p;
+    if (full) {
+        if ((rc = pin_ensure(ctx, res->h_cell_off, (n_pairs + 1) * 8, 0, 0))) return rc;
+        if ((rc = pin_ensure(ctx, res->h_ops_off, ((size_t)res->cells_done + 1) * 8, (size_t)res->cells_done * 8, 0))) return rc;
+        ((int64_t *)res->h_cell_off.p)[n_pairs] = (int64_t)res->cells_done;
+        ((int64_t *)res->h_ops_off.p)[res->cells_done] = res->words_done;
+        res->cell_off = (const int64_t *)res->h_cell_off.p; res->cells = (const int32_t *)res->h_cells.p;
+        res->beginnings = (const int32_t *)res->h_beg.p; res->op_lens = (const int32_t *)res->h_len.p;
+        res->ops_off = (const int64_t *)res->h_ops_off.p; res->ops = (const uint32_t *)res->h_ops.p;
+        res->total_cells = (uint32_t)res->cells_done; res->total_words = res->words_done;
+    }
+    res->fetched = true;
+    return SWB_OK;
+}
+
+}  // namespace
+
+int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, int32_t match, int32_t mismatch,
+                       int32_t gap, uint32_t flags, swb_result **out)
+{
+    if (!ctx || !rs || !rd || !out) return fail(SWB_E_INVALID, "swb_align: null argument");
+    *out = nullptr;
+    if (rs->parent) return fail(SWB_E_INVALID, "swb_align: a part of a reference set is not a handle");
+    if (rs->parts.empty()) return align_leaf(ctx, rs, rd, match, mismatch, gap, flags, nullptr, nullptr, out);
+    // ---- a set of several parts: part by part; part k's results cross PCIe while part k + 1 computes -------------
+    if (rd->rs != rs) return fail(SWB_E_INVALID, "swb_align: reads were encoded against a different reference set");
+    if (rs->ctx != ctx || rd->ctx != ctx) return fail(SWB_E_INVALID, "swb_align: handles belong to another context");
+    const int64_t n_refs = rs->n_refs, n_reads = rd->n_reads;
+    if (n_refs * n_reads >= ((int64_t)1 << 33)) return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^33 pairs per call");
+    std::lock_guard<std::recursive_mutex> lk(ctx->mu);
+    CU(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const auto t_wall0 = std::chrono::steady_clock::now();
+    auto res_del = [](swb_result *r) { swb_result_free(r); };
+    std::unique_ptr<swb_result, decltype(res_del)> res(new swb_result(), res_del);
+    ctx->live.fetch_add(1);
+    res->ctx = ctx; res->n_refs = n_refs; res->n_reads = n_reads; res->flags = flags;
+    res->ref_len = rs->len_orig; res->read_len = rd->len;
+    const size_t n_pairs = (size_t)(n_refs * n_reads);
+    CU(res->d_scores.alloc(n_pairs, st));
+    CU(res->d_totals.alloc((size_t)n_refs, st));
+    CU(res->d_best.alloc((size_t)n_reads * 4, st));
+    const bool full = !(flags & SWB_F_SCORES_ONLY), fetch_now = !(flags & SWB_F_NO_FETCH);
+    const int threads = 256;
+    for (size_t k = 0; k < rs->parts.size(); ++k) {
+        const swb_refset *part = rs->parts[k];
+        const int64_t first = rs->part_first[k];
+        swb_result *sub = nullptr;
+        const int rc = align_leaf(ctx, part, rd, match, mismatch, gap, flags | SWB_F_NO_FETCH, res->d_scores.p + (size_t)first * (size_t)n_reads,
+                                  res->d_totals.p + first, &sub);
+        if (rc) return rc;
+        res->subs.push_back(sub); res->sub_first.push_back(first); res->sub_copied.push_back(0);
+        for (int x : {1, 2, 3, 8, 9, 10, 11}) res->stats[x] += sub->stats[x];
+        if ((uint64_t)res->cells_done + sub->total_cells >= ((uint64_t)1 << 31) || res->total_cells + (uint64_t)sub->total_cells >= ((uint64_t)1 << 31))
+            return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^31 max cells in one call");
+        res->total_cells += sub->total_cells; res->total_words += sub->total_words;
+        if (n_reads)
+            fold_best_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(res->d_best.p, sub->d_best.p, n_reads, (int32_t)first, k == 0);
+        CU(cudaGetLastError());
+        if (fetch_now && full) { const int rc2 = copy_part(res.get(), k); if (rc2) return rc2; }
+    }
+    CU(cudaStreamSynchronize(st));
+    int64_t read_bases = 0;
+    for (int32_t m : rd->len) read_bases += m;
+    res->stats[6] = (double)rs->total_bases * (double)read_bases;
+    res->stats[7] = (double)n_refs * (double)n_reads;
+    if (fetch_now) { const int rc = finish_parts_fetch(res.get()); if (rc) return rc; }
+    res->stats[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
+    *out = res.release();
+    return SWB_OK;
+}
+
 int swb_align(swb_ctx *ctx, const swb_refset *rs, int64_t n_reads, const char *read_bytes, const int64_t *read_offsets,
               int32_t match, int32_t mismatch, int32_t gap, uint32_t flags, swb_result **out)
 {
@@ -807,6 +1063,7 @@ int swb_result_fetch(swb_result *res)
     swb_ctx *ctx = res->ctx;
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);
     CU(cudaSetDevice(ctx->device));
+    if (!res->subs.empty()) return finish_parts_fetch(res);
     cudaStream_t st = ctx->stream;
     CU(cudaEventRecord(ctx->ev[0], st));
     const size_t n_pairs = (size_t)(res->n_refs * res->n_reads);
@@ -847,9 +1104,13 @@ void swb_result_free(swb_result *res)
     if (!res) return;
     swb_ctx *c = res->ctx;
     cudaSetDevice(c->device);
+    if (!res->subs.empty()) cudaStreamSynchronize(c->stream_copy);       // the parts' arrays may still be on their way
+    for (swb_result *sub : res->subs) swb_result_free(sub);
     {
         std::lock_guard<std::recursive_mutex> lk(c->mu);
         for (auto &b : res->pins) c->pin_put(b);
+        for (swb_ctx::PinBuf *b : {&res->h_scores, &res->h_totals, &res->h_best, &res->h_cell_off, &res->h_cells, &res->h_beg,
+                                   &res->h_len, &res->h_ops_off, &res->h_ops}) { c->pin_put(*b); b->p = nullptr; b->bytes = 0; }
     }
     delete res;
     ctx_handle_released(c);

@@ -4,6 +4,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <map>
+#include <tuple>
 #include <cstdio>
 #include <cstring>
 #include <memory>
@@ -31,13 +33,15 @@ inline int cuda_fail(cudaError_t e, const char *what)
 // synchronising cudaMalloc/cudaFree.
 template <class T> struct DevBuf {
     T *p = nullptr; size_t n = 0; cudaStream_t st = nullptr;
+    bool owned = true;                          // false: a view into somebody else's allocation
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
-    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st) { o.p = nullptr; o.n = 0; }
-    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; o.p = nullptr; o.n = 0; } return *this; }
+    DevBuf(DevBuf &&o) noexcept : p(o.p), n(o.n), st(o.st), owned(o.owned) { o.p = nullptr; o.n = 0; o.owned = true; }
+    DevBuf &operator=(DevBuf &&o) noexcept { if (this != &o) { release(); p = o.p; n = o.n; st = o.st; owned = o.owned; o.p = nullptr; o.n = 0; o.owned = true; } return *this; }
     ~DevBuf() { release(); }
-    void release() { if (p) cudaFreeAsync(p, st); p = nullptr; n = 0; }
+    void release() { if (p && owned) cudaFreeAsync(p, st); p = nullptr; n = 0; owned = true; }
+    void view(T *ptr, size_t count) { release(); p = ptr; n = count; owned = false; }
     cudaError_t alloc(size_t count, cudaStream_t stream)
     {
         release();
@@ -64,6 +68,7 @@ struct swb_ctx {
     int64_t ws_bytes = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t stream_fill = nullptr;         // second stream: fill of batch k+1 runs beside the traceback of batch k
+    cudaStream_t stream_copy = nullptr;         // results of reference part k cross PCIe while part k+1 computes
     bool pipeline = true;
     DevBuf<uint32_t> ck2[2], tmx2[2];           // ping-pong checkpoint workspaces
     DevBuf<int32_t> rp2[2];
@@ -131,6 +136,21 @@ struct swb_refset {
     DevBuf<uint32_t> words, word_off;
     DevBuf<int32_t> len, orig, sorted_of;
     DevBuf<int64_t> blk_off;
+    // A large set is cut into PARTS: contiguous ranges of the caller's reference indices, each a complete packed set
+    // of its own.  An align call walks the parts in order; the results of part k are a contiguous segment of every
+    // ABI array (pair = ref * n_reads + read), so they cross PCIe while part k + 1 computes.  The parent keeps the
+    // alphabet, the lengths and the totals; `parts` is empty for a part (and for a set small enough to be one).
+    // fill work units (reference segments, make_segments) per (K, scores): device tables built on first use.  Guarded by
+    // the context mutex like every align call.
+    struct SegKey {
+        int K, match, mismatch, gap, few;
+        bool operator<(const SegKey &o) const { return std::tie(K, match, mismatch, gap, few) < std::tie(o.K, o.match, o.mismatch, o.gap, o.few); }
+    };
+    struct SegTables { size_t nv = 0; DevBuf<int32_t> ref, c0, len, skip, end; };
+    mutable std::map<SegKey, std::shared_ptr<SegTables>> seg_cache;
+    std::vector<swb_refset *> parts;
+    std::vector<int64_t> part_first;            // first global reference index of each part
+    const swb_refset *parent = nullptr;
 };
 
 struct swb_reads {
@@ -177,6 +197,13 @@ struct swb_result {
     const int32_t *cells = nullptr, *beginnings = nullptr, *op_lens = nullptr;
     const uint32_t *ops = nullptr;
     double stats[12] = {0};
+    // result of a multi-part reference set: one sub-result per part (device arrays), stitched into the host arrays
+    std::vector<swb_result *> subs;
+    std::vector<int64_t> sub_first;
+    std::vector<char> sub_copied;               // part k's arrays are already on their way to the host buffers
+    swb_ctx::PinBuf h_scores, h_totals, h_best, h_cell_off, h_cells, h_beg, h_len, h_ops_off, h_ops;
+    uint64_t cells_done = 0;                    // cells / words of the parts copied so far
+    int64_t words_done = 0;
 };
 
 
