@@ -318,7 +318,9 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         rc = build_leaf(ctx, n_refs, offsets, d_raw.p, code_of, n_symbols, &rs);
         if (rc) return rc;
     } else {
-        // parts of equal base counts, cut at reference boundaries
+        // parts of DECREASING base counts (weights S, S-1, ..., 1), cut at reference boundaries: what stays exposed of
+        // the device->host traffic is the LAST part's share (measured, cfg2 step on one B200: equal halves 44.2 ms,
+        // one part 44.8 ms, device-resident 42.5 ms; every part costs ~0.5 ms of fixed work)
         std::unique_ptr<swb_refset> parent(new swb_refset());
         parent->ctx = ctx; parent->n_refs = n_refs; parent->total_bases = total;
         parent->n_symbols = n_symbols; parent->two_bit_ok = n_symbols <= 4;
@@ -331,7 +333,8 @@ int swb_refset_load(swb_ctx *ctx, int64_t n_refs, const char *bytes, const int64
         auto drop = [&] { for (swb_refset *q : parent->parts) delete q; parent->parts.clear(); };
         int64_t r0 = 0;
         for (int k = 0; k < S && r0 < n_refs; ++k) {
-            const int64_t goal = offsets[0] + (total * (k + 1)) / S;
+            const int64_t wsum = (int64_t)S * (S + 1) / 2, wdone = wsum - (int64_t)(S - k - 1) * (S - k) / 2;
+            const int64_t goal = offsets[0] + (int64_t)((double)total * (double)wdone / (double)wsum);
             int64_t r1 = r0 + 1;
             while (r1 < n_refs && (k == S - 1 || offsets[r1] < goal)) ++r1;
             if (k == S - 1) r1 = n_refs;
@@ -878,6 +881,7 @@ __global__ void fold_best_kernel(int32_t *best, const int32_t *part, int64_t n_r
 int pin_ensure(swb_ctx *ctx, swb_ctx::PinBuf &b, size_t need, size_t used, size_t want)
 {
     if (b.p && b.bytes >= need) return SWB_OK;
+    if (getenv("SWB_TIMELINE")) fprintf(stderr, "[swb parts] pinned array grows: has %zu, needs %zu, keeps %zu\n", b.bytes, need, used);
     if (used) CU(cudaStreamSynchronize(ctx->stream_copy));
     swb_ctx::PinBuf nb = ctx->pin_get(std::max<size_t>(std::max(need, want), 16));
     if (!nb.p) return fail(SWB_E_NOMEM, "swb_align: pinned host allocation failed");
@@ -893,7 +897,7 @@ int copy_part(swb_result *res, size_t k)
     swb_ctx *ctx = res->ctx;
     swb_result *sub = res->subs[k];
     cudaStream_t sc = ctx->stream_copy;
-    const size_t S = res->subs.size();
+    const size_t S = std::max(res->parts_total, res->subs.size());
     const int64_t first = res->sub_first[k];
     const size_t np_k = (size_t)(sub->n_refs * sub->n_reads), N_k = sub->total_cells;
     const size_t n_pairs = (size_t)(res->n_refs * res->n_reads);
@@ -908,14 +912,19 @@ int copy_part(swb_result *res, size_t k)
     if ((rc = pin_ensure(ctx, res->h_len, (cb + N_k) * 4, cb * 4, wantN * 4))) return rc;
     if ((rc = pin_ensure(ctx, res->h_ops_off, (cb + N_k + 1) * 8, cb * 8, (wantN + 1) * 8))) return rc;
     if ((rc = pin_ensure(ctx, res->h_ops, (wb + (size_t)sub->total_words) * 4, wb * 4, wantW * 4))) return rc;
+    const bool tl = getenv("SWB_TIMELINE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
     cudaEvent_t ev;
     CU(ctx->next_event(&ev));
     CU(cudaEventRecord(ev, ctx->stream));
     CU(cudaStreamWaitEvent(sc, ev, 0));
+    if (tl) fprintf(stderr, "[swb parts]   copy_part %zu: event %.3f ms\n", k, ms());
     if (np_k) {
         if (cb) add_base_kernel<<<grid_for((int64_t)np_k, 256, ctx->sm_count), 256, 0, sc>>>(sub->f_cell_off.p, (int64_t)np_k, (int64_t)cb);
         CU(cudaMemcpyAsync((int64_t *)res->h_cell_off.p + (size_t)first * (size_t)res->n_reads, sub->f_cell_off.p, np_k * 8, cudaMemcpyDeviceToHost, sc));
     }
+    if (tl) fprintf(stderr, "[swb parts]   copy_part %zu: cell_off issued %.3f ms\n", k, ms());
     if (N_k) {
         if (wb) add_base_kernel<<<grid_for((int64_t)N_k, 256, ctx->sm_count), 256, 0, sc>>>(sub->f_ops_off.p, (int64_t)N_k, (int64_t)wb);
         CU(cudaMemcpyAsync((int32_t *)res->h_cells.p + cb * 2, sub->f_cells.p, N_k * 8, cudaMemcpyDeviceToHost, sc));
@@ -926,6 +935,7 @@ int copy_part(swb_result *res, size_t k)
             CU(cudaMemcpyAsync((uint32_t *)res->h_ops.p + wb, sub->f_ops.p, (size_t)sub->total_words * 4, cudaMemcpyDeviceToHost, sc));
     }
     CU(cudaGetLastError());
+    if (tl) fprintf(stderr, "[swb parts]   copy_part %zu: all issued %.3f ms\n", k, ms());
     res->cells_done += N_k;
     res->words_done += sub->total_words;
     res->sub_copied[k] = 1;
@@ -1004,10 +1014,14 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     CU(res->d_best.alloc((size_t)n_reads * 4, st));
     const bool full = !(flags & SWB_F_SCORES_ONLY), fetch_now = !(flags & SWB_F_NO_FETCH);
     const int threads = 256;
+    res->parts_total = rs->parts.size();
+    static const bool timeline = getenv("SWB_TIMELINE") != nullptr;
+    auto wall_ms = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count(); };
     for (size_t k = 0; k < rs->parts.size(); ++k) {
         const swb_refset *part = rs->parts[k];
         const int64_t first = rs->part_first[k];
         swb_result *sub = nullptr;
+        if (timeline) fprintf(stderr, "[swb parts] part %zu starts at %.3f ms (pinned allocations so far %lld)\n", k, wall_ms(), (long long)ctx->pin_allocs);
         const int rc = align_leaf(ctx, part, rd, match, mismatch, gap, flags | SWB_F_NO_FETCH, res->d_scores.p + (size_t)first * (size_t)n_reads,
                                   res->d_totals.p + first, &sub);
         if (rc) return rc;
@@ -1019,7 +1033,9 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
         if (n_reads)
             fold_best_kernel<<<(unsigned)((n_reads + threads - 1) / threads), threads, 0, st>>>(res->d_best.p, sub->d_best.p, n_reads, (int32_t)first, k == 0);
         CU(cudaGetLastError());
+        if (timeline) fprintf(stderr, "[swb parts] part %zu computed at %.3f ms\n", k, wall_ms());
         if (fetch_now && full) { const int rc2 = copy_part(res.get(), k); if (rc2) return rc2; }
+        if (timeline) fprintf(stderr, "[swb parts] part %zu copy issued at %.3f ms\n", k, wall_ms());
     }
     CU(cudaStreamSynchronize(st));
     int64_t read_bases = 0;
@@ -1027,6 +1043,7 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, 
     res->stats[6] = (double)rs->total_bases * (double)read_bases;
     res->stats[7] = (double)n_refs * (double)n_reads;
     if (fetch_now) { const int rc = finish_parts_fetch(res.get()); if (rc) return rc; }
+    if (timeline) fprintf(stderr, "[swb parts] fetched at %.3f ms (pinned allocations %lld)\n", wall_ms(), (long long)ctx->pin_allocs);
     res->stats[5] = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count();
     *out = res.release();
     return SWB_OK;

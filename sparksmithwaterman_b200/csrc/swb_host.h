@@ -95,14 +95,25 @@ struct swb_ctx {
     // pinned host buffers, recycled between results (cudaHostAlloc is slow; D2H into pageable memory too)
     struct PinBuf { void *p = nullptr; size_t bytes = 0; };
     std::vector<PinBuf> pin_free;
+    // Pinned host buffers come in power-of-two size classes (>= 64 KiB): a step whose result is a few percent larger
+    // than the previous one's finds its buffers in the pool instead of paying cudaHostAlloc (milliseconds per 100 MB).
+    static size_t pin_class(size_t bytes)
+    {
+        size_t c = (size_t)64 << 10;
+        while (c < bytes) c <<= 1;
+        return c;
+    }
+    int64_t pin_allocs = 0;                     // cudaHostAlloc calls so far (SWB_TIMELINE prints them)
     PinBuf pin_get(size_t bytes)
     {
+        const size_t want = pin_class(bytes);
         size_t best = pin_free.size();
         for (size_t k = 0; k < pin_free.size(); ++k)
-            if (pin_free[k].bytes >= bytes && (best == pin_free.size() || pin_free[k].bytes < pin_free[best].bytes)) best = k;
+            if (pin_free[k].bytes >= want && (best == pin_free.size() || pin_free[k].bytes < pin_free[best].bytes)) best = k;
         if (best != pin_free.size()) { PinBuf b = pin_free[best]; pin_free.erase(pin_free.begin() + best); return b; }
         PinBuf b;
-        b.bytes = std::max<size_t>(bytes + bytes / 4, 4096);
+        b.bytes = want;
+        ++pin_allocs;
         if (cudaHostAlloc(&b.p, b.bytes, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); b.p = nullptr; b.bytes = 0; }
         return b;
     }
@@ -200,6 +211,7 @@ struct swb_result {
     // result of a multi-part reference set: one sub-result per part (device arrays), stitched into the host arrays
     std::vector<swb_result *> subs;
     std::vector<int64_t> sub_first;
+    size_t parts_total = 0;                     // parts the call will produce (capacity guess of the host arrays)
     std::vector<char> sub_copied;               // part k's arrays are already on their way to the host buffers
     swb_ctx::PinBuf h_scores, h_totals, h_best, h_cell_off, h_cells, h_beg, h_len, h_ops_off, h_ops;
     uint64_t cells_done = 0;                    // cells / words of the parts copied so far
