@@ -97,6 +97,19 @@ int swb_align_resident(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd,
 int swb_result_fetch(swb_result *res);
 void swb_result_free(swb_result *res);
 
+/* ONE pair through the context's submission queue.
+ * Replaces: `new SmithWaterman.OptAlignments().call({ref, read}, {match, mismatch, gap}, types)` exactly as the
+ * UNCHANGED driver issues it -- once per pair, from N Spark task threads (Distribution.java:419-426, :593;
+ * operator SmithWaterman.java:62-92).  Thread-safe and meant to be called concurrently: calls that arrive while
+ * the device is busy are coalesced -- one of the waiting threads loads the distinct references of all queued
+ * requests (same scores and flags) as one set, their distinct reads as one batch, runs one align sequence and
+ * hands every caller its own 1 x 1 result (pair index 0; every swb_result_* accessor applies; free it with
+ * swb_result_free).  SWB_F_NO_FETCH is ignored: the result is always on the host. */
+int swb_align_pair(swb_ctx *ctx, const char *ref, int64_t ref_len, const char *read, int64_t read_len,
+                   int32_t match, int32_t mismatch, int32_t gap, uint32_t flags, swb_result **out);
+/* out[0] = swb_align_pair calls so far, out[1] = batches they were served in, out[2] = largest batch */
+int swb_queue_stats(swb_ctx *ctx, int64_t *out, int n);
+
 /* ---- result accessors (valid after fetch; pointers live until swb_result_free) ---- */
 int64_t swb_result_n_refs(const swb_result *res);
 int64_t swb_result_n_reads(const swb_result *res);
@@ -140,7 +153,7 @@ int swb_result_materialize(const swb_result *res, int64_t cell,
 /* timings of the call in milliseconds (CUDA events on the engine's stream) and counters:
  * out[0]=h2d  out[1]=fill  out[2]=locate+sort  out[3]=traceback  out[4]=d2h  out[5]=total device
  * out[6]=cells (sum m*n)  out[7]=pairs  out[8]=materialised max cells  out[9]=kernel launches
- * out[10]=checkpoint bytes written  out[11]=read batches */
+ * out[10]=checkpoint bytes written  out[11]=read batches (swb_align_pair: requests served by the pair's batch) */
 int swb_result_stats(const swb_result *res, double *out, int n);
 
 /* Device pointers of the HBM-resident outputs (for collectives over NVLink without a

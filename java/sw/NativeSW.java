@@ -33,6 +33,8 @@ final class NativeSW
 
 	// ---- align all reads x all references of the set --------------------------------------
 	static native long align( long ctx , long refset , byte[] readBytes , long[] readOffsets , int match , int mismatch , int gap , int flags ) ;
+	/** one pair through the native submission queue (swb_align_pair): concurrent calls are coalesced into one launch sequence */
+	static native long alignPair( long ctx , byte[] ref , byte[] read , int match , int mismatch , int gap , int flags ) ;
 	static native void resultFree( long result ) ;
 
 	// ---- result arrays ---------------------------------------------------------------------

@@ -16,9 +16,10 @@ import java.util.List ;
  * {@code Tuple2<maxScore, ArrayList<Tuple2<beginning, {refAln, readAln}>>>} (SmithWaterman.java:91).
  * Written fresh against include/swb200.h; NOT COMPILED in the build environment (no JDK there).
  *
- * Per-pair calls are legal but pay one native round trip each; the throughput path is
- * {@link #alignAll}, which the batched MapRef of java/sw/Distribution.java calls once per
- * reference file (all references x all reads in one launch sequence).
+ * Per-pair calls (the unchanged driver) go through the native submission queue, which coalesces the
+ * calls of concurrent task threads; the throughput path is {@link #alignAll}, which the batched MapRef
+ * of java/sw/Distribution.java calls once per reference file (all references x all reads in one launch
+ * sequence).
  */
 @SuppressWarnings( "serial" )
 public class SmithWaterman
@@ -29,7 +30,12 @@ public class SmithWaterman
 		@Override
 		public Tuple2<Integer,ArrayList<Tuple2<Integer,String[]>>> call( String[] seqs , int[] alignScores , char[] alignTypes )
 		{
-			return alignAll( Collections.singletonList(seqs[0]) , Collections.singletonList(seqs[1]) , alignScores , 0 ).get(0).get(0) ;
+			// one request to the native submission queue: the calls of concurrent Spark task threads (the unchanged
+			// MapRef, reference Distribution.java:419-426) are coalesced into one launch sequence per batch
+			long res = NativeSW.alignPair( NativeSW.context() , seqs[0].getBytes( StandardCharsets.ISO_8859_1 ) ,
+					seqs[1].getBytes( StandardCharsets.ISO_8859_1 ) , alignScores[0] , alignScores[1] , alignScores[2] , 0 ) ;
+			try { return unmarshal( res , Collections.singletonList(seqs[0]) , Collections.singletonList(seqs[1]) ).get(0).get(0) ; }
+			finally { NativeSW.resultFree( res ) ; }
 		}
 	}
 

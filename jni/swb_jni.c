@@ -87,6 +87,24 @@ JNIEXPORT jlong JNICALL Java_sw_NativeSW_align(JNIEnv *e, jclass c, jlong ctx, j
     if (rc) { throw_last(e, "swb_align"); return 0; }
     return (jlong)(intptr_t)res;
 }
+/* ---- one pair through the submission queue: the unchanged driver's per-pair OptAlignments.call (Distribution.java:419-426).
+ * The call may wait for other threads' requests, so the bytes are copied out instead of held critical. */
+JNIEXPORT jlong JNICALL Java_sw_NativeSW_alignPair(JNIEnv *e, jclass c, jlong ctx, jbyteArray ref, jbyteArray read, jint match,
+                                                   jint mismatch, jint gap, jint flags)
+{
+    (void)c;
+    const jsize n = (*e)->GetArrayLength(e, ref), m = (*e)->GetArrayLength(e, read);
+    jbyte *buf = (jbyte *)malloc((size_t)n + (size_t)m + 1);
+    if (!buf) { (*e)->ThrowNew(e, (*e)->FindClass(e, "java/lang/RuntimeException"), "swb_align_pair: out of memory"); return 0; }
+    (*e)->GetByteArrayRegion(e, ref, 0, n, buf);
+    (*e)->GetByteArrayRegion(e, read, 0, m, buf + n);
+    swb_result *res = 0;
+    const int rc = swb_align_pair(H(swb_ctx, ctx), (const char *)buf, n, (const char *)buf + n, m, match, mismatch, gap,
+                                  (uint32_t)flags, &res);
+    free(buf);
+    if (rc) { throw_last(e, "swb_align_pair"); return 0; }
+    return (jlong)(intptr_t)res;
+}
 JNIEXPORT void JNICALL Java_sw_NativeSW_resultFree(JNIEnv *e, jclass c, jlong res) { (void)e; (void)c; swb_result_free(H(swb_result, res)); }
 
 /* ---- result arrays ------------------------------------------------------------------------------- */

@@ -34,6 +34,9 @@ SIGNATURES = {
     "swb_align": (C.c_int, [_P, _P, C.c_int64, C.c_char_p, _I64P, C.c_int32, C.c_int32, C.c_int32,
                             C.c_uint32, C.POINTER(_P)]),
     "swb_align_resident": (C.c_int, [_P, _P, _P, C.c_int32, C.c_int32, C.c_int32, C.c_uint32, C.POINTER(_P)]),
+    "swb_align_pair": (C.c_int, [_P, C.c_char_p, C.c_int64, C.c_char_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32,
+                                 C.c_uint32, C.POINTER(_P)]),
+    "swb_queue_stats": (C.c_int, [_P, _I64P, C.c_int]),
     "swb_result_fetch": (C.c_int, [_P]),
     "swb_result_free": (None, [_P]),
     "swb_result_n_refs": (C.c_int64, [_P]),

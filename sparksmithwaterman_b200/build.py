@@ -16,8 +16,9 @@ LIB_DIR = os.path.join(HERE, "_lib")
 BIN_DIR = os.path.join(HERE, "_bin")
 LIB = os.path.join(LIB_DIR, "libswb200.so")
 MICROBENCH = os.path.join(BIN_DIR, "dpx_microbench")
+PAIR_BENCH = os.path.join(BIN_DIR, "pair_bench")
 
-SOURCES = ["swb_api.cu", "swb_fill.cu", "swb_fill_bias.cu", "swb_trace.cu", "swb_trace_tile.cu", "swb_wide.cu", "swb_wide_host.cu", "swb_multi.cu", "swb_assemble.cu", "dpx_microbench.cu"]
+SOURCES = ["swb_api.cu", "swb_fill.cu", "swb_fill_bias.cu", "swb_trace.cu", "swb_trace_tile.cu", "swb_wide.cu", "swb_wide_host.cu", "swb_multi.cu", "swb_queue.cu", "swb_assemble.cu", "dpx_microbench.cu"]
 HEADERS = ["swb_internal.h", "swb_device.cuh", "swb_host.h", os.path.join("..", "..", "include", "swb200.h")]
 NVCC_FLAGS = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a",
               "-Xcompiler", "-fPIC", "-cudart", "static"]
@@ -53,6 +54,11 @@ def build_native(force: bool = False, verbose: bool = False) -> str:
     if force or not _newer(MICROBENCH, [os.path.join(CSRC, "dpx_microbench.cu")]):
         subprocess.check_call([nvcc] + NVCC_FLAGS + ["-DSWB_MICROBENCH_MAIN", "-o", MICROBENCH,
                                                       os.path.join(CSRC, "dpx_microbench.cu")])
+    # native pairs/s harness of the single-pair (unchanged driver) path: plain C on the ABI
+    src = os.path.normpath(os.path.join(HERE, "..", "tools", "pair_bench.c"))
+    if os.path.exists(src) and (force or not _newer(PAIR_BENCH, [src, LIB])):
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-Wall", "-pthread", "-I" + os.path.normpath(os.path.join(HERE, "..", "include")),
+                               src, "-L" + LIB_DIR, "-lswb200", "-lm", "-Wl,-rpath," + LIB_DIR, "-Wl,-rpath,$ORIGIN/../_lib", "-o", PAIR_BENCH])
     return LIB
 
 

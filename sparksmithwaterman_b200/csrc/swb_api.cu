@@ -161,6 +161,7 @@ void swb_destroy(swb_ctx *c)
     cudaStreamSynchronize(c->stream);
     if (c->ev[0]) cudaEventDestroy(c->ev[0]);
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    for (cudaStream_t s : {c->stream, c->stream_fill, c->stream_copy}) if (s) { cudaStreamSynchronize(s); swbh::BlockCache::get().purge(s); }
     if (c->stream_copy) { cudaStreamSynchronize(c->stream_copy); cudaStreamDestroy(c->stream_copy); }
     if (c->stream_fill) cudaStreamDestroy(c->stream_fill);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -787,6 +788,9 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
         if (n_total >= ((uint64_t)1 << 31)) return fail(SWB_E_UNSUPPORTED, "swb_align: more than 2^31 max cells in one call");
         const uint32_t N = (uint32_t)n_total;
         res->total_cells = N;
+        static const bool tl4 = getenv("SWB_TIMELINE") != nullptr;
+        const auto t4 = std::chrono::steady_clock::now();
+        auto ms4 = [&] { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t4).count(); };
         CU(res->f_cell_off.alloc(n_pairs + 1, st));
         CU(res->f_cells.alloc((size_t)N * 2, st));
         CU(res->f_beg.alloc(N, st));
@@ -803,6 +807,15 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
         CU(d_words.alloc((size_t)N + 1, st));
         const size_t tmp_bytes = assemble_tmp_bytes(N);
         CU(d_tmp.alloc(tmp_bytes, st));
+        if (tl4) {
+            cudaMemPool_t pool; uint64_t resv = 0, used = 0; size_t fr = 0, tot = 0;
+            cudaDeviceGetDefaultMemPool(&pool, ctx->device);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrReservedMemCurrent, &resv);
+            cudaMemPoolGetAttribute(pool, cudaMemPoolAttrUsedMemCurrent, &used);
+            cudaMemGetInfo(&fr, &tot);
+            fprintf(stderr, "[swb assemble] N %u: allocations issued at %.3f ms; pool reserved %.2f GB used %.2f GB, device free %.2f GB\n", N, ms4(),
+                    resv / 1e9, used / 1e9, fr / 1e9);
+        }
         if (!descs.empty()) CU(cudaMemcpyAsync(d_desc.p, descs.data(), descs.size() * sizeof(BatchDesc), cudaMemcpyHostToDevice, st));
         int pair_bits = 1;
         while (pair_bits < 64 && ((uint64_t)1 << pair_bits) < (uint64_t)std::max<size_t>(n_pairs, 1)) ++pair_bits;
@@ -814,14 +827,18 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
         int64_t total_words = 0;
         CU(cudaMemcpyAsync(&total_words, res->f_ops_off.p + N, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        if (tl4) fprintf(stderr, "[swb assemble] sort + cell gather done at %.3f ms\n", ms4());
         res->total_words = total_words;
         CU(res->f_ops.alloc((size_t)total_words, st));
+        if (tl4) fprintf(stderr, "[swb assemble] ops array (%lld words) allocated at %.3f ms\n", (long long)total_words, ms4());
         CU(assemble_gather_ops(d_desc.p, (int)descs.size(), N, d_order.p, res->f_ops_off.p, res->f_ops.p, st));
         CU(assemble_offsets(d_pair_sorted.p, N, (int64_t)n_pairs, res->f_cell_off.p, res->d_best.p, n_reads, res->f_cells.p, st));
         launches += 8;
         CU(toc(sp_misc, st));
         CU(cudaStreamSynchronize(st));
+        if (tl4) fprintf(stderr, "[swb assemble] ops gathered at %.3f ms\n", ms4());
         res->batches.clear();                     // per-batch buffers go back to the pool
+        if (tl4) fprintf(stderr, "[swb assemble] batch buffers released at %.3f ms\n", ms4());
     } else {
         CU(toc(sp_misc, st));
         CU(cudaStreamSynchronize(st));

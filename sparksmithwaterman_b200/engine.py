@@ -60,11 +60,32 @@ class Engine:
     def load_refset(self, refs: Sequence) -> "RefSet":
         return RefSet(self, refs)
 
+    def align_pair(self, ref, read, scores=DEFAULT_SCORES, scores_only: bool = False, tie_gt: bool = False) -> "AlignResult":
+        """ONE pair through the context's submission queue (swb_align_pair): what the unchanged driver's per-pair
+        `OptAlignments.call` becomes.  Safe to call from many threads; concurrent calls are coalesced natively."""
+        rb, qb = _b(ref), _b(read)
+        flags = (SWB_F_SCORES_ONLY if scores_only else 0) | (SWB_F_TIE_GT if tie_gt else 0)
+        h = C.c_void_p()
+        check(self.lib.swb_align_pair(self.h, rb, len(rb), qb, len(qb), scores[0], scores[1], scores[2], flags, C.byref(h)))
+        return AlignResult(_PairRefs(self, rb), [qb], h, scores_only)
+
+    def queue_stats(self) -> dict:
+        out = (C.c_int64 * 3)()
+        check(self.lib.swb_queue_stats(self.h, out, 3))
+        return {"calls": int(out[0]), "batches": int(out[1]), "largest_batch": int(out[2])}
+
     def microbench(self, iters: int = 4000) -> dict:
         import json
         buf = C.create_string_buffer(1 << 15)
         check(self.lib.swb_microbench_json(self.device, iters, buf, len(buf)))
         return json.loads(buf.value.decode())
+
+
+class _PairRefs:
+    """What an AlignResult needs from its reference set, for the 1 x 1 results of Engine.align_pair."""
+
+    def __init__(self, eng: Engine, ref: bytes):
+        self.eng, self.seqs, self.n = eng, [ref], 1
 
 
 class RefSet:

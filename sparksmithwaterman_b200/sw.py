@@ -50,16 +50,13 @@ class SmithWaterman:
                  alignTypes: Sequence[str] = ALIGN_TYPES):
             if len(seqs) != 2 or len(alignScores) != 3:
                 raise ValueError("seqs = [reference, read], alignScores = [match, mismatch, gap]")
-            eng = default_engine()
-            rs = eng.load_refset([seqs[0]])
+            # one pair = one request to the engine's submission queue: calls from concurrent host threads (the
+            # unchanged driver's MapRef tasks, Distribution.java:419-426) are coalesced into one launch sequence
+            res = default_engine().align_pair(seqs[0], seqs[1], tuple(alignScores)).cache()
             try:
-                res = rs.align([seqs[1]], tuple(alignScores)).cache()
-                try:
-                    return expand_pair(res, 0, 0)
-                finally:
-                    res.free()
+                return expand_pair(res, 0, 0)
             finally:
-                rs.free()
+                res.free()
 
 
 def distributed_order(cells, sites):
@@ -79,15 +76,10 @@ class DistributedSW:
     class OptAlignments:
         def call(self, seqs: Sequence[str], alignScores: Sequence[int] = ALIGN_SCORES,
                  alignTypes: Sequence[str] = ALIGN_TYPES):
-            eng = default_engine()
-            rs = eng.load_refset([seqs[0]])
+            res = default_engine().align_pair(seqs[0], seqs[1], tuple(alignScores), tie_gt=True).cache()
             try:
-                res = rs.align([seqs[1]], tuple(alignScores), tie_gt=True).cache()
-                try:
-                    score, cells, sites = res.pair(0, 0)
-                    _, sites = distributed_order(cells, sites)
-                    return score, [(b, [ra, qa]) for (b, ra, qa) in sites]
-                finally:
-                    res.free()
+                score, cells, sites = res.pair(0, 0)
+                _, sites = distributed_order(cells, sites)
+                return score, [(b, [ra, qa]) for (b, ra, qa) in sites]
             finally:
-                rs.free()
+                res.free()

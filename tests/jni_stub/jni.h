@@ -24,6 +24,7 @@ struct JNINativeInterface_ {
     jbyteArray (*NewByteArray)(JNIEnv *, jsize);
     jintArray (*NewIntArray)(JNIEnv *, jsize);
     jlongArray (*NewLongArray)(JNIEnv *, jsize);
+    void (*GetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, jbyte *);
     void (*SetByteArrayRegion)(JNIEnv *, jbyteArray, jsize, jsize, const jbyte *);
     void (*SetIntArrayRegion)(JNIEnv *, jintArray, jsize, jsize, const jint *);
     void (*SetLongArrayRegion)(JNIEnv *, jlongArray, jsize, jsize, const jlong *);

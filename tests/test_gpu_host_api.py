@@ -153,3 +153,49 @@ def test_scores_only_mode_is_exact(engine):
         assert (so.best_hits[:, :2] == full.best_hits[:, :2]).all()
         so.free(); full.free()
     rs.free()
+
+
+def test_submission_queue_coalesces_concurrent_pair_calls(engine):
+    """The unchanged driver's path: N host threads each call OptAlignments.call on their own pairs
+    (Distribution.java:419-426).  swb_align_pair coalesces them; every caller still gets exactly its pair's
+    result (score, cells, beginnings, strings), including score-0 pairs, tie-heavy pairs, mixed case, a
+    second score set in the same queue, and a request the engine refuses (only THAT caller sees the error)."""
+    from concurrent.futures import ThreadPoolExecutor
+    from sparksmithwaterman_b200._ffi import SwbError
+    rnd = random.Random(11)
+    refs = ["".join(rnd.choice("ACGT") for _ in range(rnd.randint(60, 1500))) for _ in range(24)]
+    refs += ["AT" * 90, "acgtTTacgt" * 9, "AAAA", REF * 5]
+    reads = ["".join(rnd.choice("ACGT") for _ in range(rnd.randint(20, 150))) for _ in range(10)]
+    reads += [refs[3][10:130], "AT" * 30, "CCCC", READ_20, "", refs[1][100:360]]          # the last one: 260 rows, int32 path
+    jobs = [(r, q, (5, -3, -4) if (r + q) % 5 else (2, -1, -2)) for r in range(len(refs)) for q in range(len(reads))]
+    rnd.shuffle(jobs)
+    jobs = jobs[:320] + [("BAD", 0, (5, -3, -4))] * 3
+    before = engine.queue_stats()
+
+    def one(job):
+        r, q, sc = job
+        if r == "BAD":
+            try:
+                engine.align_pair("AC\xe9GT", reads[q], sc)
+            except SwbError as e:
+                return "non-ASCII" in str(e)
+            return False
+        res = engine.align_pair(refs[r], reads[q], sc).cache()
+        got = res.pair(0, 0, max_cells=200)
+        cnt = res.pair_cell_count(0, 0)
+        best = res.best_hits[0].tolist()
+        batch = int(res.stats["batches"])
+        res.free()
+        exp = oracle.align(refs[r], reads[q], *sc, max_cells=200)
+        ok = got[0] == exp.score and got[1] == exp.cells and got[2] == exp.sites
+        ok &= best[0] == exp.score and (best[2:] == list(exp.cells[0]) if exp.score > 0 else best[2:] == [0, 0])
+        if exp.score == 0:
+            ok &= cnt == len(refs[r]) * len(reads[q])
+        return ok and batch >= 1
+
+    with ThreadPoolExecutor(16) as ex:
+        results = list(ex.map(one, jobs))
+    assert all(results), [j for j, ok in zip(jobs, results) if not ok][:5]
+    after = engine.queue_stats()
+    assert after["calls"] - before["calls"] == len(jobs)
+    assert after["batches"] - before["batches"] < len(jobs) and after["largest_batch"] >= 2      # coalescing happened
