@@ -55,7 +55,7 @@ def main():
     sizes = [min(a.chunk, a.reads - k) for k in range(0, a.reads, a.chunk)]
     # all chunks up front (same bytes on every rank): host generation is not part of the job
     chunks = [synth.make_reads(n, 150, refs[:4096], seed=synth.READ_SEED + k) for k, n in enumerate(sizes)]
-    res = rs.align(chunks[0][:256]); res.free()                     # warm-up
+    res = rs.align(synth.make_reads(sizes[0], 150, refs[:4096], seed=synth.READ_SEED - 1)); res.free()   # warm-up on a throw-away chunk of the real size: pinned result buffers, device pool
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
