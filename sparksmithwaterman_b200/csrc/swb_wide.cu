@@ -472,6 +472,18 @@ template <int KL, bool BYTE> struct TraceGeo {
     static constexpr int GUARD = 4 * (COLB + ES) / 4 + 4;           // words before slot 0: the diagonal look-ahead may reach below a slot
     static size_t smem_bytes(int nt) { return ((size_t)nt + GUARD + (size_t)nt * TW) * 4; }
 };
+// CTA-wide groups: speculative SUB-WALKS.  The path enters every lane-row of the corridor through that lane-row's
+// bottom row, at a column the diagonal through the round's start predicts to within a few cells.  All threads walk
+// the lane-rows from NCAND candidate entry columns each (in parallel, one lane-row deep, no carried score: a cell's
+// own stored value stands in for it); the walker then only CHAINS the records: the exit column of one lane-row
+// selects the candidate of the next.  The serial part of a 1,024-row round drops from ~60 tile visits to 32 table
+// look-ups; whatever the candidates miss (or the last lane-rows of a path, where the exact score decides the end)
+// is left to the exact walker below.
+constexpr int SUB_NCAND = 16, SUB_CW = 8, SUB_WORDS = 8, SUB_MAX_MOVES = 60;
+constexpr int CTAW_TILES = 128, CTAW_THREADS = 512;
+constexpr int SUB_STAGE = (15 + (CTAW_TILES / 4) * SUB_MAX_MOVES) / 16 + 4;         // staging words for one round's chained ops
+constexpr int SUB_SMEM_WORDS = (CTAW_TILES / 4) * SUB_NCAND * SUB_WORDS + CTAW_TILES / 4 + SUB_STAGE;
+
 
 template <int KL, int NT, int G, bool BYTE>
 __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, const uint64_t *keys, uint32_t n_cells,
@@ -481,16 +493,27 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
     using TG = TraceGeo<KL, BYTE>;
     constexpr int ES = TG::ES, ROWW = TG::ROWW, COLB = TG::COLB, TW = TG::TW;
     constexpr int DG = COLB + ES;                                   // one diagonal step, in bytes
-    constexpr int DB = G >= 128 ? 4 : (G > 1 ? 2 : 1);             // blocks per lane-row of the corridor
-    constexpr int HS = G / DB;                                     // lane-rows a corridor covers
+    constexpr bool CTAW = G > 32;                                  // the whole CTA works on one max cell
+    constexpr int TILES = CTAW ? CTAW_TILES : G;                   // tiles of a corridor
+    constexpr int DB = CTAW ? 4 : (G > 1 ? 2 : 1);                 // blocks per lane-row of the corridor
+    constexpr int HS = TILES / DB;                                 // lane-rows a corridor covers
+    constexpr int NSLOT = CTAW ? TILES : NT;                       // tile slots of the CTA
+    constexpr int TPW = 32;                                        // tiles per warp: the recompute is issue-bound, not latency-bound
+                                                                   // (8 busy lanes in each of 16 warps: 2.3x slower than 32 in 4)
     static_assert(G == 1 || G == 32 || G == NT, "a group is a thread, a warp or the whole CTA");
+    static_assert(HS <= 32, "one lane of the first warp per lane-row");
     extern __shared__ uint32_t tsm[];
     __shared__ int bc_state[3];                                    // CTA-wide groups: the walker's state for the next round
-    int32_t *slot_blk = reinterpret_cast<int32_t *>(tsm);           // [NT] block of the tile in each thread's slot
-    uint32_t *slots = tsm + NT + TG::GUARD;
-    uint32_t *mytile = slots + (size_t)threadIdx.x * TW;
+    int32_t *slot_blk = reinterpret_cast<int32_t *>(tsm);           // [NSLOT] block of the tile in each slot
+    uint32_t *slots = tsm + NSLOT + TG::GUARD;
     const int gl = threadIdx.x % G;                                // lane in group
-    const int leader = threadIdx.x - gl;
+    const int leader = CTAW ? 0 : threadIdx.x - gl;
+    // tile of the corridor this thread recomputes (-1: none), which is also its slot
+    const int tg = !CTAW ? gl : (((threadIdx.x & 31) < TPW && (int)(threadIdx.x >> 5) * TPW + (int)(threadIdx.x & 31) < TILES)
+                                     ? (int)(threadIdx.x >> 5) * TPW + (int)(threadIdx.x & 31) : -1);
+    const int myslot = CTAW ? max(tg, 0) : (int)threadIdx.x;
+    uint32_t *mytile = slots + (size_t)myslot * TW;
+    int32_t *subrec = reinterpret_cast<int32_t *>(slots + (size_t)NSLOT * TW);   // CTA-wide: [HS][SUB_NCAND][SUB_WORDS], then sel[HS], stage[SUB_STAGE]
     const unsigned gmask = 0xffffffffu;
     const uint32_t n_groups = gridDim.x * (NT / G);
     const uint32_t gid = (blockIdx.x * NT + threadIdx.x) / G;
@@ -535,10 +558,11 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             // ---- corridor: slot (k, d) = lane-row T0 - k, block b_k - d, b_k from the diagonal through (ci, cj)
             // (DB = 2: blocks b_k, b_k - 1; DB = 4: b_k + 1 .. b_k - 2 -- a path with many gaps drifts off the diagonal)
             const int T0 = (ci - 1) / KL;
-            const int k = gl / DB, d = gl % DB;
+            const int k = tg / DB, d = tg % DB;
             const int Tk = T0 - k;
+            const long long dbg_t0 = P.dbg ? clock64() : 0;
             int myblk = -1;
-            if (Tk >= 0) {
+            if (tg >= 0 && Tk >= 0) {
                 const int t = Tk % WL;
                 const int di = k == 0 ? 0 : ci - (Tk * KL + KL);   // rows the path climbs to reach lane-row Tk
                 const int step = cj - di - 1 + t;
@@ -560,10 +584,148 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     if ((u & 3) == 3) { cw[KL / 4 + (u >> 2)] = cacc; cacc = 0; }
                 });
             }
-            slot_blk[threadIdx.x] = myblk;
+            if (tg >= 0) slot_blk[myslot] = myblk;
             if (P.dbg) { if (gl == 0) atomicAdd(P.dbg, 1ull); if (myblk >= 0) atomicAdd(P.dbg + 2, 1ull); }
             if (G == 32) __syncwarp(gmask);
             else if (G > 32) __syncthreads();
+            const long long dbg_t1 = P.dbg ? clock64() : 0;
+            if (CTAW) {
+                const int ci_s = ci, cj_s = cj;
+                // ---- sub-walks: record = {exit column, moves, score consumed, beginning, 128 op bits}; moves < 0: unusable
+                for (int sub = gl; sub < HS * SUB_NCAND; sub += G) {
+                    const int kk = sub / SUB_NCAND, delta = sub % SUB_NCAND - SUB_CW;
+                    const int T = T0 - kk;
+                    int *out = subrec + sub * SUB_WORDS;
+                    int wi = kk == 0 ? ci_s : (T + 1) * KL;                       // entry: the lane-row's bottom row
+                    int wj = kk == 0 ? cj_s : cj_s - (ci_s - wi) + delta;
+                    bool ok = T >= 0 && (kk > 0 || delta == 0) && wj >= 1 && wj <= C.n;
+                    int n = 0, ds = 0, beg = 0;
+                    unsigned long long lo = 0, hi = 0;
+                    const int t = ok ? T % WL : 0;
+                    while (ok) {
+                        if (wj < 1) { ok = false; break; }
+                        const int step = wj - 1 + t;
+                        const int b = step / WCB;
+                        int slot = leader + DB * kk, dd = 0;
+                        while (dd < DB && slot_blk[slot + dd] != b) ++dd;
+                        if (dd == DB) { ok = false; break; }
+                        slot += dd;
+                        int r = wi - T * KL;                                       // 1..KL
+                        int c = step - b * WCB + 1;                                // 1..WCB
+                        const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
+                        const uint8_t *p = base + c * COLB + r * ES;
+                        const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);
+                        const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);
+                        for (;;) {
+                            const int h0 = elem(p), h1 = elem(p - DG), h2 = elem(p - 2 * DG), h3 = elem(p - 3 * DG), h4 = elem(p - 4 * DG);
+                            const int hn = elem(p - ES), hw = elem(p - COLB);
+                            const int s0 = (pr[0] == pq[0]) ? match : mismatch, s1 = (pr[-1] == pq[-1]) ? match : mismatch;
+                            const int s2 = (pr[-2] == pq[-2]) ? match : mismatch, s3 = (pr[-3] == pq[-3]) ? match : mismatch;
+                            const int lim = min(r, c);
+                            int L = 0;
+                            if (!tie_gt && ((h1 + s0 - h0) & M) == 0) {
+                                const bool ok1 = lim > 1 && ((h2 + s1 - h1) & M) == 0;
+                                const bool ok2 = ok1 && lim > 2 && ((h3 + s2 - h2) & M) == 0;
+                                const bool ok3 = ok2 && lim > 3 && ((h4 + s3 - h3) & M) == 0;
+                                L = 1 + (int)ok1 + (int)ok2 + (int)ok3;
+                            }
+                            unsigned long long bits;
+                            int adv;
+                            if (L > 0) {
+                                ds += s0 + (L > 1 ? s1 : 0) + (L > 2 ? s2 : 0) + (L > 3 ? s3 : 0);
+                                beg = wj - (L - 1);
+                                wi -= L; wj -= L; r -= L; c -= L;
+                                p -= L * DG; pr -= L; pq -= L;
+                                bits = 0x55u >> (8 - 2 * L); adv = L;
+                            } else {
+                                const bool eq_i = ((hn + gap - h0) & M) == 0, eq_d = ((hw + gap - h0) & M) == 0;
+                                const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
+                                beg = wj;
+                                ds += (op == 1u) ? s0 : gap;
+                                const int up = op != 3u, left = op != 2u;
+                                r -= up; wi -= up; pr -= up;
+                                c -= left; wj -= left; pq -= left;
+                                p -= up * ES + left * COLB;
+                                bits = op; adv = 1;
+                            }
+                            if (n < 32) { lo |= bits << (2 * n); if (2 * n + 8 > 64) hi |= bits >> (64 - 2 * n); }
+                            else hi |= bits << (2 * n - 64);
+                            n += adv;
+                            if (n > SUB_MAX_MOVES - 4) { ok = false; break; }
+                            if (r == 0 || c == 0) break;
+                        }
+                        if (!ok || wi == T * KL) break;                             // the lane-row's boundary row: done
+                    }
+                    out[0] = wj - (cj_s - (ci_s - T * KL)) + SUB_CW;              // candidate index of the next lane-row's entry
+                    out[1] = ok ? n : -1; out[2] = ds; out[3] = beg;
+                    out[4] = (int)(uint32_t)lo; out[5] = (int)(uint32_t)(lo >> 32); out[6] = (int)(uint32_t)hi; out[7] = (int)(uint32_t)(hi >> 32);
+                }
+                __syncthreads();
+                if (P.dbg && gl == 0) atomicAdd(P.dbg + 6, (unsigned long long)(clock64() - dbg_t1));
+                const long long dbg_t2 = P.dbg ? clock64() : 0;
+                if (gl < 32) {
+                    // ---- chain: a serial chase through the records (one look-up per lane-row), then lane kk of the first
+                    // warp appends lane-row kk's moves: prefix sums give every lane-row its bit offset and the score left
+                    int32_t *sel = subrec + HS * SUB_NCAND * SUB_WORDS;
+                    uint32_t *stage = reinterpret_cast<uint32_t *>(sel + HS);
+                    const int bigp = max(max(match, mismatch), 1);
+                    int idx = SUB_CW, kk_end = 0;
+                    for (int kk = 0; kk < HS; ++kk) {
+                        if (T0 - kk < 0 || idx < 0 || idx >= SUB_NCAND) break;
+                        const int *so = subrec + (kk * SUB_NCAND + idx) * SUB_WORDS;
+                        if (so[1] <= 0) break;
+                        if (gl == 0) sel[kk] = idx;
+                        idx = so[0];
+                        kk_end = kk + 1;
+                    }
+                    __syncwarp();
+                    const bool have = gl < kk_end;
+                    const int *so = subrec + (gl * SUB_NCAND + (have ? sel[gl] : 0)) * SUB_WORDS;
+                    const int n = have ? so[1] : 0, ds = have ? so[2] : 0;
+                    int pn = n, pd = ds;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a = __shfl_up_sync(0xffffffffu, pn, o), b2 = __shfl_up_sync(0xffffffffu, pd, o);
+                        if (gl >= o) { pn += a; pd += b2; }
+                    }
+                    // near the end of a path the exact score decides where it stops: those lane-rows go to the walker below
+                    const unsigned badm = __ballot_sync(0xffffffffu, have && (hcur - (pd - ds) <= n * bigp));
+                    const int kk_ok = badm ? min(kk_end, __ffs((int)badm) - 1) : kk_end;
+                    if (kk_ok > 0) {
+                        const int used0 = (int)(oplen & 15);
+                        const int total = __shfl_sync(0xffffffffu, pn, kk_ok - 1);
+                        const int dtot = __shfl_sync(0xffffffffu, pd, kk_ok - 1);
+                        const int nwords = (used0 + total + 15) >> 4;
+                        for (int w = gl; w <= nwords; w += 32) stage[w] = (w == 0) ? opword : 0u;
+                        __syncwarp();
+                        if (gl < kk_ok) {
+                            const int pos = used0 + (pn - n);
+                            const int word0 = pos >> 4, sh = 2 * (pos & 15);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                if (n > 16 * q) {
+                                    const unsigned long long v = (unsigned long long)(uint32_t)so[4 + q] << sh;
+                                    atomicOr(&stage[word0 + q], (uint32_t)v);
+                                    if ((uint32_t)(v >> 32)) atomicOr(&stage[word0 + q + 1], (uint32_t)(v >> 32));
+                                }
+                        }
+                        __syncwarp();
+                        const int64_t oplen_new = oplen + total;
+                        const int full_words = (int)((oplen_new >> 4) - (oplen >> 4));
+                        for (int w = gl; w < full_words; w += 32) myops[(oplen >> 4) + w] = stage[w];
+                        opword = stage[full_words];
+                        oplen = oplen_new;
+                        hcur -= dtot;
+                        beginning = __shfl_sync(0xffffffffu, have ? so[3] : 0, kk_ok - 1);
+                        const int idx_next = __shfl_sync(0xffffffffu, have ? so[0] : 0, kk_ok - 1);
+                        ci = (T0 - (kk_ok - 1)) * KL;
+                        cj = cj_s - (ci_s - ci) + (idx_next - SUB_CW);
+                        if (P.dbg && gl == 0) atomicAdd(P.dbg + 5, (unsigned long long)kk_ok);
+                    }
+                    __syncwarp();
+                    if (P.dbg && gl == 0) atomicAdd(P.dbg + 7, (unsigned long long)(clock64() - dbg_t2));
+                }
+            }
             if (G == 1) {
                 // ---- walk (SmithWaterman.java:380-409): one thread per max cell
                 for (;;) {
@@ -712,6 +874,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     if (hcur <= 0) break;
                 }
             }
+            if (P.dbg && gl == 0) { atomicAdd(P.dbg + 3, (unsigned long long)(dbg_t1 - dbg_t0)); atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - dbg_t1)); }
             if (G == 32) {
                 __syncwarp(gmask);                                 // every lane walked: the state is already uniform
             } else if (G > 32) {
@@ -762,7 +925,7 @@ template <int KL, int NT, int G, bool BYTE>
 cudaError_t launch_trace_k(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
                            int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
 {
-    const size_t smem = TraceGeo<KL, BYTE>::smem_bytes(NT);
+    const size_t smem = G > 32 ? TraceGeo<KL, BYTE>::smem_bytes(CTAW_TILES) + (size_t)SUB_SMEM_WORDS * 4 : TraceGeo<KL, BYTE>::smem_bytes(NT);
     cudaError_t e = cudaFuncSetAttribute(wide_trace_kernel<KL, NT, G, BYTE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     const int per_sm = std::max(1, std::min(8, (int)((220 * 1024) / (smem + 1024))));
@@ -783,7 +946,7 @@ cudaError_t launch_trace_kl(const WideParams &P, const uint64_t *keys, uint32_t 
     const int g = env_g ? env_g : ((int64_t)n_cells <= (int64_t)sm_count ? 128 : ((int64_t)n_cells < (int64_t)sm_count * 256 ? 32 : 1));
     constexpr int NTB = KL >= 32 ? 64 : 128;                              // byte tiles: 80 / 91 / 56 KB per CTA
     if (bytes) {
-        if (g >= 128) return launch_trace_k<KL, 128, 128, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        if (g >= 128) return launch_trace_k<KL, CTAW_THREADS, CTAW_THREADS, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
         if (g == 32) return launch_trace_k<KL, NTB, 32, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
         return launch_trace_k<KL, NTB, 1, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
     }

@@ -131,8 +131,8 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         static const bool wide_debug = getenv("SWB_WIDE_DEBUG") != nullptr;
         P.dbg = nullptr;
         if (wide_debug) {
-            CU(ctx->w_dbg.reserve(4, st));
-            CU(cudaMemsetAsync(ctx->w_dbg.p, 0, 32, st));
+            CU(ctx->w_dbg.reserve(8, st));
+            CU(cudaMemsetAsync(ctx->w_dbg.p, 0, 64, st));
             P.dbg = ctx->w_dbg.p;
         }
         uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_ticket = ctx->counters.p + 2;
@@ -190,10 +190,10 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         CU(toc());
         CU(cudaStreamSynchronize(st));      // the host tables of this batch are reused by the next one
         if (P.dbg) {
-            unsigned long long h[4];
-            CU(cudaMemcpy(h, P.dbg, 32, cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[swb wide] KL=%d pairs=%d cells=%u: traceback rounds=%llu tiles walked=%llu tiles recomputed=%llu\n",
-                    KL, np, n_cells, h[0], h[1], h[2]);
+            unsigned long long h[8];
+            CU(cudaMemcpy(h, P.dbg, 64, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[swb wide] KL=%d pairs=%d cells=%u: traceback rounds=%llu tiles walked=%llu tiles recomputed=%llu; group-leader cycles: recompute %llu walk %llu; lane-rows chained %llu (sub-walk phase %llu cycles, chain %llu)\n",
+                    KL, np, n_cells, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
         }
         res->stats[8] += n_cells;
         res->batches.push_back(std::move(bo));
