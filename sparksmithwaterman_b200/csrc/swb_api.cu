@@ -153,7 +153,7 @@ void swb_destroy(swb_ctx *c)
     for (int k = 0; k < 2; ++k) { c->ck2[k].release(); c->tmx2[k].release(); c->rp2[k].release(); }
     cudaStreamSynchronize(c->stream_fill);
     c->v_ref.release(); c->v_c0.release(); c->v_len.release(); c->v_skip.release(); c->v_end.release();
-    c->w_brow.release(); c->w_rec.release(); c->w_wreads.release(); c->w_rpad.release(); c->w_rpad_off.release(); c->w_rpad_len.release(); c->w_dbg.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
+    c->w_brow.release(); c->w_rec.release(); c->w_wreads.release(); c->w_rpad.release(); c->w_rpad_off.release(); c->w_rpad_len.release(); c->w_dbg.release(); c->w_mail.release(); c->w_tmx.release(); c->w_prog.release(); c->w_pair_ref.release();
     c->w_pair_read.release(); c->w_band_off.release(); c->w_blk_off.release(); c->w_brow_off.release();
     c->w_items.release(); c->w_tasks.release();
     for (cudaEvent_t e : c->ev_pool) cudaEventDestroy(e);

@@ -150,6 +150,7 @@ struct swb_ctx {
     DevBuf<uint8_t> w_rpad;                     // wide reads, aligned + padded (0xFE) to whole bands
     DevBuf<int64_t> w_rpad_off, w_rpad_len;
     DevBuf<unsigned long long> w_dbg;
+    DevBuf<int32_t> w_mail;                     // tokens of the pipelined CTA-wide traceback
     DevBuf<int64_t> w_band_off, w_blk_off, w_brow_off;
     DevBuf<int2> w_items;
     DevBuf<WideTask> w_tasks;

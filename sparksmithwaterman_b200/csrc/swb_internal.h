@@ -152,6 +152,10 @@ struct WideParams {
     int32_t *rec;                // block records [bands * blocks][32 lanes][RW]
     int32_t *tmx;                // tile maxima   [bands * blocks][32 lanes]
     int32_t *scores;
+    int32_t *mail;               // pipelined CTA-wide traceback: tokens [cells][mail_stride][8] (zeroed by the host), nullptr = mode off
+    int32_t *mail_latest;        // [cells] highest token index published
+    int32_t mail_stride;         // tokens per cell = rounds + 2
+    int32_t pipe_c;              // CTAs per cell (cluster size), set by the launcher
     unsigned long long *dbg;     // optional counters (SWB_WIDE_DEBUG): [0] traceback rounds, [1] tiles walked, [2] tiles recomputed
 };
 

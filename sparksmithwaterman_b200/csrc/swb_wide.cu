@@ -54,6 +54,14 @@ __device__ __forceinline__ void st_relaxed4(int32_t *p, int a, int b, int c, int
     asm volatile("st.relaxed.gpu.global.v4.s32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+__device__ __forceinline__ int ld_acquire(const int32_t *p)
+{
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release(int32_t *p, int v) { asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
 struct WCtx {
     const uint8_t *ref;     // codes of this pair's reference (n bytes)
     const uint8_t *read;    // codes of this pair's read in the padded buffer (16-byte aligned, 0xFE beyond m)
@@ -479,10 +487,11 @@ template <int KL, bool BYTE> struct TraceGeo {
 // selects the candidate of the next.  The serial part of a 1,024-row round drops from ~60 tile visits to 32 table
 // look-ups; whatever the candidates miss (or the last lane-rows of a path, where the exact score decides the end)
 // is left to the exact walker below.
-constexpr int SUB_NCAND = 16, SUB_CW = 8, SUB_WORDS = 8, SUB_MAX_MOVES = 60;
+constexpr int SUB_NCAND = 32, SUB_CW = 16, SUB_WORDS = 8, SUB_MAX_MOVES = 60;
 constexpr int CTAW_TILES = 128, CTAW_THREADS = 512;
 constexpr int SUB_STAGE = (15 + (CTAW_TILES / 4) * SUB_MAX_MOVES) / 16 + 4;         // staging words for one round's chained ops
 constexpr int SUB_SMEM_WORDS = (CTAW_TILES / 4) * SUB_NCAND * SUB_WORDS + CTAW_TILES / 4 + SUB_STAGE;
+constexpr int CTAW_ROUND_LANE_ROWS = CTAW_TILES / 4;                               // lane-rows per round of the pipelined mode
 
 
 template <int KL, int NT, int G, bool BYTE>
@@ -543,6 +552,355 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
     auto elem = [&](const uint8_t *p) -> int {
         return BYTE ? (int)*p : *reinterpret_cast<const int32_t *>(p);
     };
+
+
+    if constexpr (CTAW) {
+        // ================================================================================================
+        // CTA-wide mode, PIPELINED over the CTAs of a cluster.  A long path is cut into ROUNDS of HS lane-rows
+        // (fixed rows: round r covers lane-rows T00 - HS r .. T00 - HS r - HS + 1).  CTA q of the cell's cluster owns the
+        // rounds q, q + C, q + 2C, ...  For each of them it PREPARES -- recomputes the corridor of tiles along the
+        // diagonal predicted from the latest published walker state and runs the speculative sub-walks -- while the
+        // walker is still rounds away, then waits for the round's TOKEN (the walker state at the round's first row,
+        // in global memory, release / acquire), CONSUMES (chains the sub-walk records, exact walker for what they
+        // miss, corrective corridors if the path left the predicted one) and publishes the next token.  Only the
+        // chain and the exact walker are serial along a path; the expensive recompute runs C rounds ahead.
+        // The CTAs of a cluster are co-scheduled, so a waiting CTA's producer is always running.
+        const int Cc = P.pipe_c;
+        const uint32_t cell = blockIdx.x / (uint32_t)Cc;
+        const int q = (int)(blockIdx.x % (uint32_t)Cc);
+        if (cell >= n_cells) return;
+        const uint64_t key = keys[cell];
+        const int pair = (int)wide_key_pair(key);
+        const int ci0 = (int)wide_key_i(key), cj0 = (int)wide_key_j(key);
+        const WCtx C = make_ctx<KL>(P, pair);
+        const int h0 = P.scores[(int64_t)P.pair_ref[pair] * P.n_reads + P.pair_read[pair]];
+        int32_t *tok = P.mail + (int64_t)cell * P.mail_stride * 8;      // token k = walker state at the first row of round k
+        int32_t *latest = P.mail_latest + cell;                        // highest token index published so far
+        uint32_t *myops = ops + (int64_t)cell * ops_stride;
+        const int T00 = (ci0 - 1) / KL;
+        const int wl = (int)threadIdx.x;                                // lane of the walking warp (threads 0..31)
+        const int big = max(abs(match), abs(mismatch));
+        const int bigp = max(max(match, mismatch), 1);
+        int32_t *sel = subrec + HS * SUB_NCAND * SUB_WORDS;
+        uint32_t *stage = reinterpret_cast<uint32_t *>(sel + HS);
+        __shared__ int bc[8];
+        int hcur = h0, ci = ci0, cj = cj0, beginning = 0;
+        int64_t oplen = 0;
+        uint32_t opword = 0;
+        int T0 = 0, pi = 0, pj = 0;                                    // the prepared corridor: lane-rows T0, T0 - 1, ..; diagonal through (pi, pj)
+
+        auto prepare = [&](int qi, int qj, bool exact) {
+            pi = qi; pj = qj; T0 = (qi - 1) / KL;
+            if (tg >= 0) {
+                const int k = tg / DB, d = tg % DB;
+                const int Tk = T0 - k;
+                int myblk = -1;
+                if (Tk >= 0) {
+                    const int t = Tk % WL;
+                    const int di = k == 0 ? 0 : qi - (Tk * KL + KL);   // rows the path climbs to reach lane-row Tk
+                    const int step = qj - di - 1 + t;
+                    const int b = (step >= 0 ? step / WCB : -1) + 1 - d;           // blocks b_k + 1 .. b_k - 2
+                    if (b >= 0 && b < C.n_blocks) myblk = b;
+                }
+                if (myblk >= 0) {
+                    WTile<KL> W;
+                    W.load(C, Tk / WL, Tk % WL, myblk);
+                    store_col(0, W.diag, W.H);
+                    uint32_t *cw = mytile + TG::CODE0;
+#pragma unroll
+                    for (int q4 = 0; q4 < KL / 4; ++q4)
+                        cw[q4] = (uint32_t)W.rc[4 * q4] | ((uint32_t)W.rc[4 * q4 + 1] << 8) | ((uint32_t)W.rc[4 * q4 + 2] << 16) | ((uint32_t)W.rc[4 * q4 + 3] << 24);
+                    uint32_t cacc = 0;
+                    W.run(C, [&](int u, int top, const int (&Hc)[KL], int c) {
+                        store_col(u + 1, top, Hc);
+                        cacc |= (uint32_t)c << (8 * (u & 3));
+                        if ((u & 3) == 3) { cw[KL / 4 + (u >> 2)] = cacc; cacc = 0; }
+                    });
+                    if (P.dbg) atomicAdd(P.dbg + 2, 1ull);
+                }
+                slot_blk[tg] = myblk;
+            }
+            __syncthreads();
+            // ---- sub-walks: record = {candidate index of the next lane-row's entry, moves (< 0: unusable), score consumed,
+            //      beginning, 128 op bits}
+            for (int sub = (int)threadIdx.x; sub < HS * SUB_NCAND; sub += NT) {
+                const int kk = sub / SUB_NCAND, delta = sub % SUB_NCAND - SUB_CW;
+                const int T = T0 - kk;
+                int *out = subrec + sub * SUB_WORDS;
+                int wi = kk == 0 ? qi : (T + 1) * KL;                             // entry: the lane-row's bottom row
+                int wj = qj - (qi - wi) + delta;
+                bool ok = T >= 0 && (kk > 0 || !exact || delta == 0) && wj >= 1 && wj <= C.n;
+                int n = 0, ds = 0, beg = 0;
+                unsigned long long lo = 0, hi = 0;
+                const int t = ok ? T % WL : 0;
+                while (ok) {
+                    if (wj < 1) { ok = false; break; }
+                    const int step = wj - 1 + t;
+                    const int b = step / WCB;
+                    int slot = DB * kk, dd = 0;
+                    while (dd < DB && slot_blk[slot + dd] != b) ++dd;
+                    if (dd == DB) { ok = false; break; }
+                    slot += dd;
+                    int r = wi - T * KL;                                           // 1..KL
+                    int c = step - b * WCB + 1;                                    // 1..WCB
+                    const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
+                    const uint8_t *p = base + c * COLB + r * ES;
+                    const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);
+                    const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);
+                    for (;;) {
+                        const int e0 = elem(p), e1 = elem(p - DG), e2 = elem(p - 2 * DG), e3 = elem(p - 3 * DG), e4 = elem(p - 4 * DG);
+                        const int hn = elem(p - ES), hw = elem(p - COLB);
+                        const int s0 = (pr[0] == pq[0]) ? match : mismatch, s1 = (pr[-1] == pq[-1]) ? match : mismatch;
+                        const int s2 = (pr[-2] == pq[-2]) ? match : mismatch, s3 = (pr[-3] == pq[-3]) ? match : mismatch;
+                        const int lim = min(r, c);
+                        int L = 0;
+                        if (!tie_gt && ((e1 + s0 - e0) & M) == 0) {
+                            const bool ok1 = lim > 1 && ((e2 + s1 - e1) & M) == 0;
+                            const bool ok2 = ok1 && lim > 2 && ((e3 + s2 - e2) & M) == 0;
+                            const bool ok3 = ok2 && lim > 3 && ((e4 + s3 - e3) & M) == 0;
+                            L = 1 + (int)ok1 + (int)ok2 + (int)ok3;
+                        }
+                        unsigned long long bits;
+                        int adv;
+                        if (L > 0) {
+                            ds += s0 + (L > 1 ? s1 : 0) + (L > 2 ? s2 : 0) + (L > 3 ? s3 : 0);
+                            beg = wj - (L - 1);
+                            wi -= L; wj -= L; r -= L; c -= L;
+                            p -= L * DG; pr -= L; pq -= L;
+                            bits = 0x55u >> (8 - 2 * L); adv = L;
+                        } else {
+                            const bool eq_i = ((hn + gap - e0) & M) == 0, eq_d = ((hw + gap - e0) & M) == 0;
+                            const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
+                            beg = wj;
+                            ds += (op == 1u) ? s0 : gap;
+                            const int up = op != 3u, left = op != 2u;
+                            r -= up; wi -= up; pr -= up;
+                            c -= left; wj -= left; pq -= left;
+                            p -= up * ES + left * COLB;
+                            bits = op; adv = 1;
+                        }
+                        if (n < 32) { lo |= bits << (2 * n); if (2 * n + 8 > 64) hi |= bits >> (64 - 2 * n); }
+                        else hi |= bits << (2 * n - 64);
+                        n += adv;
+                        if (n > SUB_MAX_MOVES - 4) { ok = false; break; }
+                        if (r == 0 || c == 0) break;
+                    }
+                    if (!ok || wi == T * KL) break;                                 // the lane-row's boundary row: done
+                }
+                out[0] = wj - (qj - (qi - T * KL)) + SUB_CW;
+                out[1] = ok ? n : -1; out[2] = ds; out[3] = beg;
+                out[4] = (int)(uint32_t)lo; out[5] = (int)(uint32_t)(lo >> 32); out[6] = (int)(uint32_t)hi; out[7] = (int)(uint32_t)(hi >> 32);
+            }
+            __syncthreads();
+        };
+
+        // the walking warp (threads 0..31, every lane keeps the whole state): chain, then the exact walker; never above lane-row Tlo
+        auto consume = [&](int Tlo) {
+            if (ci == pi) {
+                // ---- chain: a serial chase through the records, then lane kk appends lane-row kk's moves
+                int idx = cj - pj + SUB_CW, kk_end = 0;
+                for (int kk = 0; kk < HS; ++kk) {
+                    if (T0 - kk < Tlo || idx < 0 || idx >= SUB_NCAND) break;
+                    const int *so = subrec + (kk * SUB_NCAND + idx) * SUB_WORDS;
+                    if (so[1] <= 0) break;
+                    if (wl == 0) sel[kk] = idx;
+                    idx = so[0];
+                    kk_end = kk + 1;
+                }
+                __syncwarp();
+                const bool have = wl < kk_end;
+                const int *so = subrec + (wl * SUB_NCAND + (have ? sel[wl] : 0)) * SUB_WORDS;
+                const int n = have ? so[1] : 0, ds = have ? so[2] : 0;
+                int pn = n, pd = ds;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int a = __shfl_up_sync(0xffffffffu, pn, o), b2 = __shfl_up_sync(0xffffffffu, pd, o);
+                    if (wl >= o) { pn += a; pd += b2; }
+                }
+                // near the end of a path the exact score decides where it stops: those lane-rows go to the walker below
+                const unsigned badm = __ballot_sync(0xffffffffu, have && (hcur - (pd - ds) <= n * bigp));
+                const int kk_ok = badm ? min(kk_end, __ffs((int)badm) - 1) : kk_end;
+                if (kk_ok > 0) {
+                    const int used0 = (int)(oplen & 15);
+                    const int total = __shfl_sync(0xffffffffu, pn, kk_ok - 1);
+                    const int dtot = __shfl_sync(0xffffffffu, pd, kk_ok - 1);
+                    const int nwords = (used0 + total + 15) >> 4;
+                    for (int w = wl; w <= nwords; w += 32) stage[w] = (w == 0) ? opword : 0u;
+                    __syncwarp();
+                    if (wl < kk_ok) {
+                        const int pos = used0 + (pn - n);
+                        const int word0 = pos >> 4, sh = 2 * (pos & 15);
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            if (n > 16 * q4) {
+                                const unsigned long long v = (unsigned long long)(uint32_t)so[4 + q4] << sh;
+                                atomicOr(&stage[word0 + q4], (uint32_t)v);
+                                if ((uint32_t)(v >> 32)) atomicOr(&stage[word0 + q4 + 1], (uint32_t)(v >> 32));
+                            }
+                    }
+                    __syncwarp();
+                    const int64_t oplen_new = oplen + total;
+                    const int full_words = (int)((oplen_new >> 4) - (oplen >> 4));
+                    for (int w = wl; w < full_words; w += 32) myops[(oplen >> 4) + w] = stage[w];
+                    opword = stage[full_words];
+                    oplen = oplen_new;
+                    hcur -= dtot;
+                    beginning = __shfl_sync(0xffffffffu, have ? so[3] : 0, kk_ok - 1);
+                    const int idx_next = __shfl_sync(0xffffffffu, have ? so[0] : 0, kk_ok - 1);
+                    ci = (T0 - (kk_ok - 1)) * KL;
+                    cj = pj - (pi - ci) + (idx_next - SUB_CW);
+                    if (P.dbg && wl == 0) atomicAdd(P.dbg + 5, (unsigned long long)kk_ok);
+                }
+                __syncwarp();
+            }
+            // ---- exact walker (SmithWaterman.java:380-409), all 32 lanes in lock step: lane k probes the diagonal cell
+            // (r - k, c - k), one ballot finds a whole run of alignment moves
+            auto push = [&](uint32_t op, int n) {
+                const uint32_t pattern = op * 0x55555555u;
+                while (n > 0) {
+                    const int used = (int)(oplen & 15);
+                    const int take = min(n, 16 - used);
+                    const uint32_t bits = take == 16 ? pattern : (pattern & ((1u << (2 * take)) - 1u));
+                    opword |= bits << (2 * used);
+                    oplen += take; n -= take;
+                    if ((oplen & 15) == 0) { if (wl == 0) myops[(oplen >> 4) - 1] = opword; opword = 0; }
+                }
+            };
+            while (hcur > 0 && ci >= 1) {
+                const int T = (ci - 1) / KL;
+                const int kk = T0 - T;
+                if (T < Tlo || kk < 0 || kk >= HS || cj < 1) break;
+                const int t = T % WL;
+                const int step = cj - 1 + t;
+                const int b = step / WCB;
+                int slot = DB * kk, dd = 0;
+                while (dd < DB && slot_blk[slot + dd] != b) ++dd;
+                if (dd == DB) break;
+                slot += dd;
+                int r = ci - T * KL;                           // 1..KL
+                int c = step - b * WCB + 1;                    // 1..WCB
+                if (P.dbg && wl == 0) atomicAdd(P.dbg + 1, 1ull);
+                const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
+                const uint8_t *p = base + c * COLB + r * ES;
+                const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);
+                const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);
+                for (;;) {
+                    const int lim = min(r, c);
+                    const bool inside = wl < lim;
+                    const uint8_t *pk = p - wl * DG;
+                    const int hk = inside ? elem(pk) : 0, hnwk = inside ? elem(pk - DG) : 1;
+                    const bool is_m = inside && pr[-wl] == pq[-wl];
+                    const int sck = is_m ? match : mismatch;
+                    const bool okk = inside && (((hnwk + sck - hk) & M) == 0);
+                    const unsigned okm = __ballot_sync(0xffffffffu, okk), mm = __ballot_sync(0xffffffffu, is_m);
+                    const int run = tie_gt ? 0 : (okm == 0xffffffffu ? 32 : __ffs((int)~okm) - 1);
+                    const int L = (hcur > 32 * big) ? run : min(run, 1);
+                    if (L > 0) {
+                        const unsigned lm = L >= 32 ? 0xffffffffu : ((1u << L) - 1u);
+                        const int nm = __popc(mm & lm);
+                        hcur -= nm * match + (L - nm) * mismatch;
+                        beginning = cj - (L - 1);
+                        ci -= L; cj -= L; r -= L; c -= L;
+                        p -= L * DG; pr -= L; pq -= L;
+                        push(1u, L);
+                    }
+                    if (hcur <= 0 || r == 0 || c == 0) break;
+                    if (L == run && run < lim) {
+                        const int hn = elem(p - ES), hw = elem(p - COLB);
+                        const bool eq_i = ((hn + gap - hcur) & M) == 0, eq_d = ((hw + gap - hcur) & M) == 0;
+                        const int s0 = (pr[0] == pq[0]) ? match : mismatch;
+                        const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
+                        beginning = cj;
+                        hcur -= (op == 1u) ? s0 : gap;
+                        const int up = op != 3u, left = op != 2u;
+                        r -= up; ci -= up; pr -= up;
+                        c -= left; cj -= left; pq -= left;
+                        p -= up * ES + left * COLB;
+                        push(op, 1);
+                        if (hcur <= 0 || r == 0 || c == 0) break;
+                    }
+                }
+            }
+        };
+
+        for (int r = q;; r += Cc) {
+            const int Tr_hi = T00 - HS * r;
+            if (Tr_hi < 0 || h0 <= 0) break;
+            const int Tr_lo = max(Tr_hi - HS + 1, 0);
+            // ---- 1. where will the path enter this round?  The diagonal through the latest published state.
+            if (threadIdx.x == 0) {
+                int lt = r == 0 ? 0 : min(ld_acquire(latest), r);
+                int tci = ci0, tcj = cj0, tdone = 0;
+                if (lt >= 1) { tci = ld_relaxed(tok + lt * 8 + 2); tcj = ld_relaxed(tok + lt * 8 + 3); tdone = ld_relaxed(tok + lt * 8 + 7); }
+                bc[0] = tci; bc[1] = tcj; bc[2] = tdone;
+            }
+            __syncthreads();
+            const int tci = bc[0], tcj = bc[1];
+            const bool tdone = bc[2] != 0;
+            __syncthreads();
+            if (tdone) break;
+            const int row_r = r == 0 ? ci0 : (Tr_hi + 1) * KL;
+            const long long dbg_t0 = P.dbg ? clock64() : 0;
+            prepare(row_r, tcj - (tci - row_r), r == 0);
+            const long long dbg_t1 = P.dbg ? clock64() : 0;
+            // ---- 2. the round's token
+            if (r > 0) {
+                if (threadIdx.x == 0) {
+                    int done = 0;
+                    for (;;) {
+                        if (ld_acquire(tok + r * 8) == r + 1) break;
+                        const int lt = ld_acquire(latest);
+                        if (lt >= 1 && lt < r && ld_relaxed(tok + lt * 8 + 7)) { done = 1; break; }       // the path ended in an earlier round
+                        __nanosleep(200);
+                    }
+                    bc[7] = done;
+                    if (!done) for (int k = 1; k < 7; ++k) bc[k] = ld_relaxed(tok + r * 8 + k);
+                    if (!done && ld_relaxed(tok + r * 8 + 7)) bc[7] = 1;
+                }
+                __syncthreads();
+                const bool done = bc[7] != 0;
+                hcur = bc[1]; ci = bc[2]; cj = bc[3]; oplen = bc[4]; opword = (uint32_t)bc[5]; beginning = bc[6];
+                __syncthreads();
+                if (done) break;
+            }
+            const long long dbg_t2 = P.dbg ? clock64() : 0;
+            // ---- 3. walk the round's lane-rows
+            bool first = true;
+            for (;;) {
+                if (!first) prepare(ci, cj, true);                     // the path left the prepared corridor: one around the true cell
+                const int ci_before = ci, cj_before = cj;
+                if (threadIdx.x < 32) {
+                    consume(Tr_lo);
+                    if (wl == 0) { bc[0] = hcur; bc[1] = ci; bc[2] = cj; }
+                }
+                __syncthreads();
+                hcur = bc[0]; ci = bc[1]; cj = bc[2];
+                __syncthreads();
+                if (!first && ci == ci_before && cj == cj_before) hcur = 0;   // cannot happen (a corridor around the true cell holds it); never spin
+                first = false;
+                if (P.dbg && threadIdx.x == 0) atomicAdd(P.dbg, 1ull);
+                if (hcur <= 0 || ci < 1 || cj < 1 || (ci - 1) / KL < Tr_lo) break;
+            }
+            // ---- 4. publish the next token
+            const bool done = hcur <= 0 || ci < 1 || cj < 1;
+            if (threadIdx.x == 0) {
+                int32_t *tk = tok + (r + 1) * 8;
+                tk[1] = hcur; tk[2] = ci; tk[3] = cj; tk[4] = (int)oplen; tk[5] = (int)opword; tk[6] = beginning; tk[7] = done ? 1 : 0;
+                __threadfence();
+                st_release(tk, r + 2);
+                __threadfence();
+                atomicMax(latest, r + 1);
+                if (done) {
+                    if (oplen & 15) myops[oplen >> 4] = opword;
+                    beginnings[cell] = beginning;
+                    op_lens[cell] = (int32_t)oplen;
+                }
+                if (P.dbg) { atomicAdd(P.dbg + 3, (unsigned long long)(dbg_t1 - dbg_t0)); atomicAdd(P.dbg + 6, (unsigned long long)(dbg_t2 - dbg_t1)); atomicAdd(P.dbg + 4, (unsigned long long)(clock64() - dbg_t2)); }
+            }
+            if (done) break;
+        }
+        return;
+    }
 
     for (uint32_t cell = gid; cell < n_cells; cell += n_groups) {            // group-uniform
         const uint64_t key = keys[cell];
@@ -935,6 +1293,38 @@ cudaError_t launch_trace_k(const WideParams &P, const uint64_t *keys, uint32_t n
     return cudaGetLastError();
 }
 
+// CTA-wide, pipelined mode: one cluster of C CTAs per max cell (co-scheduled: a CTA waits for tokens of its cluster mates)
+template <int KL>
+cudaError_t launch_trace_pipe(const WideParams &P0, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
+                              int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
+{
+    auto kern = wide_trace_kernel<KL, CTAW_THREADS, CTAW_THREADS, true>;
+    const size_t smem = TraceGeo<KL, true>::smem_bytes(CTAW_TILES) + (size_t)SUB_SMEM_WORDS * 4;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    static const int env_c = getenv("SWB_WIDE_PIPE") ? atoi(getenv("SWB_WIDE_PIPE")) : 0;
+    int c = 8;
+    while (c > 1 && (int64_t)n_cells * c > (int64_t)sm_count) c >>= 1;      // every cluster resident at once: rounds overlap across cells too
+    if (env_c > 0) c = std::min(env_c, 8);
+    WideParams P = P0;
+    for (;; c >>= 1) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)(n_cells * (uint32_t)c));
+        cfg.blockDim = dim3(CTAW_THREADS);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = (unsigned)c; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        int n_clusters = 0;
+        e = c > 1 ? cudaOccupancyMaxActiveClusters(&n_clusters, kern, &cfg) : cudaSuccess;
+        if (c > 1 && (e != cudaSuccess || n_clusters < 1)) { cudaGetLastError(); continue; }   // this cluster size does not fit: halve
+        P.pipe_c = c;
+        return cudaLaunchKernelEx(&cfg, kern, P, keys, n_cells, beginnings, op_lens, ops, ops_stride);
+    }
+}
+
 template <int KL>
 cudaError_t launch_trace_kl(const WideParams &P, const uint64_t *keys, uint32_t n_cells, int32_t *beginnings,
                             int32_t *op_lens, uint32_t *ops, int64_t ops_stride, int sm_count, cudaStream_t st)
@@ -946,7 +1336,7 @@ cudaError_t launch_trace_kl(const WideParams &P, const uint64_t *keys, uint32_t 
     const int g = env_g ? env_g : ((int64_t)n_cells <= (int64_t)sm_count ? 128 : ((int64_t)n_cells < (int64_t)sm_count * 256 ? 32 : 1));
     constexpr int NTB = KL >= 32 ? 64 : 128;                              // byte tiles: 80 / 91 / 56 KB per CTA
     if (bytes) {
-        if (g >= 128) return launch_trace_k<KL, CTAW_THREADS, CTAW_THREADS, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
+        if (g >= 128 && P.mail) return launch_trace_pipe<KL>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
         if (g == 32) return launch_trace_k<KL, NTB, 32, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
         return launch_trace_k<KL, NTB, 1, true>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride, sm_count, st);
     }

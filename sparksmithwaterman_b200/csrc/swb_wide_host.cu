@@ -185,6 +185,16 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         CU(bo.beg.alloc(n_cells, st));
         CU(bo.oplen.alloc(n_cells, st));
         CU(bo.ops.alloc((size_t)n_cells * (size_t)bo.ops_stride, st));
+        P.mail = nullptr; P.mail_latest = nullptr; P.mail_stride = 0; P.pipe_c = 1;
+        if (n_cells > 0 && n_cells <= 65536u) {
+            // few, long walks: the pipelined CTA-wide traceback (swb_wide.cu) passes the walker's state from round to round
+            // through tokens in global memory; one round = 32 lane-rows of KL rows
+            const int64_t stride = (int64_t)m_max / ((int64_t)KL * 32) + 4;
+            const size_t words = (size_t)n_cells * (size_t)stride * 8 + n_cells;
+            CU(ctx->w_mail.reserve(words, st));
+            CU(cudaMemsetAsync(ctx->w_mail.p, 0, words * 4, st));
+            P.mail = ctx->w_mail.p; P.mail_latest = ctx->w_mail.p + (size_t)n_cells * (size_t)stride * 8; P.mail_stride = (int32_t)stride;
+        }
         CU(launch_wide_trace(KL, P, bo.keys.p, n_cells, bo.beg.p, bo.oplen.p, bo.ops.p, bo.ops_stride, ctx->sm_count, st));
         ++*launches;
         CU(toc());
