@@ -23,9 +23,14 @@
 //     list, SmithWaterman.java:176-185; the radix sort of the keys gives its row-major order);
 //   * traceback (GetAlignment.call, SmithWaterman.java:354-436): tiles are recomputed into byte tiles
 //     in shared memory, one per thread.  G = 1: one thread per max cell (many cells, short walks).
-//     G = 32: one warp per max cell (few cells, long walks -- cfg3's 100k-column paths): the lanes
-//     recompute a CORRIDOR of 32 tiles along the predicted diagonal ahead of the walker, lane 0 walks
-//     through them until the path leaves the corridor; wrong predictions only cost another round.
+//     G = 32: one warp per max cell (fewer cells than threads): the lanes recompute a CORRIDOR of 32 tiles
+//     along the predicted diagonal ahead of the walker, the warp walks through them in lock step (one
+//     ballot per diagonal run) until the path leaves the corridor; wrong predictions only cost another
+//     round.  CTA-wide (no more cells than SMs, long walks -- cfg3's 100k-column paths): a cluster of CTAs
+//     per cell; corridors of 128 tiles are recomputed rounds ahead together with per-tile EXIT TABLES (where
+//     does a path that enters the tile here leave it, in how many moves, at what score), so the serial part
+//     of a walk is one table look-up per tile; the moves themselves are re-walked in parallel, 32 tile
+//     visits at a time.
 #include "swb_internal.h"
 
 #include <algorithm>
@@ -426,6 +431,64 @@ struct WTile {
 
 }  // namespace
 
+// Exit tables.  While a tile is recomputed, every cell also carries WHERE the traceback that passes through it leaves
+// the tile, in how many moves, and what score it consumes on the way -- the same three-neighbour dependency as H
+// itself, so it rides along in the same pass:
+//     packed = exit code | moves << 8 | consumed score << 16
+//     exit code: 0..32 = boundary row above the lane (row 0 of the tile) at tile column code; 33..64 = checkpointed
+//     column (column 0) at tile row code - 32; 127 = the path ends inside the tile (a cell of score 0)
+// The type of a positive cell is the reference's cascade (GetCellScore, SmithWaterman.java:227-249: alignment over
+// insertion over deletion on ties; DistributedSW.java:310-326 the other way round).
+constexpr int EXIT_END = 127;
+constexpr int EXIT_TAB = 2 * WCB;                                // entries: bottom row (32 columns), then right column (KL rows <= 32)
+template <int KL, class Fn>
+__device__ __forceinline__ void run_with_exits(WTile<KL> &W, const WCtx &C, bool tie_gt, uint32_t *tab, Fn &&fn)
+{
+    static_assert(KL <= WCB, "right-column entries share the second half of the table");
+    const int gap = C.gap, match = C.match, mismatch = C.mismatch;
+    const int4 *sq = reinterpret_cast<const int4 *>(W.rec + WGeo<KL>::KW);
+    uint32_t Pr[KL];
+#pragma unroll
+    for (int r = 0; r < KL; ++r) Pr[r] = (uint32_t)(WCB + 1 + r);                  // column 0: leaves through (row r + 1, column 0)
+    const uint32_t inc_gap = (1u << 8) + ((uint32_t)gap << 16);
+    int diag = W.diag;
+#pragma unroll 1
+    for (int q = 0; q < WCB / 4; ++q) {
+        const int4 a = __ldg(sq + q);
+        const int tq[4] = {a.x, a.y, a.z, a.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int u = 4 * q + e;
+            const int j = W.j0 + u;
+            const int c = (j >= 1 && j <= C.n) ? (int)__ldg(C.ref + j - 1) : 0xFD;
+            const int top = tq[e];
+            if (c != 0xFD) {
+                int nw = diag, nn = top;
+                uint32_t pnw = (uint32_t)u, pn = (uint32_t)(u + 1);               // boundary row: (0, c - 1) and (0, c)
+#pragma unroll
+                for (int r = 0; r < KL; ++r) {
+                    const int sc = (W.rc[r] == c) ? match : mismatch;
+                    const int dv = nw + sc, wv = W.H[r] + gap, nv = nn + gap;
+                    const int hn = max(max(dv, 0), max(wv, nv));
+                    const uint32_t pa = pnw + (1u << 8) + ((uint32_t)sc << 16), pi2 = pn + inc_gap, pd = Pr[r] + inc_gap;
+                    uint32_t sel = tie_gt ? (wv == hn ? pd : (nv == hn ? pi2 : pa)) : (dv == hn ? pa : (nv == hn ? pi2 : pd));
+                    if (hn <= 0) sel = EXIT_END;
+                    pnw = Pr[r]; Pr[r] = sel; pn = sel;
+                    nw = W.H[r]; W.H[r] = hn; nn = hn;
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < KL; ++r) Pr[r] = EXIT_END;
+            }
+            tab[u] = Pr[KL - 1];
+            fn(u, top, W.H, c);
+            diag = top;
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < KL; ++r) tab[WCB + r] = Pr[r];
+}
+
 // one thread per flagged tile: every cell of the tile that equals the pair's score becomes a key
 template <int KL>
 __global__ void __launch_bounds__(128) wide_locate_kernel(const WideParams P, const WideTask *tasks,
@@ -480,18 +543,10 @@ template <int KL, bool BYTE> struct TraceGeo {
     static constexpr int GUARD = 4 * (COLB + ES) / 4 + 4;           // words before slot 0: the diagonal look-ahead may reach below a slot
     static size_t smem_bytes(int nt) { return ((size_t)nt + GUARD + (size_t)nt * TW) * 4; }
 };
-// CTA-wide groups: speculative SUB-WALKS.  The path enters every lane-row of the corridor through that lane-row's
-// bottom row, at a column the diagonal through the round's start predicts to within a few cells.  All threads walk
-// the lane-rows from NCAND candidate entry columns each (in parallel, one lane-row deep, no carried score: a cell's
-// own stored value stands in for it); the walker then only CHAINS the records: the exit column of one lane-row
-// selects the candidate of the next.  The serial part of a 1,024-row round drops from ~60 tile visits to 32 table
-// look-ups; whatever the candidates miss (or the last lane-rows of a path, where the exact score decides the end)
-// is left to the exact walker below.
-constexpr int SUB_NCAND = 32, SUB_CW = 16, SUB_WORDS = 8, SUB_MAX_MOVES = 60;
-constexpr int CTAW_TILES = 128, CTAW_THREADS = 512;
-constexpr int SUB_STAGE = (15 + (CTAW_TILES / 4) * SUB_MAX_MOVES) / 16 + 4;         // staging words for one round's chained ops
-constexpr int SUB_SMEM_WORDS = (CTAW_TILES / 4) * SUB_NCAND * SUB_WORDS + CTAW_TILES / 4 + SUB_STAGE;
-constexpr int CTAW_ROUND_LANE_ROWS = CTAW_TILES / 4;                               // lane-rows per round of the pipelined mode
+// CTA-wide mode (few max cells, long walks): see the pipelined block in wide_trace_kernel.
+constexpr int CTAW_TILES = 128, CTAW_THREADS = 256;
+constexpr int SUB_STAGE = (15 + 32 * 2 * WCB) / 16 + 4;                             // staging words for one batch of chained tile visits (32 visits of <= 64 moves)
+constexpr int SUB_SMEM_WORDS = CTAW_TILES * 64 + SUB_STAGE;                                  // exit tables [tile][64] + the op staging words
 
 
 template <int KL, int NT, int G, bool BYTE>
@@ -522,7 +577,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                                      ? (int)(threadIdx.x >> 5) * TPW + (int)(threadIdx.x & 31) : -1);
     const int myslot = CTAW ? max(tg, 0) : (int)threadIdx.x;
     uint32_t *mytile = slots + (size_t)myslot * TW;
-    int32_t *subrec = reinterpret_cast<int32_t *>(slots + (size_t)NSLOT * TW);   // CTA-wide: [HS][SUB_NCAND][SUB_WORDS], then sel[HS], stage[SUB_STAGE]
+    int32_t *subrec = reinterpret_cast<int32_t *>(slots + (size_t)NSLOT * TW);   // CTA-wide: exit tables [TILES][64], then stage[SUB_STAGE]
     const unsigned gmask = 0xffffffffu;
     const uint32_t n_groups = gridDim.x * (NT / G);
     const uint32_t gid = (blockIdx.x * NT + threadIdx.x) / G;
@@ -578,28 +633,33 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
         int32_t *latest = P.mail_latest + cell;                        // highest token index published so far
         uint32_t *myops = ops + (int64_t)cell * ops_stride;
         const int T00 = (ci0 - 1) / KL;
+        // corridor shape: 32 lane-rows x 4 blocks along the predicted diagonal, or 16 x 8 for a path of low score density
+        // (many gaps: it wanders off a diagonal -- the random pair of cfg3 left a 4-block corridor 1.4 times per round)
+        const bool wide_shape = (long long)h0 * 2 < (long long)max(match, 1) * (long long)min(ci0, cj0);
+        const int DBr = wide_shape ? 8 : 4, HSr = TILES / DBr;
         const int wl = (int)threadIdx.x;                                // lane of the walking warp (threads 0..31)
         const int big = max(abs(match), abs(mismatch));
         const int bigp = max(max(match, mismatch), 1);
-        int32_t *sel = subrec + HS * SUB_NCAND * SUB_WORDS;
-        uint32_t *stage = reinterpret_cast<uint32_t *>(sel + HS);
+        uint32_t *tabs = reinterpret_cast<uint32_t *>(subrec);           // [TILES][64] exit tables
+        uint32_t *stage = tabs + TILES * 64;
         __shared__ int bc[8];
         int hcur = h0, ci = ci0, cj = cj0, beginning = 0;
         int64_t oplen = 0;
         uint32_t opword = 0;
-        int T0 = 0, pi = 0, pj = 0;                                    // the prepared corridor: lane-rows T0, T0 - 1, ..; diagonal through (pi, pj)
+        int T0 = 0;                                                    // the prepared corridor: lane-rows T0, T0 - 1, .., T0 - HS + 1
 
-        auto prepare = [&](int qi, int qj, bool exact) {
-            pi = qi; pj = qj; T0 = (qi - 1) / KL;
+        // corridor of tiles along the diagonal through (qi, qj): byte tiles + exit tables
+        auto prepare = [&](int qi, int qj) {
+            T0 = (qi - 1) / KL;
             if (tg >= 0) {
-                const int k = tg / DB, d = tg % DB;
+                const int k = tg / DBr, d = tg % DBr;
                 const int Tk = T0 - k;
                 int myblk = -1;
                 if (Tk >= 0) {
                     const int t = Tk % WL;
                     const int di = k == 0 ? 0 : qi - (Tk * KL + KL);   // rows the path climbs to reach lane-row Tk
                     const int step = qj - di - 1 + t;
-                    const int b = (step >= 0 ? step / WCB : -1) + 1 - d;           // blocks b_k + 1 .. b_k - 2
+                    const int b = (step >= 0 ? step / WCB : -1) + DBr / 2 - 1 - d;   // blocks b_k + 1 .. b_k - 2 (b_k + 3 .. b_k - 4)
                     if (b >= 0 && b < C.n_blocks) myblk = b;
                 }
                 if (myblk >= 0) {
@@ -611,7 +671,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     for (int q4 = 0; q4 < KL / 4; ++q4)
                         cw[q4] = (uint32_t)W.rc[4 * q4] | ((uint32_t)W.rc[4 * q4 + 1] << 8) | ((uint32_t)W.rc[4 * q4 + 2] << 16) | ((uint32_t)W.rc[4 * q4 + 3] << 24);
                     uint32_t cacc = 0;
-                    W.run(C, [&](int u, int top, const int (&Hc)[KL], int c) {
+                    run_with_exits<KL>(W, C, tie_gt, tabs + tg * 64, [&](int u, int top, const int (&Hc)[KL], int c) {
                         store_col(u + 1, top, Hc);
                         cacc |= (uint32_t)c << (8 * (u & 3));
                         if ((u & 3) == 3) { cw[KL / 4 + (u >> 2)] = cacc; cacc = 0; }
@@ -621,140 +681,16 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                 slot_blk[tg] = myblk;
             }
             __syncthreads();
-            // ---- sub-walks: record = {candidate index of the next lane-row's entry, moves (< 0: unusable), score consumed,
-            //      beginning, 128 op bits}
-            for (int sub = (int)threadIdx.x; sub < HS * SUB_NCAND; sub += NT) {
-                const int kk = sub / SUB_NCAND, delta = sub % SUB_NCAND - SUB_CW;
-                const int T = T0 - kk;
-                int *out = subrec + sub * SUB_WORDS;
-                int wi = kk == 0 ? qi : (T + 1) * KL;                             // entry: the lane-row's bottom row
-                int wj = qj - (qi - wi) + delta;
-                bool ok = T >= 0 && (kk > 0 || !exact || delta == 0) && wj >= 1 && wj <= C.n;
-                int n = 0, ds = 0, beg = 0;
-                unsigned long long lo = 0, hi = 0;
-                const int t = ok ? T % WL : 0;
-                while (ok) {
-                    if (wj < 1) { ok = false; break; }
-                    const int step = wj - 1 + t;
-                    const int b = step / WCB;
-                    int slot = DB * kk, dd = 0;
-                    while (dd < DB && slot_blk[slot + dd] != b) ++dd;
-                    if (dd == DB) { ok = false; break; }
-                    slot += dd;
-                    int r = wi - T * KL;                                           // 1..KL
-                    int c = step - b * WCB + 1;                                    // 1..WCB
-                    const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
-                    const uint8_t *p = base + c * COLB + r * ES;
-                    const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);
-                    const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);
-                    for (;;) {
-                        const int e0 = elem(p), e1 = elem(p - DG), e2 = elem(p - 2 * DG), e3 = elem(p - 3 * DG), e4 = elem(p - 4 * DG);
-                        const int hn = elem(p - ES), hw = elem(p - COLB);
-                        const int s0 = (pr[0] == pq[0]) ? match : mismatch, s1 = (pr[-1] == pq[-1]) ? match : mismatch;
-                        const int s2 = (pr[-2] == pq[-2]) ? match : mismatch, s3 = (pr[-3] == pq[-3]) ? match : mismatch;
-                        const int lim = min(r, c);
-                        int L = 0;
-                        if (!tie_gt && ((e1 + s0 - e0) & M) == 0) {
-                            const bool ok1 = lim > 1 && ((e2 + s1 - e1) & M) == 0;
-                            const bool ok2 = ok1 && lim > 2 && ((e3 + s2 - e2) & M) == 0;
-                            const bool ok3 = ok2 && lim > 3 && ((e4 + s3 - e3) & M) == 0;
-                            L = 1 + (int)ok1 + (int)ok2 + (int)ok3;
-                        }
-                        unsigned long long bits;
-                        int adv;
-                        if (L > 0) {
-                            ds += s0 + (L > 1 ? s1 : 0) + (L > 2 ? s2 : 0) + (L > 3 ? s3 : 0);
-                            beg = wj - (L - 1);
-                            wi -= L; wj -= L; r -= L; c -= L;
-                            p -= L * DG; pr -= L; pq -= L;
-                            bits = 0x55u >> (8 - 2 * L); adv = L;
-                        } else {
-                            const bool eq_i = ((hn + gap - e0) & M) == 0, eq_d = ((hw + gap - e0) & M) == 0;
-                            const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
-                            beg = wj;
-                            ds += (op == 1u) ? s0 : gap;
-                            const int up = op != 3u, left = op != 2u;
-                            r -= up; wi -= up; pr -= up;
-                            c -= left; wj -= left; pq -= left;
-                            p -= up * ES + left * COLB;
-                            bits = op; adv = 1;
-                        }
-                        if (n < 32) { lo |= bits << (2 * n); if (2 * n + 8 > 64) hi |= bits >> (64 - 2 * n); }
-                        else hi |= bits << (2 * n - 64);
-                        n += adv;
-                        if (n > SUB_MAX_MOVES - 4) { ok = false; break; }
-                        if (r == 0 || c == 0) break;
-                    }
-                    if (!ok || wi == T * KL) break;                                 // the lane-row's boundary row: done
-                }
-                out[0] = wj - (qj - (qi - T * KL)) + SUB_CW;
-                out[1] = ok ? n : -1; out[2] = ds; out[3] = beg;
-                out[4] = (int)(uint32_t)lo; out[5] = (int)(uint32_t)(lo >> 32); out[6] = (int)(uint32_t)hi; out[7] = (int)(uint32_t)(hi >> 32);
-            }
-            __syncthreads();
         };
 
-        // the walking warp (threads 0..31, every lane keeps the whole state): chain, then the exact walker; never above lane-row Tlo
+        // the walking warp (threads 0..31, every lane keeps the whole state); never above lane-row Tlo.
+        //  (a) CHAIN: while the walker stands on an entry edge of a tile (bottom row or right column), the tile's exit
+        //      table says where the path leaves it, in how many moves and what score that consumes -- one look-up per
+        //      tile; up to 32 tile visits per batch, then lane v re-walks visit v inside its byte tile to get the moves
+        //      themselves (n is known, so no score is carried) and prefix sums place them in the op stream;
+        //  (b) the exact walker for one tile visit when (a) cannot move: an interior start cell, the last tiles of a
+        //      path (the exact score decides where it stops).
         auto consume = [&](int Tlo) {
-            if (ci == pi) {
-                // ---- chain: a serial chase through the records, then lane kk appends lane-row kk's moves
-                int idx = cj - pj + SUB_CW, kk_end = 0;
-                for (int kk = 0; kk < HS; ++kk) {
-                    if (T0 - kk < Tlo || idx < 0 || idx >= SUB_NCAND) break;
-                    const int *so = subrec + (kk * SUB_NCAND + idx) * SUB_WORDS;
-                    if (so[1] <= 0) break;
-                    if (wl == 0) sel[kk] = idx;
-                    idx = so[0];
-                    kk_end = kk + 1;
-                }
-                __syncwarp();
-                const bool have = wl < kk_end;
-                const int *so = subrec + (wl * SUB_NCAND + (have ? sel[wl] : 0)) * SUB_WORDS;
-                const int n = have ? so[1] : 0, ds = have ? so[2] : 0;
-                int pn = n, pd = ds;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int a = __shfl_up_sync(0xffffffffu, pn, o), b2 = __shfl_up_sync(0xffffffffu, pd, o);
-                    if (wl >= o) { pn += a; pd += b2; }
-                }
-                // near the end of a path the exact score decides where it stops: those lane-rows go to the walker below
-                const unsigned badm = __ballot_sync(0xffffffffu, have && (hcur - (pd - ds) <= n * bigp));
-                const int kk_ok = badm ? min(kk_end, __ffs((int)badm) - 1) : kk_end;
-                if (kk_ok > 0) {
-                    const int used0 = (int)(oplen & 15);
-                    const int total = __shfl_sync(0xffffffffu, pn, kk_ok - 1);
-                    const int dtot = __shfl_sync(0xffffffffu, pd, kk_ok - 1);
-                    const int nwords = (used0 + total + 15) >> 4;
-                    for (int w = wl; w <= nwords; w += 32) stage[w] = (w == 0) ? opword : 0u;
-                    __syncwarp();
-                    if (wl < kk_ok) {
-                        const int pos = used0 + (pn - n);
-                        const int word0 = pos >> 4, sh = 2 * (pos & 15);
-#pragma unroll
-                        for (int q4 = 0; q4 < 4; ++q4)
-                            if (n > 16 * q4) {
-                                const unsigned long long v = (unsigned long long)(uint32_t)so[4 + q4] << sh;
-                                atomicOr(&stage[word0 + q4], (uint32_t)v);
-                                if ((uint32_t)(v >> 32)) atomicOr(&stage[word0 + q4 + 1], (uint32_t)(v >> 32));
-                            }
-                    }
-                    __syncwarp();
-                    const int64_t oplen_new = oplen + total;
-                    const int full_words = (int)((oplen_new >> 4) - (oplen >> 4));
-                    for (int w = wl; w < full_words; w += 32) myops[(oplen >> 4) + w] = stage[w];
-                    opword = stage[full_words];
-                    oplen = oplen_new;
-                    hcur -= dtot;
-                    beginning = __shfl_sync(0xffffffffu, have ? so[3] : 0, kk_ok - 1);
-                    const int idx_next = __shfl_sync(0xffffffffu, have ? so[0] : 0, kk_ok - 1);
-                    ci = (T0 - (kk_ok - 1)) * KL;
-                    cj = pj - (pi - ci) + (idx_next - SUB_CW);
-                    if (P.dbg && wl == 0) atomicAdd(P.dbg + 5, (unsigned long long)kk_ok);
-                }
-                __syncwarp();
-            }
-            // ---- exact walker (SmithWaterman.java:380-409), all 32 lanes in lock step: lane k probes the diagonal cell
-            // (r - k, c - k), one ballot finds a whole run of alignment moves
             auto push = [&](uint32_t op, int n) {
                 const uint32_t pattern = op * 0x55555555u;
                 while (n > 0) {
@@ -766,16 +702,100 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     if ((oplen & 15) == 0) { if (wl == 0) myops[(oplen >> 4) - 1] = opword; opword = 0; }
                 }
             };
-            while (hcur > 0 && ci >= 1) {
+            for (;;) {
+                // ---- (a) chain
+                int nv = 0, hc = hcur, xi = ci, xj = cj;
+                int my_slot = 0, my_r = 0, my_c = 0, my_n = 0;
+                while (nv < 32 && hc > 0 && xi >= 1 && xj >= 1) {
+                    const int T = (xi - 1) / KL;
+                    const int kk = T0 - T;
+                    if (T < Tlo || kk < 0 || kk >= HSr) break;
+                    const int t = T % WL;
+                    const int step = xj - 1 + t;
+                    const int b = step / WCB;
+                    int slot = DBr * kk, dd = 0;
+                    while (dd < DBr && slot_blk[slot + dd] != b) ++dd;
+                    if (dd == DBr) break;
+                    slot += dd;
+                    const int r = xi - T * KL, c = step - b * WCB + 1;            // 1..KL, 1..WCB
+                    if (r != KL && c != WCB) break;                               // interior cell: (b)
+                    const uint32_t pk = tabs[slot * 64 + (r == KL ? c - 1 : WCB + r - 1)];
+                    const int code = (int)(pk & 127u), n = (int)((pk >> 8) & 127u), ds = (int)pk >> 16;
+                    if (code == EXIT_END || n == 0 || hc <= n * bigp) break;      // the path may end inside: (b)
+                    if (wl == nv) { my_slot = slot; my_r = r; my_c = c; my_n = n; }
+                    hc -= ds;
+                    if (code <= WCB) { xi = T * KL; xj = b * WCB + code - t; }
+                    else { xi = T * KL + (code - WCB); xj = b * WCB - t; }
+                    ++nv;
+                }
+                if (nv > 0) {
+                    // lane v: the moves of visit v (walk order), 2 bits each
+                    unsigned long long lo = 0, hi = 0;
+                    int last_beg = 0;
+                    if (wl < nv) {
+                        const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)my_slot * TW);
+                        const uint8_t *p = base + my_c * COLB + my_r * ES;
+                        const uint8_t *pr = base + TG::CODE0 * 4 + (my_r - 1);
+                        const uint8_t *pq = base + TG::CODE0 * 4 + KL + (my_c - 1);
+                        for (int k = 0; k < my_n; ++k) {
+                            const int e0 = elem(p), e1 = elem(p - DG), hn = elem(p - ES), hw = elem(p - COLB);
+                            const int s0 = (pr[0] == pq[0]) ? match : mismatch;
+                            const bool eq_a = ((e1 + s0 - e0) & M) == 0, eq_i = ((hn + gap - e0) & M) == 0, eq_d = ((hw + gap - e0) & M) == 0;
+                            const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
+                            const int up = op != 3u, left = op != 2u;
+                            pr -= up; pq -= left;
+                            p -= up * ES + left * COLB;
+                            if (k < 32) lo |= (unsigned long long)op << (2 * k); else hi |= (unsigned long long)op << (2 * k - 64);
+                        }
+                        (void)last_beg;
+                    }
+                    const int n = wl < nv ? my_n : 0;
+                    int pn = n;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int a = __shfl_up_sync(0xffffffffu, pn, o);
+                        if (wl >= o) pn += a;
+                    }
+                    const int used0 = (int)(oplen & 15);
+                    const int total = __shfl_sync(0xffffffffu, pn, nv - 1);
+                    const int nwords = (used0 + total + 15) >> 4;
+                    for (int w = wl; w <= nwords; w += 32) stage[w] = (w == 0) ? opword : 0u;
+                    __syncwarp();
+                    if (wl < nv) {
+                        const int pos = used0 + (pn - n);
+                        const int word0 = pos >> 4, sh = 2 * (pos & 15);
+                        const uint32_t w4[4] = {(uint32_t)lo, (uint32_t)(lo >> 32), (uint32_t)hi, (uint32_t)(hi >> 32)};
+#pragma unroll
+                        for (int q4 = 0; q4 < 4; ++q4)
+                            if (n > 16 * q4) {
+                                const unsigned long long v = (unsigned long long)w4[q4] << sh;
+                                atomicOr(&stage[word0 + q4], (uint32_t)v);
+                                if ((uint32_t)(v >> 32)) atomicOr(&stage[word0 + q4 + 1], (uint32_t)(v >> 32));
+                            }
+                    }
+                    __syncwarp();
+                    const int64_t oplen_new = oplen + total;
+                    const int full_words = (int)((oplen_new >> 4) - (oplen >> 4));
+                    for (int w = wl; w < full_words; w += 32) myops[(oplen >> 4) + w] = stage[w];
+                    opword = stage[full_words];
+                    __syncwarp();
+                    oplen = oplen_new;
+                    hcur = hc; ci = xi; cj = xj;
+                    if (P.dbg && wl == 0) atomicAdd(P.dbg + 5, (unsigned long long)nv);
+                    continue;
+                }
+                // ---- (b) exact walker (SmithWaterman.java:380-409), one tile visit, all 32 lanes in lock step: lane k probes
+                // the diagonal cell (r - k, c - k), one ballot finds a whole run of alignment moves
+                if (!(hcur > 0 && ci >= 1 && cj >= 1)) return;
                 const int T = (ci - 1) / KL;
                 const int kk = T0 - T;
-                if (T < Tlo || kk < 0 || kk >= HS || cj < 1) break;
+                if (T < Tlo || kk < 0 || kk >= HSr) return;
                 const int t = T % WL;
                 const int step = cj - 1 + t;
                 const int b = step / WCB;
-                int slot = DB * kk, dd = 0;
-                while (dd < DB && slot_blk[slot + dd] != b) ++dd;
-                if (dd == DB) break;
+                int slot = DBr * kk, dd = 0;
+                while (dd < DBr && slot_blk[slot + dd] != b) ++dd;
+                if (dd == DBr) return;
                 slot += dd;
                 int r = ci - T * KL;                           // 1..KL
                 int c = step - b * WCB + 1;                    // 1..WCB
@@ -820,13 +840,14 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                         if (hcur <= 0 || r == 0 || c == 0) break;
                     }
                 }
+                if (hcur <= 0) return;
             }
         };
 
         for (int r = q;; r += Cc) {
-            const int Tr_hi = T00 - HS * r;
+            const int Tr_hi = T00 - HSr * r;
             if (Tr_hi < 0 || h0 <= 0) break;
-            const int Tr_lo = max(Tr_hi - HS + 1, 0);
+            const int Tr_lo = max(Tr_hi - HSr + 1, 0);
             // ---- 1. where will the path enter this round?  The diagonal through the latest published state.
             if (threadIdx.x == 0) {
                 int lt = r == 0 ? 0 : min(ld_acquire(latest), r);
@@ -841,7 +862,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             if (tdone) break;
             const int row_r = r == 0 ? ci0 : (Tr_hi + 1) * KL;
             const long long dbg_t0 = P.dbg ? clock64() : 0;
-            prepare(row_r, tcj - (tci - row_r), r == 0);
+            prepare(row_r, tcj - (tci - row_r));
             const long long dbg_t1 = P.dbg ? clock64() : 0;
             // ---- 2. the round's token
             if (r > 0) {
@@ -867,7 +888,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             // ---- 3. walk the round's lane-rows
             bool first = true;
             for (;;) {
-                if (!first) prepare(ci, cj, true);                     // the path left the prepared corridor: one around the true cell
+                if (!first) prepare(ci, cj);                           // the path left the prepared corridor: one around the true cell
                 const int ci_before = ci, cj_before = cj;
                 if (threadIdx.x < 32) {
                     consume(Tr_lo);
@@ -947,143 +968,6 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             if (G == 32) __syncwarp(gmask);
             else if (G > 32) __syncthreads();
             const long long dbg_t1 = P.dbg ? clock64() : 0;
-            if (CTAW) {
-                const int ci_s = ci, cj_s = cj;
-                // ---- sub-walks: record = {exit column, moves, score consumed, beginning, 128 op bits}; moves < 0: unusable
-                for (int sub = gl; sub < HS * SUB_NCAND; sub += G) {
-                    const int kk = sub / SUB_NCAND, delta = sub % SUB_NCAND - SUB_CW;
-                    const int T = T0 - kk;
-                    int *out = subrec + sub * SUB_WORDS;
-                    int wi = kk == 0 ? ci_s : (T + 1) * KL;                       // entry: the lane-row's bottom row
-                    int wj = kk == 0 ? cj_s : cj_s - (ci_s - wi) + delta;
-                    bool ok = T >= 0 && (kk > 0 || delta == 0) && wj >= 1 && wj <= C.n;
-                    int n = 0, ds = 0, beg = 0;
-                    unsigned long long lo = 0, hi = 0;
-                    const int t = ok ? T % WL : 0;
-                    while (ok) {
-                        if (wj < 1) { ok = false; break; }
-                        const int step = wj - 1 + t;
-                        const int b = step / WCB;
-                        int slot = leader + DB * kk, dd = 0;
-                        while (dd < DB && slot_blk[slot + dd] != b) ++dd;
-                        if (dd == DB) { ok = false; break; }
-                        slot += dd;
-                        int r = wi - T * KL;                                       // 1..KL
-                        int c = step - b * WCB + 1;                                // 1..WCB
-                        const uint8_t *base = reinterpret_cast<const uint8_t *>(slots + (size_t)slot * TW);
-                        const uint8_t *p = base + c * COLB + r * ES;
-                        const uint8_t *pr = base + TG::CODE0 * 4 + (r - 1);
-                        const uint8_t *pq = base + TG::CODE0 * 4 + KL + (c - 1);
-                        for (;;) {
-                            const int h0 = elem(p), h1 = elem(p - DG), h2 = elem(p - 2 * DG), h3 = elem(p - 3 * DG), h4 = elem(p - 4 * DG);
-                            const int hn = elem(p - ES), hw = elem(p - COLB);
-                            const int s0 = (pr[0] == pq[0]) ? match : mismatch, s1 = (pr[-1] == pq[-1]) ? match : mismatch;
-                            const int s2 = (pr[-2] == pq[-2]) ? match : mismatch, s3 = (pr[-3] == pq[-3]) ? match : mismatch;
-                            const int lim = min(r, c);
-                            int L = 0;
-                            if (!tie_gt && ((h1 + s0 - h0) & M) == 0) {
-                                const bool ok1 = lim > 1 && ((h2 + s1 - h1) & M) == 0;
-                                const bool ok2 = ok1 && lim > 2 && ((h3 + s2 - h2) & M) == 0;
-                                const bool ok3 = ok2 && lim > 3 && ((h4 + s3 - h3) & M) == 0;
-                                L = 1 + (int)ok1 + (int)ok2 + (int)ok3;
-                            }
-                            unsigned long long bits;
-                            int adv;
-                            if (L > 0) {
-                                ds += s0 + (L > 1 ? s1 : 0) + (L > 2 ? s2 : 0) + (L > 3 ? s3 : 0);
-                                beg = wj - (L - 1);
-                                wi -= L; wj -= L; r -= L; c -= L;
-                                p -= L * DG; pr -= L; pq -= L;
-                                bits = 0x55u >> (8 - 2 * L); adv = L;
-                            } else {
-                                const bool eq_i = ((hn + gap - h0) & M) == 0, eq_d = ((hw + gap - h0) & M) == 0;
-                                const uint32_t op = tie_gt ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_i ? 2u : 3u);
-                                beg = wj;
-                                ds += (op == 1u) ? s0 : gap;
-                                const int up = op != 3u, left = op != 2u;
-                                r -= up; wi -= up; pr -= up;
-                                c -= left; wj -= left; pq -= left;
-                                p -= up * ES + left * COLB;
-                                bits = op; adv = 1;
-                            }
-                            if (n < 32) { lo |= bits << (2 * n); if (2 * n + 8 > 64) hi |= bits >> (64 - 2 * n); }
-                            else hi |= bits << (2 * n - 64);
-                            n += adv;
-                            if (n > SUB_MAX_MOVES - 4) { ok = false; break; }
-                            if (r == 0 || c == 0) break;
-                        }
-                        if (!ok || wi == T * KL) break;                             // the lane-row's boundary row: done
-                    }
-                    out[0] = wj - (cj_s - (ci_s - T * KL)) + SUB_CW;              // candidate index of the next lane-row's entry
-                    out[1] = ok ? n : -1; out[2] = ds; out[3] = beg;
-                    out[4] = (int)(uint32_t)lo; out[5] = (int)(uint32_t)(lo >> 32); out[6] = (int)(uint32_t)hi; out[7] = (int)(uint32_t)(hi >> 32);
-                }
-                __syncthreads();
-                if (P.dbg && gl == 0) atomicAdd(P.dbg + 6, (unsigned long long)(clock64() - dbg_t1));
-                const long long dbg_t2 = P.dbg ? clock64() : 0;
-                if (gl < 32) {
-                    // ---- chain: a serial chase through the records (one look-up per lane-row), then lane kk of the first
-                    // warp appends lane-row kk's moves: prefix sums give every lane-row its bit offset and the score left
-                    int32_t *sel = subrec + HS * SUB_NCAND * SUB_WORDS;
-                    uint32_t *stage = reinterpret_cast<uint32_t *>(sel + HS);
-                    const int bigp = max(max(match, mismatch), 1);
-                    int idx = SUB_CW, kk_end = 0;
-                    for (int kk = 0; kk < HS; ++kk) {
-                        if (T0 - kk < 0 || idx < 0 || idx >= SUB_NCAND) break;
-                        const int *so = subrec + (kk * SUB_NCAND + idx) * SUB_WORDS;
-                        if (so[1] <= 0) break;
-                        if (gl == 0) sel[kk] = idx;
-                        idx = so[0];
-                        kk_end = kk + 1;
-                    }
-                    __syncwarp();
-                    const bool have = gl < kk_end;
-                    const int *so = subrec + (gl * SUB_NCAND + (have ? sel[gl] : 0)) * SUB_WORDS;
-                    const int n = have ? so[1] : 0, ds = have ? so[2] : 0;
-                    int pn = n, pd = ds;
-#pragma unroll
-                    for (int o = 1; o < 32; o <<= 1) {
-                        const int a = __shfl_up_sync(0xffffffffu, pn, o), b2 = __shfl_up_sync(0xffffffffu, pd, o);
-                        if (gl >= o) { pn += a; pd += b2; }
-                    }
-                    // near the end of a path the exact score decides where it stops: those lane-rows go to the walker below
-                    const unsigned badm = __ballot_sync(0xffffffffu, have && (hcur - (pd - ds) <= n * bigp));
-                    const int kk_ok = badm ? min(kk_end, __ffs((int)badm) - 1) : kk_end;
-                    if (kk_ok > 0) {
-                        const int used0 = (int)(oplen & 15);
-                        const int total = __shfl_sync(0xffffffffu, pn, kk_ok - 1);
-                        const int dtot = __shfl_sync(0xffffffffu, pd, kk_ok - 1);
-                        const int nwords = (used0 + total + 15) >> 4;
-                        for (int w = gl; w <= nwords; w += 32) stage[w] = (w == 0) ? opword : 0u;
-                        __syncwarp();
-                        if (gl < kk_ok) {
-                            const int pos = used0 + (pn - n);
-                            const int word0 = pos >> 4, sh = 2 * (pos & 15);
-#pragma unroll
-                            for (int q = 0; q < 4; ++q)
-                                if (n > 16 * q) {
-                                    const unsigned long long v = (unsigned long long)(uint32_t)so[4 + q] << sh;
-                                    atomicOr(&stage[word0 + q], (uint32_t)v);
-                                    if ((uint32_t)(v >> 32)) atomicOr(&stage[word0 + q + 1], (uint32_t)(v >> 32));
-                                }
-                        }
-                        __syncwarp();
-                        const int64_t oplen_new = oplen + total;
-                        const int full_words = (int)((oplen_new >> 4) - (oplen >> 4));
-                        for (int w = gl; w < full_words; w += 32) myops[(oplen >> 4) + w] = stage[w];
-                        opword = stage[full_words];
-                        oplen = oplen_new;
-                        hcur -= dtot;
-                        beginning = __shfl_sync(0xffffffffu, have ? so[3] : 0, kk_ok - 1);
-                        const int idx_next = __shfl_sync(0xffffffffu, have ? so[0] : 0, kk_ok - 1);
-                        ci = (T0 - (kk_ok - 1)) * KL;
-                        cj = cj_s - (ci_s - ci) + (idx_next - SUB_CW);
-                        if (P.dbg && gl == 0) atomicAdd(P.dbg + 5, (unsigned long long)kk_ok);
-                    }
-                    __syncwarp();
-                    if (P.dbg && gl == 0) atomicAdd(P.dbg + 7, (unsigned long long)(clock64() - dbg_t2));
-                }
-            }
             if (G == 1) {
                 // ---- walk (SmithWaterman.java:380-409): one thread per max cell
                 for (;;) {
@@ -1303,11 +1187,14 @@ cudaError_t launch_trace_pipe(const WideParams &P0, const uint64_t *keys, uint32
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     static const int env_c = getenv("SWB_WIDE_PIPE") ? atoi(getenv("SWB_WIDE_PIPE")) : 0;
-    int c = 8;
-    while (c > 1 && (int64_t)n_cells * c > (int64_t)sm_count) c >>= 1;      // every cluster resident at once: rounds overlap across cells too
+    // CTAs per cell.  Measured on cfg3 (ten 100 kbp pairs): 1 / 2 / 3 / 4 / 8 CTAs -> 9.3 / 4.9 / 4.7 / 5.6 / 7.8 ms.  Three keep one
+    // prepare hidden behind two walks; more only lengthen the distance over which the entry point is predicted (the
+    // path drifts off the predicted diagonal and the prepared corridor has to be redone).
+    int c = 3;
+    while (c > 1 && (int64_t)n_cells * c > (int64_t)sm_count) --c;           // every cluster resident at once
     if (env_c > 0) c = std::min(env_c, 8);
     WideParams P = P0;
-    for (;; c >>= 1) {
+    for (;; --c) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)(n_cells * (uint32_t)c));
         cfg.blockDim = dim3(CTAW_THREADS);

@@ -189,7 +189,7 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         if (n_cells > 0 && n_cells <= 65536u) {
             // few, long walks: the pipelined CTA-wide traceback (swb_wide.cu) passes the walker's state from round to round
             // through tokens in global memory; one round = 32 lane-rows of KL rows
-            const int64_t stride = (int64_t)m_max / ((int64_t)KL * 32) + 4;
+            const int64_t stride = (int64_t)m_max / ((int64_t)KL * 16) + 4;      // a round is 32 or 16 lane-rows
             const size_t words = (size_t)n_cells * (size_t)stride * 8 + n_cells;
             CU(ctx->w_mail.reserve(words, st));
             CU(cudaMemsetAsync(ctx->w_mail.p, 0, words * 4, st));

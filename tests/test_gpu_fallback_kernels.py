@@ -54,7 +54,8 @@ print("checked", n)
                                     "SWB_REF_PARTS=3", "SWB_REF_PARTS=6,SWB_NO_TILE_TRACE",
                                     # every wide-path geometry and traceback grouping on the same inputs
                                     "SWB_WIDE_KL=8", "SWB_WIDE_KL=32,SWB_WIDE_TRACE_G=1", "SWB_WIDE_KL=16,SWB_WIDE_TRACE_G=32",
-                                    "SWB_WIDE_KL=32,SWB_WIDE_TRACE_G=128", "SWB_WIDE_NO_PROFILE"])
+                                    "SWB_WIDE_KL=32,SWB_WIDE_TRACE_G=128", "SWB_WIDE_KL=16,SWB_WIDE_TRACE_G=128,SWB_WIDE_PIPE=2",
+                                    "SWB_WIDE_KL=8,SWB_WIDE_TRACE_G=128,SWB_WIDE_PIPE=4", "SWB_WIDE_NO_PROFILE"])
 def test_forced_fallback_kernels_are_exact(switch):
     env = dict(os.environ)
     for s in switch.split(","):
