@@ -220,3 +220,31 @@ def test_jni_shim_compiles_and_matches_the_java_natives(tmp_path):
                  if " swb_" in l}
     lib_syms = {l.split()[-1] for l in subprocess.check_output(["nm", "-D", "--defined-only", _ffi.LIB_PATH], text=True).splitlines()}
     assert undefined and undefined <= lib_syms
+
+
+def test_running_median_and_refset_info(tmp_path):
+    """metrics.RunningMedian / RefSetInfo mirror the reference's reporter (src/metrics/RunningMedian.java:111-171,
+    RefSetInfo.java:56-196): two-heap median, per-directory statistics, Java-formatted report."""
+    import random
+    import statistics
+    from sparksmithwaterman_b200 import metrics
+    rnd = random.Random(3)
+    rm = metrics.RunningMedian()
+    seen = []
+    for _ in range(500):
+        v = rnd.randint(0, 5000)
+        seen.append(v)
+        rm.add(v)
+        assert rm.get_running_median() == statistics.median(seen)
+    (tmp_path / "sub").mkdir()
+    (tmp_path / "b.fa").write_text(">gi|1|x\nACGT\nAC\n>gi|2|y\nA\n")
+    (tmp_path / "sub" / "a.fa").write_text(">gi|3|z\n" + "ACGTACGTAC" * 123 + "\n")
+    d, n_files, longs, doubles, files = metrics.RefSetInfo.get_info(str(tmp_path))
+    assert n_files == 2 and longs == [3, 1237, 1, 1230] and doubles[1] == 6.0 and abs(doubles[0] - 1237 / 3) < 1e-9
+    assert sorted(files) == [("a.fa", 1), ("b.fa", 2)]
+    text = metrics.RefSetInfo.all_info_str(str(tmp_path))
+    assert "# reference sequences  =  3          \n" in text and "# total base pairs     =  1,237      \n" in text
+    assert "max     =  1,230     \n" in text and "mean    =  412.33 \n" in text and "median  =  6.00   \n" in text
+    assert "File Name                          |# Sequences\n-----------------------------------+-----------\n" \
+           "a.fa                               |          1\nb.fa                               |          2\n" in text
+    assert metrics.info_of_lengths([])[0] == [0, 0, (1 << 63) - 1, 0]
