@@ -407,8 +407,11 @@ def main():
                 prof = json.load(f)
             cap = next(k for k in prof["kernels"] if "fill_bias_kernel" in k["kernel"])
             gb = float(cap["dram__bytes_read.sum"].split()[0]) + float(cap["dram__bytes_write.sum"].split()[0])
-            rp_per_launch = (B / 2.0) / max(agg["batches"] / K, 1)
-            traffic = round(gb * 1e9 / float(prof["meta"]["read_pairs_per_launch"]) * rp_per_launch)
+            # a launch covers (read pairs) x (reference bases of one part); the step's read-pair x base product is
+            # spread over its launches
+            launches_per_step = max(agg["batches"] / K, 1)
+            cap_rp_bases = float(prof["meta"].get("rp_bases_per_launch") or prof["meta"]["read_pairs_per_launch"] * ref_bases)
+            traffic = round(gb * 1e9 / cap_rp_bases * (B / 2.0) * ref_bases / launches_per_step)
             traffic_src = f"scaled from profiles/{prof_name} (ncu --set full of the same kernel and refset), not measured in this run"
             break
         except Exception:
