@@ -72,3 +72,34 @@ def test_long_pair_homologous(engine):
         got = res.pair(r, 0)
         assert got[0] == exp.score and got[1] == exp.cells and got[2] == exp.sites
     res.free(); rs.free()
+
+
+@pytest.mark.parametrize("tie_gt", [False, True])
+@pytest.mark.parametrize("scores", [(5, -3, -4), (2, -1, -2)])
+def test_few_long_walks_cluster_traceback(engine, tie_gt, scores):
+    """Few max cells with long paths take the pipelined CTA-wide traceback (cluster of CTAs per cell, per-tile exit
+    tables, table chain + parallel re-walk): a homologous pair, a gappy one (low score density: the 16 x 8 corridor),
+    a low-complexity one where directions tie all along the path, under both tie rules (SmithWaterman.java:227-249
+    '>=' cascade, DistributedSW.java:310-326 strict '>': there the host layer re-orders the cells diagonal-major and
+    stably by beginning, sw.distributed_order)."""
+    from sparksmithwaterman_b200 import sw
+    rnd = random.Random(71 + int(tie_gt))
+    a = _rand(rnd, 3300)
+    b = _mutate(rnd, a, sub=0.06, indel=0.03)
+    g = _mutate(rnd, a[500:2900], sub=0.25, indel=0.30)                  # gappy: wanders off the diagonal
+    lc = _mutate(rnd, "AC" * 1600, sub=0.03, indel=0.0)
+    lc_read = _mutate(rnd, lc[200:2400], sub=0.02, indel=0.01)
+    refs, reads = [a, lc], [b, g, lc_read]
+    rs = engine.load_refset(refs)
+    res = rs.align(reads, scores, tie_gt=tie_gt).cache()
+    assert res.total_cells <= 100, res.total_cells                       # else another traceback mode would run
+    for r in range(len(refs)):
+        for q in range(len(reads)):
+            exp = oracle.align(refs[r], reads[q], *scores, tie_gt=tie_gt)
+            score, cells, sites = res.pair(r, q)
+            if tie_gt:
+                cells, sites = sw.distributed_order(cells, sites)
+            assert score == exp.score, (r, q)
+            assert cells == exp.cells, (r, q)
+            assert sites == exp.sites, (r, q)
+    res.free(); rs.free()
