@@ -704,6 +704,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             };
             for (;;) {
                 // ---- (a) chain
+                const long long dc0 = P.dbg ? clock64() : 0;
                 int nv = 0, hc = hcur, xi = ci, xj = cj;
                 int my_slot = 0, my_r = 0, my_c = 0, my_n = 0;
                 while (nv < 32 && hc > 0 && xi >= 1 && xj >= 1) {
@@ -730,6 +731,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                 }
                 if (nv > 0) {
                     // lane v: the moves of visit v (walk order), 2 bits each
+                    const long long dc1 = P.dbg ? clock64() : 0;
                     unsigned long long lo = 0, hi = 0;
                     int last_beg = 0;
                     if (wl < nv) {
@@ -749,6 +751,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                         }
                         (void)last_beg;
                     }
+                    const long long dc2 = P.dbg ? clock64() : 0;
                     const int n = wl < nv ? my_n : 0;
                     int pn = n;
 #pragma unroll
@@ -781,7 +784,11 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     __syncwarp();
                     oplen = oplen_new;
                     hcur = hc; ci = xi; cj = xj;
-                    if (P.dbg && wl == 0) atomicAdd(P.dbg + 5, (unsigned long long)nv);
+                    if (P.dbg && wl == 0) {
+                        atomicAdd(P.dbg + 5, (unsigned long long)nv);
+                        atomicAdd(P.dbg + 8, (unsigned long long)(dc1 - dc0)); atomicAdd(P.dbg + 9, (unsigned long long)(dc2 - dc1));
+                        atomicAdd(P.dbg + 10, (unsigned long long)(clock64() - dc2)); atomicAdd(P.dbg + 11, 1ull);
+                    }
                     continue;
                 }
                 // ---- (b) exact walker (SmithWaterman.java:380-409), one tile visit, all 32 lanes in lock step: lane k probes

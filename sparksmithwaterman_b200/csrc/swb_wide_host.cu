@@ -131,8 +131,8 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         static const bool wide_debug = getenv("SWB_WIDE_DEBUG") != nullptr;
         P.dbg = nullptr;
         if (wide_debug) {
-            CU(ctx->w_dbg.reserve(8, st));
-            CU(cudaMemsetAsync(ctx->w_dbg.p, 0, 64, st));
+            CU(ctx->w_dbg.reserve(16, st));
+            CU(cudaMemsetAsync(ctx->w_dbg.p, 0, 128, st));
             P.dbg = ctx->w_dbg.p;
         }
         uint32_t *d_ntasks = ctx->counters.p, *d_ncells = ctx->counters.p + 1, *d_ticket = ctx->counters.p + 2;
@@ -200,10 +200,11 @@ int run_wide_path(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, const
         CU(toc());
         CU(cudaStreamSynchronize(st));      // the host tables of this batch are reused by the next one
         if (P.dbg) {
-            unsigned long long h[8];
-            CU(cudaMemcpy(h, P.dbg, 64, cudaMemcpyDeviceToHost));
-            fprintf(stderr, "[swb wide] KL=%d pairs=%d cells=%u: traceback rounds=%llu tiles walked=%llu tiles recomputed=%llu; group-leader cycles: recompute %llu walk %llu; lane-rows chained %llu (sub-walk phase %llu cycles, chain %llu)\n",
-                    KL, np, n_cells, h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]);
+            unsigned long long h[16];
+            CU(cudaMemcpy(h, P.dbg, 128, cudaMemcpyDeviceToHost));
+            fprintf(stderr, "[swb wide] KL=%d pairs=%d cells=%u: traceback rounds=%llu, tiles: recomputed %llu, walked exactly %llu, chained %llu in %llu batches; "
+                            "cycles (first thread of every CTA): prepare %llu, token wait %llu, consume %llu (chain %llu, re-walk %llu, append %llu)\n",
+                    KL, np, n_cells, h[0], h[2], h[1], h[5], h[11], h[3], h[6], h[4], h[8], h[9], h[10]);
         }
         res->stats[8] += n_cells;
         res->batches.push_back(std::move(bo));
