@@ -546,7 +546,8 @@ template <int KL, bool BYTE> struct TraceGeo {
 // CTA-wide mode (few max cells, long walks): see the pipelined block in wide_trace_kernel.
 constexpr int CTAW_TILES = 128, CTAW_THREADS = 256;
 constexpr int SUB_STAGE = (15 + 32 * 2 * WCB) / 16 + 4;                             // staging words for one batch of chained tile visits (32 visits of <= 64 moves)
-constexpr int SUB_SMEM_WORDS = CTAW_TILES * 64 + SUB_STAGE;                                  // exit tables [tile][64] + the op staging words
+constexpr int NXT_STRIDE = 66;                                                     // next-entry table: 65 exit codes per tile (uint16), padded
+constexpr int SUB_SMEM_WORDS = CTAW_TILES * 64 + CTAW_TILES * NXT_STRIDE / 2 + SUB_STAGE;   // exit tables [tile][64], next-entry tables, op staging
 
 
 template <int KL, int NT, int G, bool BYTE>
@@ -641,7 +642,8 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
         const int big = max(abs(match), abs(mismatch));
         const int bigp = max(max(match, mismatch), 1);
         uint32_t *tabs = reinterpret_cast<uint32_t *>(subrec);           // [TILES][64] exit tables
-        uint32_t *stage = tabs + TILES * 64;
+        uint16_t *nxt = reinterpret_cast<uint16_t *>(tabs + TILES * 64); // [TILES][NXT_STRIDE]: exit code -> slot * 64 + entry of the next tile
+        uint32_t *stage = tabs + TILES * 64 + TILES * NXT_STRIDE / 2;
         __shared__ int bc[8];
         int hcur = h0, ci = ci0, cj = cj0, beginning = 0;
         int64_t oplen = 0;
@@ -649,12 +651,12 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
         int T0 = 0;                                                    // the prepared corridor: lane-rows T0, T0 - 1, .., T0 - HS + 1
 
         // corridor of tiles along the diagonal through (qi, qj): byte tiles + exit tables
-        auto prepare = [&](int qi, int qj) {
+        auto prepare = [&](int qi, int qj, int Tlo) {
             T0 = (qi - 1) / KL;
+            int myblk = -1;
             if (tg >= 0) {
                 const int k = tg / DBr, d = tg % DBr;
                 const int Tk = T0 - k;
-                int myblk = -1;
                 if (Tk >= 0) {
                     const int t = Tk % WL;
                     const int di = k == 0 ? 0 : qi - (Tk * KL + KL);   // rows the path climbs to reach lane-row Tk
@@ -679,6 +681,36 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                     if (P.dbg) atomicAdd(P.dbg + 2, 1ull);
                 }
                 slot_blk[tg] = myblk;
+            }
+            __syncthreads();
+            // next-entry table of my tile: the cell a path leaves the tile through is an entry cell (bottom row or right
+            // column) of a neighbouring tile -- which slot, which entry -- or of none (outside the corridor / the round)
+            if (tg >= 0 && myblk >= 0) {
+                const int kk = tg / DBr, Tk = T0 - kk, t = Tk % WL;
+                // the only tiles a path can step into from this one: the lane-row above (blocks b - 1, b, b + 1: its skew
+                // differs by one step, or by 31 across a band boundary) and block b - 1 of this lane-row
+                auto find = [&](int kk2, int b2) -> int {
+                    if (kk2 < 0 || kk2 >= HSr || T0 - kk2 < Tlo || T0 - kk2 < 0 || b2 < 0) return -1;
+                    int sl = -1;
+                    for (int dd = 0; dd < DBr; ++dd) if (slot_blk[DBr * kk2 + dd] == b2) sl = DBr * kk2 + dd;
+                    return sl;
+                };
+                const int sUm = find(kk + 1, myblk - 1), sU0 = find(kk + 1, myblk), sUp = find(kk + 1, myblk + 1), sL = find(kk, myblk - 1);
+                const int t2 = (Tk - 1 + WL) % WL;                                   // skew of the lane-row above
+                for (int code = 0; code <= 2 * WCB; ++code) {
+                    int nx = 0xFFFF;
+                    if (code <= WCB) {                                              // leaves through the boundary row, tile column `code`
+                        const int xj = myblk * WCB + code - t;
+                        if (Tk >= 1 && xj >= 1) {
+                            const int step2 = xj - 1 + t2, b2 = step2 / WCB;
+                            const int sl = b2 == myblk ? sU0 : (b2 == myblk - 1 ? sUm : (b2 == myblk + 1 ? sUp : -1));
+                            if (sl >= 0) nx = sl * 64 + (step2 - b2 * WCB);         // bottom row of the tile above, column c2 = step2 - b2 * WCB + 1
+                        }
+                    } else if (sL >= 0 && myblk * WCB - t >= 1) {
+                        nx = sL * 64 + WCB + (code - WCB) - 1;                      // right column of the tile to the left, row code - WCB
+                    }
+                    nxt[tg * NXT_STRIDE + code] = (uint16_t)nx;
+                }
             }
             __syncthreads();
         };
@@ -707,27 +739,38 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
                 const long long dc0 = P.dbg ? clock64() : 0;
                 int nv = 0, hc = hcur, xi = ci, xj = cj;
                 int my_slot = 0, my_r = 0, my_c = 0, my_n = 0;
-                while (nv < 32 && hc > 0 && xi >= 1 && xj >= 1) {
+                if (hc > 0 && xi >= 1 && xj >= 1) {
+                    // the tile and entry the walker stands on (found the slow way once per batch) ...
                     const int T = (xi - 1) / KL;
                     const int kk = T0 - T;
-                    if (T < Tlo || kk < 0 || kk >= HSr) break;
-                    const int t = T % WL;
-                    const int step = xj - 1 + t;
-                    const int b = step / WCB;
-                    int slot = DBr * kk, dd = 0;
-                    while (dd < DBr && slot_blk[slot + dd] != b) ++dd;
-                    if (dd == DBr) break;
-                    slot += dd;
-                    const int r = xi - T * KL, c = step - b * WCB + 1;            // 1..KL, 1..WCB
-                    if (r != KL && c != WCB) break;                               // interior cell: (b)
-                    const uint32_t pk = tabs[slot * 64 + (r == KL ? c - 1 : WCB + r - 1)];
-                    const int code = (int)(pk & 127u), n = (int)((pk >> 8) & 127u), ds = (int)pk >> 16;
-                    if (code == EXIT_END || n == 0 || hc <= n * bigp) break;      // the path may end inside: (b)
-                    if (wl == nv) { my_slot = slot; my_r = r; my_c = c; my_n = n; }
-                    hc -= ds;
-                    if (code <= WCB) { xi = T * KL; xj = b * WCB + code - t; }
-                    else { xi = T * KL + (code - WCB); xj = b * WCB - t; }
-                    ++nv;
+                    int cur = -1;
+                    if (T >= Tlo && kk >= 0 && kk < HSr) {
+                        const int step = xj - 1 + T % WL;
+                        const int b = step / WCB;
+                        int slot = DBr * kk, dd = 0;
+                        while (dd < DBr && slot_blk[slot + dd] != b) ++dd;
+                        const int r = xi - T * KL, c = step - b * WCB + 1;            // 1..KL, 1..WCB
+                        if (dd < DBr && (r == KL || c == WCB)) cur = (slot + dd) * 64 + (r == KL ? c - 1 : WCB + r - 1);
+                    }
+                    // ... then two look-ups per tile visit: the exit table of the entry, the next-entry table of the exit
+                    int last_cur = -1, last_code = 0;
+                    while (nv < 32 && cur >= 0) {
+                        const uint32_t pk = tabs[cur];
+                        const int code = (int)(pk & 127u), n = (int)((pk >> 8) & 127u), ds = (int)pk >> 16;
+                        if (code == EXIT_END || n == 0 || hc <= n * bigp) break;  // the path may end inside: (b)
+                        if (wl == nv) { my_slot = cur >> 6; const int e = cur & 63; my_r = e < WCB ? KL : e - WCB + 1; my_c = e < WCB ? e + 1 : WCB; my_n = n; }
+                        hc -= ds;
+                        last_cur = cur; last_code = code;
+                        ++nv;
+                        const int nx = (int)nxt[(cur >> 6) * NXT_STRIDE + code];
+                        cur = nx == 0xFFFF ? -1 : nx;
+                    }
+                    if (nv > 0) {
+                        const int slot = last_cur >> 6;
+                        const int T2 = T0 - slot / DBr, t2 = T2 % WL, b2 = slot_blk[slot];
+                        if (last_code <= WCB) { xi = T2 * KL; xj = b2 * WCB + last_code - t2; }
+                        else { xi = T2 * KL + (last_code - WCB); xj = b2 * WCB - t2; }
+                    }
                 }
                 if (nv > 0) {
                     // lane v: the moves of visit v (walk order), 2 bits each
@@ -869,7 +912,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             if (tdone) break;
             const int row_r = r == 0 ? ci0 : (Tr_hi + 1) * KL;
             const long long dbg_t0 = P.dbg ? clock64() : 0;
-            prepare(row_r, tcj - (tci - row_r));
+            prepare(row_r, tcj - (tci - row_r), Tr_lo);
             const long long dbg_t1 = P.dbg ? clock64() : 0;
             // ---- 2. the round's token
             if (r > 0) {
@@ -895,7 +938,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
             // ---- 3. walk the round's lane-rows
             bool first = true;
             for (;;) {
-                if (!first) prepare(ci, cj);                           // the path left the prepared corridor: one around the true cell
+                if (!first) prepare(ci, cj, Tr_lo);                    // the path left the prepared corridor: one around the true cell
                 const int ci_before = ci, cj_before = cj;
                 if (threadIdx.x < 32) {
                     consume(Tr_lo);
