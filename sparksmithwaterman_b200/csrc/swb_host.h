@@ -223,6 +223,7 @@ struct swb_refset {
     mutable std::map<SegKey, std::shared_ptr<SegTables>> seg_cache;
     std::vector<swb_refset *> parts;
     std::vector<int64_t> part_first;            // first global reference index of each part
+    swb_refset *whole = nullptr;                // a set with parts: the same references as one set (device-resident / scores-only calls)
     const swb_refset *parent = nullptr;
 };
 
