@@ -572,7 +572,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
             auto &idx = classes[(size_t)kc];
             if (idx.empty()) continue;
             const int K = kKList[kc];
-            const int KW = ((K + 1 + 3) / 4) * 4;
+            const int RW = ((K + 1 + 7) / 8 + CB / 8) * 8;        // record words per (block, lane): Geo<K>::RW
             std::stable_sort(idx.begin(), idx.end(),
                              [&](int32_t a, int32_t b) { return rd->len[(size_t)a] > rd->len[(size_t)b]; });
             const int64_t n_rp_total = ((int64_t)idx.size() + 1) / 2;
@@ -602,7 +602,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
             // stage F (ctx->stream_fill): fill of batch k+1;  stage T (ctx->stream): flag/locate/sort/trace of
             // batch k.  The fill saturates the integer pipe, the traceback is latency-bound: run together they
             // share the SMs.  Two checkpoint workspaces, ping-pong; events order the reuse.
-            const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)(KW + CB) * GL * 4 + GL * 4);   // block records (checkpoint + seam) + tile max
+            const int64_t bytes_per_rp = rs->blocks_per_rp * ((int64_t)RW * GL * 4 + GL * 4);   // block records (checkpoint + seam) + tile max
             int64_t rp_per_batch = std::max<int64_t>(1, ctx->ws_bytes / std::max<int64_t>(bytes_per_rp, 1));
             const bool pipelined = !(flags & SWB_F_SCORES_ONLY) && n_rp_total > rp_per_batch / 2 && ctx->pipeline;
             if (pipelined) rp_per_batch = std::max<int64_t>(1, rp_per_batch / 2);       // two workspaces
@@ -638,7 +638,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
                 if (ev_trace_done[S.buf]) CU(cudaStreamWaitEvent(sF, ev_trace_done[S.buf], 0));
                 CU(rpb.reserve(S.h_rp.size(), sF));
                 CU(cudaMemcpyAsync(rpb.p, S.h_rp.data(), S.h_rp.size() * 4, cudaMemcpyHostToDevice, sF));
-                const size_t ck_words = (size_t)S.n_rp * rs->blocks_per_rp * (KW + CB) * GL;
+                const size_t ck_words = (size_t)S.n_rp * rs->blocks_per_rp * RW * GL;
                 const size_t tmx_words = (size_t)S.n_rp * rs->blocks_per_rp * GL;
                 CU(ck.reserve(ck_words, sF));
                 CU(tmx.reserve(tmx_words, sF));

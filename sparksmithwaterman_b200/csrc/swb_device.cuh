@@ -84,33 +84,63 @@ __device__ __forceinline__ void load_profile(const uint32_t *p, uint32_t (&sv)[K
     }
 }
 
-// Block record of one lane (Geo<K>::RW words, contiguous): words 0..K-1 = H at the block start, word K = diag,
-// words KW..KW+CB-1 = the seam.  The fill stages a group's 8 records in shared memory (lane t at stage + t*RW;
-// 8 lanes x 16 B at a 144 B stride: conflict-free) and copies them out with coalesced STG.128.
+// Block records in HBM.  The record of (block, lane t) is RP PIECES of 32 bytes: pieces 0 .. CKP-1 hold the checkpoint
+// (words 0..K-1 = H at the block start, word K = diag), the last CB/8 the seam.  Piece p of a block's eight lanes is
+// contiguous (256 bytes at ((blk * RP + p) * GL + t) * 32), so the fill writes every piece straight from registers with
+// one 256-bit store per lane (STG.E.ENL2.256, sm_100) -- no shared-memory staging (staging + copy-out cost 108 LSU
+// wavefronts per warp and block, the direct stores 40) -- and a traceback reads a lane's record as RP whole sectors.
+// (16-byte chunks interleaved over the lanes gave the fill the same gain but made a tile nine half-used sectors:
+// tile traceback 4.1 -> 5.4 ms per step.)
+constexpr int REC_P = GL * 8;                                        // words between consecutive pieces of one lane
 template <int K>
-__device__ __forceinline__ void stage_checkpoint(uint32_t *my_stage, const uint32_t (&H)[K], uint32_t diag)
+__device__ __forceinline__ uint32_t *rec_lane(uint32_t *rec, int64_t blk, int t)
 {
-    constexpr int KW = Geo<K>::KW;
+    return rec + blk * (int64_t)(GL * Geo<K>::RW) + t * 8;
+}
+template <int K>
+__device__ __forceinline__ const uint32_t *rec_lane(const uint32_t *rec, int64_t blk, int t)
+{
+    return rec + blk * (int64_t)(GL * Geo<K>::RW) + t * 8;
+}
+__device__ __forceinline__ void stg256(uint32_t *p, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e, uint32_t f,
+                                       uint32_t g, uint32_t h)
+{
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a), "r"(b), "r"(c), "r"(d), "r"(e),
+                 "r"(f), "r"(g), "r"(h) : "memory");
+}
+__device__ __forceinline__ void ldg256(const uint32_t *p, uint32_t (&w)[8])
+{
+    asm volatile("ld.global.nc.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+}
+
+// the lane's checkpoint (K cells + diag) -> pieces 0 .. CKP-1 of its record
+template <int K>
+__device__ __forceinline__ void store_checkpoint(uint32_t *lane_rec, const uint32_t (&H)[K], uint32_t diag)
+{
 #pragma unroll
-    for (int q = 0; q < KW / 4; ++q) {
-        uint4 v;
-        v.x = (4 * q + 0 < K) ? H[(4 * q + 0 < K) ? 4 * q + 0 : 0] : ((4 * q + 0 == K) ? diag : 0u);
-        v.y = (4 * q + 1 < K) ? H[(4 * q + 1 < K) ? 4 * q + 1 : 0] : ((4 * q + 1 == K) ? diag : 0u);
-        v.z = (4 * q + 2 < K) ? H[(4 * q + 2 < K) ? 4 * q + 2 : 0] : ((4 * q + 2 == K) ? diag : 0u);
-        v.w = (4 * q + 3 < K) ? H[(4 * q + 3 < K) ? 4 * q + 3 : 0] : ((4 * q + 3 == K) ? diag : 0u);
-        *reinterpret_cast<uint4 *>(my_stage + 4 * q) = v;
+    for (int p = 0; p < Geo<K>::CKP; ++p) {
+        uint32_t v[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int w = 8 * p + e;
+            v[e] = (w < K) ? H[w < K ? w : 0] : (w == K ? diag : 0u);
+        }
+        stg256(lane_rec + p * REC_P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
     }
 }
 
-// the group's staged block (GL * RW words) -> global, 128 contiguous bytes per round of the 8 lanes
-template <int K>
-__device__ __forceinline__ void copy_out_block(uint32_t *dst, const uint32_t *stage, int t)
+// pieces 0 .. CKP-1 of a lane's record -> the checkpointed words (w < K: cell w, w == K: diag) through fn(w, word)
+template <int K, class Fn>
+__device__ __forceinline__ void load_checkpoint(const uint32_t *lane_rec, bool ld, Fn &&fn)
 {
-    constexpr int RW = Geo<K>::RW;
 #pragma unroll
-    for (int q = 0; q < RW / 4; ++q) {
-        const uint4 v = *reinterpret_cast<const uint4 *>(stage + q * (GL * 4) + t * 4);
-        *reinterpret_cast<uint4 *>(dst + q * (GL * 4) + t * 4) = v;
+    for (int p = 0; p < Geo<K>::CKP; ++p) {
+        uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        if (ld) ldg256(lane_rec + p * REC_P, v);
+#pragma unroll
+        for (int e = 0; e < 8; ++e)
+            if (8 * p + e <= K) fn(8 * p + e, v[e]);
     }
 }
 

@@ -29,9 +29,7 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
-    uint32_t *prof = prof_all + warp * (G::PROF_WORDS + 4 * GL * G::RW);
-    uint32_t *stage = prof + G::PROF_WORDS + g * (GL * G::RW);    // this group's block records, staged for a coalesced copy-out
-    uint32_t *my_stage = stage + t * G::RW;
+    uint32_t *prof = prof_all + warp * G::PROF_WORDS;
     const int n_quads = (P.n_vrefs + 3) >> 2;
     const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
@@ -106,10 +104,11 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
 
             // SEAMS: the boundary row this lane receives at every step (matrix row t*K) is kept next to the block
             // checkpoint, so that the traceback can recompute ONE lane's tile (K rows x CB steps) without the lanes
-            // above it.  Record of (block, lane) = checkpoint + seam, contiguous (Geo::RW words): staged in shared
-            // memory (one STS.128 per 4 steps) and copied out at the block end, 128 contiguous bytes per group store.
+            // above it.  Record of (block, lane) = checkpoint + seam in 32-byte pieces (swb_device.cuh): every piece is
+            // written straight from registers, one 256-bit store per 8 steps, 256 contiguous bytes per group store.
             const bool own_chunk = (s0 < my_steps) && ((s0 >> 4) >= skip);
-            uint32_t t0 = 0, t1 = 0, t2 = 0;
+            uint32_t *seam = rec_lane<K>(P.rec, blk0 + (s0 >> 4), t) + G::CKP * REC_P;       // this block's seam pieces
+            uint32_t tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
             if (fast) {
 #pragma unroll
@@ -129,14 +128,14 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
                     }
                     diag = top;
                     tmax = colmax<K>(tmax, H);
-                    if ((u & 3) == 0) t0 = top; else if ((u & 3) == 1) t1 = top; else if ((u & 3) == 2) t2 = top;
-                    else *reinterpret_cast<uint4 *>(my_stage + G::KW + (u >> 2) * 4) = make_uint4(t0, t1, t2, top);
+                    tq[u & 7] = top;
+                    if ((u & 7) == 7 && own_chunk) stg256(seam + (u >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                 }
             } else {
 #pragma unroll 1
-                for (int uq = 0; uq < 16; uq += 4) {
+                for (int uq = 0; uq < 16; uq += 8) {
 #pragma unroll
-                    for (int uu = 0; uu < 4; ++uu) {
+                    for (int uu = 0; uu < 8; ++uu) {
                         const int u = uq + uu;
                         const int s = s0 + u;
                         const uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1) & lmask;
@@ -157,16 +156,13 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
                             tmax = colmax<K>(tmax, H);
                         }
                         diag = top;
-                        if (uu == 0) t0 = top; else if (uu == 1) t1 = top; else if (uu == 2) t2 = top;
-                        else *reinterpret_cast<uint4 *>(my_stage + G::KW + (uq >> 2) * 4) = make_uint4(t0, t1, t2, top);
+                        tq[uu] = top;
+                        if (uu == 7 && own_chunk) stg256(seam + (uq >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                     }
                 }
             }
 
-            // ---- end of a checkpoint block: copy out its record, tile max, stage the next block's checkpoint
-            __syncwarp();
-            if (own_chunk) copy_out_block<K>(P.rec + (blk0 + (s0 >> 4)) * (int64_t)(GL * G::RW), stage, t);
-            __syncwarp();
+            // ---- end of a checkpoint block: tile max, the next block's checkpoint
             const int s_next = s0 + 16;
             {
                 const int b = s_next / CB;                       // block that starts at s_next
@@ -175,7 +171,8 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
                     gmax = vmax2(gmax, tmax);
                 }
                 tmax = 0;
-                stage_checkpoint<K>(my_stage, H, diag);           // state before step s_next
+                if (s_next < my_steps && b >= skip)               // block b is owned by this group
+                    store_checkpoint<K>(rec_lane<K>(P.rec, blk0 + b, t), H, diag);       // state before step s_next
             }
         }
         // last (partial) block
@@ -214,7 +211,7 @@ static cudaError_t launch_fill_k(const BatchParams &P, uint32_t *work_counter, i
     const int64_t items = (int64_t)n_quads * P.n_rp;
     // persistent CTAs, never more than there is work
     const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count * ctas_per_sm);
-    const size_t smem = (size_t)warps * (G::PROF_WORDS + 4 * GL * G::RW) * sizeof(uint32_t);
+    const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
     cudaError_t e = cudaSuccess;
     {
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of

@@ -47,9 +47,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int t = lane & (GL - 1), g = lane >> 3;
-    uint32_t *prof = prof_all + warp * (G::PROF_WORDS + 4 * GL * G::RW);
-    uint32_t *stage = prof + G::PROF_WORDS + g * (GL * G::RW);    // this group's block records (see swb_fill.cu)
-    uint32_t *my_stage = stage + t * G::RW;
+    uint32_t *prof = prof_all + warp * G::PROF_WORDS;
     const int n_quads = (P.n_vrefs + 3) >> 2;
     const uint32_t n_items = (uint32_t)n_quads * (uint32_t)P.n_rp;
 
@@ -124,10 +122,12 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
             wprev = wnew;
             const bool fast = (s0 >= GL - 1) && (s0 + 16 <= nmin);
 
-            // SEAMS (see swb_fill.cu): the boundary row this lane receives at every step, stored BIASED -- the
+            // SEAMS (see swb_fill.cu): the boundary row this lane receives at every step, written straight to the
+            // block's record (one 256-bit store per 8 steps), BIASED -- the
             // bias of step u of a block is |gap| * (9 - t + u) in both halves (P.seam_bias tells the traceback).
             const bool own_chunk = (s0 < my_steps) && ((s0 >> 4) >= skip);
-            uint32_t t0 = 0, t1 = 0, t2 = 0;
+            uint32_t *seam = rec_lane<K>(P.rec, blk0 + (s0 >> 4), t) + G::CKP * REC_P;       // this block's seam pieces
+            uint32_t tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
             if (fast) {
 #pragma unroll
@@ -151,14 +151,14 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     diag = top;
                     if (!SUB) tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
                     else if ((u & 1) == 0 || u == CB - 1) tmax = viaddmax(colmax_even<K>(floorv, H), negfloor, tmax);
-                    if ((u & 3) == 0) t0 = top; else if ((u & 3) == 1) t1 = top; else if ((u & 3) == 2) t2 = top;
-                    else *reinterpret_cast<uint4 *>(my_stage + G::KW + (u >> 2) * 4) = make_uint4(t0, t1, t2, top);
+                    tq[u & 7] = top;
+                    if ((u & 7) == 7 && own_chunk) stg256(seam + (u >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                 }
             } else {
 #pragma unroll 1
-                for (int uq = 0; uq < 16; uq += 4) {
+                for (int uq = 0; uq < 16; uq += 8) {
 #pragma unroll
-                    for (int uu = 0; uu < 4; ++uu) {
+                    for (int uu = 0; uu < 8; ++uu) {
                         const int u = uq + uu;
                         const int s = s0 + u;
                         floorv = imad_add(floorv, one, gpos);
@@ -186,17 +186,13 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                             for (int r = 0; r < K; ++r) H[r] = floorv;
                         }
                         diag = top;
-                        if (uu == 0) t0 = top; else if (uu == 1) t1 = top; else if (uu == 2) t2 = top;
-                        else *reinterpret_cast<uint4 *>(my_stage + G::KW + (uq >> 2) * 4) = make_uint4(t0, t1, t2, top);
+                        tq[uu] = top;
+                        if (uu == 7 && own_chunk) stg256(seam + (uq >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                     }
                 }
             }
 
-            // ---- block boundary: copy out the finished block's record, move jref by CB columns, then (un-biased)
-            // tile max + the next block's checkpoint into the staging record
-            __syncwarp();
-            if (own_chunk) copy_out_block<K>(P.rec + (blk0 + (s0 >> 4)) * (int64_t)(GL * G::RW), stage, t);
-            __syncwarp();
+            // ---- block boundary: move jref by CB columns, then (un-biased) tile max + the next block's checkpoint
             const int s_next = s0 + 16;
             {
 #pragma unroll
@@ -213,7 +209,8 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                 uint32_t U[K];
 #pragma unroll
                 for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
-                stage_checkpoint<K>(my_stage, U, imad_add(diag, one, unbias));
+                if (s_next < my_steps && b >= skip)                                 // block b is owned by this group
+                    store_checkpoint<K>(rec_lane<K>(P.rec, blk0 + b, t), U, imad_add(diag, one, unbias));
             }
         }
         {
@@ -247,7 +244,7 @@ static cudaError_t launch_fill_bias_k2(const BatchParams &P, uint32_t *work_coun
     const int warps = env_warps > 0 ? env_warps : 16;         // measured: 10/12/14/16 warps -> 42.0/39.8/39.4/39.2 ms
     const int64_t items = (int64_t)n_quads * P.n_rp;
     const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count);   // one CTA per SM
-    const size_t smem = (size_t)warps * (G::PROF_WORDS + 4 * GL * G::RW) * sizeof(uint32_t);
+    const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
     cudaError_t e = cudaSuccess;
     {
         // ask for the largest shared-memory carve-out: the traceback CTAs of the previous batch (68 KB of

@@ -34,8 +34,10 @@ constexpr int kNumK = 10;
 constexpr int kKList[kNumK] = {4, 5, 7, 8, 10, 13, 16, 19, 25, 32};   // 8 K >= m: 36/50/75-80/100/125/150/200/250 bp reads fit with <= 7 % padding
 
 template <int K> struct Geo {
-    static constexpr int KW = ((K + 1 + 3) / 4) * 4;            // checkpoint words per lane (K cells + diag)
-    static constexpr int RW = KW + CB;                          // record words per (block, lane): checkpoint + seam
+    static constexpr int KW = ((K + 1 + 3) / 4) * 4;            // checkpoint words per lane (K cells + diag), padded to 16 bytes
+    static constexpr int CKP = (K + 1 + 7) / 8;                 // checkpoint PIECES (32 bytes each) of a record
+    static constexpr int RP = CKP + CB / 8;                     // pieces per (block, lane) record: checkpoint + seam
+    static constexpr int RW = RP * 8;                           // record words
     static constexpr int KP = ((K + 3) / 4) * 4;                // profile words per lane per code
     static constexpr int KS = ((KP / 4) % 2 == 1) ? KP : KP + 4; // padded: odd number of 16B units -> conflict-free LDS.128
     static constexpr int CSTRIDE = GL * KS;                     // words per reference code
@@ -102,9 +104,10 @@ struct BatchParams {
     int32_t tie_gt;                 // traceback tie rule: 0 = '>=' cascade (a > i > d), 1 = strict '>' (d > i > a)
     // outputs / workspace
     int32_t  *scores;               // [n_refs_orig * n_reads]
-    // block records [n_rp][blocks_per_rp][GL lanes][RW words]: per lane, contiguous, the CHECKPOINT at the block
-    // start (K cells + diagonal boundary, unbiased) followed by the SEAM of the block (the boundary row the lane
-    // receives at each of its CB steps) -- everything a traceback needs to recompute the tile (block, lane).
+    // block records [n_rp][blocks_per_rp][RP pieces][GL lanes][8 words]: per lane the CHECKPOINT at the block start
+    // (K cells + diagonal boundary, unbiased) and the SEAM of the block (the boundary row the lane receives at each
+    // of its CB steps) -- everything a traceback needs to recompute the tile (block, lane) -- in 32-byte pieces;
+    // piece p of a block's eight lanes is contiguous (swb_device.cuh).
     uint32_t *rec;
     uint32_t *tmx;                  // tile maxima  [n_rp][blocks_per_rp][GL]
     int32_t tmx_slack;              // 0: tile maxima / pair scores of the fill are exact; > 0: subsampled, true max - slack <= tmx <= true max

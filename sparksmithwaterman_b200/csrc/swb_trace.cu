@@ -268,28 +268,27 @@ __global__ void __launch_bounds__(128) trace_kernel(const BatchParams P, const u
 
             uint32_t H[K], diag = 0;
             {
-                const uint4 *ckA = reinterpret_cast<const uint4 *>(P.rec + ((bk0 + b0) * GL + t) * (int64_t)G::RW);
-                const uint4 *ckB = reinterpret_cast<const uint4 *>(P.rec + ((bk1 + b1) * GL + t) * (int64_t)G::RW);
+                const uint32_t *ckA = rec_lane<K>(P.rec, bk0 + b0, t);
+                const uint32_t *ckB = rec_lane<K>(P.rec, bk1 + b1, t);
                 const bool la = busy0 && b0 > 0, lb = busy1 && b1 > 0;
                 const uint32_t sel = rh ? 0x7632u : 0x5410u;        // (A.half rh) | (B.half rh) << 16
-                const uint4 z = make_uint4(0, 0, 0, 0);
 #pragma unroll
-                for (int q = 0; q < KW / 4; ++q) {
-                    const uint4 a = la ? __ldg(ckA + q) : z;
-                    const uint4 bq = lb ? __ldg(ckB + q) : z;
-                    const uint32_t v[4] = {__byte_perm(a.x, bq.x, sel), __byte_perm(a.y, bq.y, sel),
-                                           __byte_perm(a.z, bq.z, sel), __byte_perm(a.w, bq.w, sel)};
+                for (int p = 0; p < G::CKP; ++p) {
+                    uint32_t a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, bq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if (la) ldg256(ckA + p * REC_P, a);
+                    if (lb) ldg256(ckB + p * REC_P, bq);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int w = 4 * q + e;
-                        if (w < K) H[w < K ? w : 0] = v[e];
-                        else if (w == K) diag = v[e];
+                    for (int e = 0; e < 8; ++e) {
+                        const int w = 8 * p + e;
+                        const uint32_t v = __byte_perm(a[e], bq[e], sel);
+                        if (w < K) H[w < K ? w : 0] = v;
+                        else if (w == K) diag = v;
                     }
                 }
             }
             // the path almost always continues into the block to the left: pull its records towards L2
-            if (busy0 && b0 > 1) prefetch_l2(P.rec + ((bk0 + b0 - 1) * GL + t) * (int64_t)G::RW);
-            if (busy1 && b1 > 1) prefetch_l2(P.rec + ((bk1 + b1 - 1) * GL + t) * (int64_t)G::RW);
+            if (busy0 && b0 > 1) prefetch_l2(rec_lane<K>(P.rec, bk0 + b0 - 1, t));
+            if (busy1 && b1 > 1) prefetch_l2(rec_lane<K>(P.rec, bk1 + b1 - 1, t));
             // reference-code windows of this lane for the block: 0-based columns j0 .. j0+15
             uint32_t win0, win1; int ulo0, uhi0, ulo1, uhi1;
             {

@@ -155,34 +155,22 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             const int b = busy ? step / CB : 0;
             int H[K], diag = 0;
             {
-                const uint4 *ck = reinterpret_cast<const uint4 *>(P.rec + ((bk + b) * GL + t) * (int64_t)G::RW);
-                const bool ld = busy && b > 0;
-                const uint4 z = make_uint4(0, 0, 0, 0);
-#pragma unroll
-                for (int q = 0; q < KW / 4; ++q) {
-                    const uint4 a = ld ? __ldg(ck + q) : z;
-                    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const int w = 4 * q + e;
-                        if (w < K) H[w < K ? w : 0] = half_of(v[e], rh);
-                        else if (w == K) diag = half_of(v[e], rh);
-                    }
-                }
+                load_checkpoint<K>(rec_lane<K>(P.rec, bk + b, t), busy && b > 0, [&](int w, uint32_t v) {
+                    if (w < K) H[w < K ? w : 0] = half_of(v, rh); else diag = half_of(v, rh);
+                });
             }
             int top[CB];
             {
-                const uint4 *sq = reinterpret_cast<const uint4 *>(P.rec + ((bk + b) * GL + t) * (int64_t)G::RW + KW);
+                const uint32_t *sq = rec_lane<K>(P.rec, bk + b, t) + G::CKP * REC_P;
                 const bool ld = busy && t > 0;                      // lane 0's boundary row is matrix row 0
-                const uint4 z = make_uint4(0, 0, 0, 0);
                 const int bias0 = sbias * (9 - t);
 #pragma unroll
-                for (int q = 0; q < CB / 4; ++q) {
-                    const uint4 a = ld ? __ldg(sq + q) : z;
-                    const uint32_t v[4] = {a.x, a.y, a.z, a.w};
+                for (int p = 0; p < CB / 8; ++p) {
+                    uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                    if (ld) ldg256(sq + p * REC_P, v);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e)
-                        top[4 * q + e] = ld ? half_of(v[e], rh) - (bias0 + sbias * (4 * q + e)) : 0;
+                    for (int e = 0; e < 8; ++e)
+                        top[8 * p + e] = ld ? half_of(v[e], rh) - (bias0 + sbias * (8 * p + e)) : 0;
                 }
             }
             // reference codes of the block's 16 steps for this lane: 0-based columns j0 .. j0 + 15
@@ -300,7 +288,7 @@ struct TileSweep {
     int diag, S, t, b;
     uint32_t win, rowok;
     int ulo, uhi;
-    const uint4 *sq;
+    const uint32_t *sq;
     bool has_top;
     uint64_t pkey;
     int64_t pair;
@@ -312,7 +300,7 @@ struct TileSweep {
         const int rp = (int)(T.rp_half >> 1), rh = (int)(T.rp_half & 1u), ref = (int)T.ref_sorted;
         t = (int)T.lane; b = (int)T.block;
         S = 0x7fffffff; pkey = 0; pair = 0; diag = 0; win = 0; rowok = 0; ulo = 0; uhi = -1;
-        sq = reinterpret_cast<const uint4 *>(P.rec); has_top = false;
+        sq = P.rec; has_top = false;
 #pragma unroll
         for (int r = 0; r < K; ++r) { rc[r] = 0xFE; H[r] = 0; }
         if (!live) return;
@@ -332,20 +320,11 @@ struct TileSweep {
         }
         const int64_t blk = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref] + b;
         if (b > 0) {
-            const uint4 *ck = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW);
-#pragma unroll
-            for (int q = 0; q < KW / 4; ++q) {
-                const uint4 a = __ldg(ck + q);
-                const uint32_t v[4] = {a.x, a.y, a.z, a.w};
-#pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int w = 4 * q + e;
-                    if (w < K) H[w < K ? w : 0] = half_of(v[e], rh);
-                    else if (w == K) diag = half_of(v[e], rh);
-                }
-            }
+            load_checkpoint<K>(rec_lane<K>(P.rec, blk, t), true, [&](int w, uint32_t v) {
+                if (w < K) H[w < K ? w : 0] = half_of(v, rh); else diag = half_of(v, rh);
+            });
         }
-        sq = reinterpret_cast<const uint4 *>(P.rec + (blk * GL + t) * (int64_t)G::RW + KW);
+        sq = rec_lane<K>(P.rec, blk, t) + G::CKP * REC_P;
         has_top = t > 0;                                         // lane 0's boundary row is matrix row 0
         const uint32_t *rw = P.ref_words + P.ref_word_off[ref];
         const int j0 = b * CB - t;
@@ -363,12 +342,25 @@ struct TileSweep {
     {
         const int gap = P.gap, match = P.match, mismatch = P.mismatch;
         const int bias0 = P.seam_bias * (9 - t);
-        uint4 nxt = has_top ? __ldg(sq) : make_uint4(0, 0, 0, 0);
+        uint32_t sv[CB];                                        // the seam: two 32-byte pieces
+#pragma unroll
+        for (int p = 0; p < CB / 8; ++p) {
+            uint32_t v[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+            if (has_top) ldg256(sq + p * REC_P, v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sv[8 * p + e] = v[e];
+        }
 #pragma unroll 1
         for (int q = 0; q < CB / 4; ++q) {
-            const uint4 a = nxt;
-            if (q + 1 < CB / 4 && has_top) nxt = __ldg(sq + q + 1);
-            const uint32_t av[4] = {a.x, a.y, a.z, a.w};
+            // the quad's four seam words without dynamic register indexing
+            uint32_t av[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                uint32_t x = sv[e];
+#pragma unroll
+                for (int qq = 1; qq < CB / 4; ++qq) x = (q == qq) ? sv[4 * qq + e] : x;
+                av[e] = x;
+            }
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int u = 4 * q + e;

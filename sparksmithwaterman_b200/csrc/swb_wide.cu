@@ -440,7 +440,7 @@ struct WTile {
 // The type of a positive cell is the reference's cascade (GetCellScore, SmithWaterman.java:227-249: alignment over
 // insertion over deletion on ties; DistributedSW.java:310-326 the other way round).
 constexpr int EXIT_END = 127;
-constexpr int EXIT_TAB = 2 * WCB;                                // entries: bottom row (32 columns), then right column (KL rows <= 32)
+
 template <int KL, class Fn>
 __device__ __forceinline__ void run_with_exits(WTile<KL> &W, const WCtx &C, bool tie_gt, uint32_t *tab, Fn &&fn)
 {
