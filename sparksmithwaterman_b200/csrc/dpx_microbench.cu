@@ -19,12 +19,16 @@ __device__ __forceinline__ uint32_t add2(uint32_t a, uint32_t b) { uint32_t r; a
 __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) { uint32_t r; asm("max.s16x2 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 __device__ __forceinline__ uint32_t max2relu(uint32_t a, uint32_t b) { uint32_t r; asm("max.s16x2.relu %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) { uint32_t r; asm("add.f16x2 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+__device__ __forceinline__ uint32_t hmax2(uint32_t a, uint32_t b) { uint32_t r; asm("max.f16x2 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+
 constexpr int NCHAIN = 8;
 constexpr int UNROLL = 16;
 
 enum Mix { VIADDMNMX16 = 0, VIMNMX3_16, VIADD16, IADD32, IMAD32, VIADDMNMX32, LOP, MIX_DPX_IMAD, MIX_DPX_LDS,
            MIX_SW_CELL, VIMNMX2_16, VIMNMX2_16_RELU, VIADDMNMX16_RELU, MIX_DPX_VIMNMX2, MIX_DPX_VIADD, MIX_VIMNMX2_IMAD,
-           PRMT_OP, SHF_OP, MIX_DPX_SHFL, IMNMX32, MIX_VIADD_VIMNMX2, NMIX };
+           PRMT_OP, SHF_OP, MIX_DPX_SHFL, IMNMX32, MIX_VIADD_VIMNMX2,
+           HMNMX2_OP, HADD2_OP, MIX_DPX_HMNMX2, MIX_DPX_HADD2, MIX_HCELL, MIX_DPX_CELL_AND_HCELL, NMIX };
 
 template <int MIX>
 __global__ void __launch_bounds__(256) bench_kernel(uint32_t *out, long long *cyc, int iters, uint32_t a0, uint32_t b0, uint32_t one)
@@ -63,6 +67,31 @@ __global__ void __launch_bounds__(256) bench_kernel(uint32_t *out, long long *cy
                 else if (MIX == MIX_DPX_SHFL) { x[c] = max2(add2(x[c], b0), y[c]); if (c == 0) y[0] ^= __shfl_up_sync(0xffffffffu, x[1], 1); }
                 else if (MIX == IMNMX32) { x[c] = (uint32_t)max((int)x[c], (int)y[c]); y[c] = (uint32_t)min((int)y[c], (int)x[c]) + 1u; }
                 else if (MIX == MIX_VIADD_VIMNMX2) { x[c] = add2(x[c], y[c]); y[c] = max2(y[c], x[c]); }
+                else if (MIX == HMNMX2_OP) { x[c] = hmax2(x[c], y[c]); y[c] = hmax2(y[c], b0); }
+                else if (MIX == HADD2_OP) { x[c] = hadd2(x[c], y[c]); y[c] = hadd2(y[c], b0); }
+                else if (MIX == MIX_DPX_HMNMX2) { x[c] = max2(add2(x[c], b0), y[c]); y[c] = hmax2(y[c], a0); }
+                else if (MIX == MIX_DPX_HADD2) { x[c] = max2(add2(x[c], b0), y[c]); y[c] = hadd2(y[c], a0); }
+                else if (MIX == MIX_HCELL) {
+                    // the linear-gap cell in f16x2 (values kept in [1024, 2048): same bits as biased int16): 5 ops
+                    uint32_t t = hadd2(y[c], a0);
+                    uint32_t pre = hmax2(hmax2(t, x[c]), b0);
+                    y[c] = x[c];
+                    x[c] = hmax2(hadd2(x[(c + 1) % NCHAIN], b0), pre);
+                }
+                else if (MIX == MIX_DPX_CELL_AND_HCELL) {
+                    // chains 0..4: the DPX cell (IMAD + VIMNMX3 + VIADDMNMX); chains 5..7: the f16x2 cell (5 ops)
+                    if (c < 5) {
+                        uint32_t t = y[c] * one + a0;
+                        uint32_t pre = max2(max2(t, x[c]), b0);
+                        y[c] = x[c];
+                        x[c] = max2(add2(x[(c + 1) % 5], b0), pre);
+                    } else {
+                        uint32_t t = hadd2(y[c], a0);
+                        uint32_t pre = hmax2(hmax2(t, x[c]), b0);
+                        y[c] = x[c];
+                        x[c] = hmax2(hadd2(x[5 + (c - 4) % 3], b0), pre);
+                    }
+                }
                 else if (MIX == MIX_SW_CELL) {
                     // the three-op linear-gap cell: t = nw + s ; pre = max(w + g, t) ; h = max(n + g, pre)
                     uint32_t t = add2(y[c], a0);
@@ -90,6 +119,8 @@ const MixInfo kInfo[NMIX] = {
     {"viaddmnmx_s16x2+vimnmx2", 2, 2}, {"viaddmnmx_s16x2+viadd16x2", 2, 2}, {"vimnmx2+imad", 2, 2},
     {"prmt", 2, 2}, {"shf", 2, 2}, {"viaddmnmx_s16x2+shfl/8", 1, 1}, {"imnmx_s32(+iadd)", 3, 3},
     {"viadd16x2+vimnmx2", 2, 2},
+    {"hmnmx2_f16x2", 2, 2}, {"hadd2_f16x2", 2, 2}, {"viaddmnmx_s16x2+hmnmx2", 1, 2}, {"viaddmnmx_s16x2+hadd2", 1, 2},
+    {"sw_cell_5op_f16x2", 5, 5}, {"5x(imad+2dpx)+3x(5 f16x2 ops) per 8 cells", 4, 4},
 };
 
 template <int MIX>
