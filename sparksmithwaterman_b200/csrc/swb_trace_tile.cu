@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
 {
     using G = Geo<K>;
     using TG = TileGeo<K>;
-    constexpr int KW = G::KW, KS = G::KS, ROWW = TG::ROWW;
+    constexpr int KS = G::KS, ROWW = TG::ROWW;
     constexpr unsigned FULL = 0xffffffffu;
     extern __shared__ __align__(16) uint32_t smem[];
     __shared__ uint32_t seg_next;
@@ -296,7 +296,6 @@ struct TileSweep {
     __device__ __forceinline__ void setup(const BatchParams &P, const TileTask &T, bool live)
     {
         using G = Geo<K>;
-        constexpr int KW = G::KW;
         const int rp = (int)(T.rp_half >> 1), rh = (int)(T.rp_half & 1u), ref = (int)T.ref_sorted;
         t = (int)T.lane; b = (int)T.block;
         S = 0x7fffffff; pkey = 0; pair = 0; diag = 0; win = 0; rowok = 0; ulo = 0; uhi = -1;

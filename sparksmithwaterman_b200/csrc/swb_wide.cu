@@ -973,6 +973,7 @@ __global__ void __launch_bounds__(NT) wide_trace_kernel(const WideParams P, cons
         return;
     }
 
+    if constexpr (!CTAW)
     for (uint32_t cell = gid; cell < n_cells; cell += n_groups) {            // group-uniform
         const uint64_t key = keys[cell];
         const int pair = (int)wide_key_pair(key);
