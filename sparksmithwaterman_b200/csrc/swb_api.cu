@@ -521,6 +521,10 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
     CU(cudaMemsetAsync(res->d_scores.p, 0, std::max<size_t>(n_pairs, 1) * 4, st));
 
     const auto t_wall0 = std::chrono::steady_clock::now();
+    const bool tlh = getenv("SWB_TIMELINE_HOST") != nullptr;
+    auto mark = [&](const char *what) {
+        if (tlh) fprintf(stderr, "[swb host] %8.3f ms  %s\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wall0).count(), what);
+    };
     // phase timing: event pairs are only recorded inside the loop and read after the last sync
     ctx->ev_used = 0;
     struct Span { cudaEvent_t a, b; int phase; };
@@ -663,6 +667,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
                 else
                     CU(launch_fill(K, P, d_work, ctx->sm_count, sF));
                 ++launches;
+                mark("fill issued");
                 CU(toc(sp_fill, sF));
                 CU(ctx->next_event(&S.ev_fill));
                 CU(cudaEventRecord(S.ev_fill, sF));
@@ -697,8 +702,10 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
                                          ctx->sm_count, 1, st));
                         ++launches;
                     }
+                    mark("flag + locate issued");
                     CU(cudaMemcpyAsync(h_counts, ctx->counters.p, 8, cudaMemcpyDeviceToHost, st));
                     CU(cudaStreamSynchronize(st));
+                    mark("counts on the host");
                     if (h_counts[0] <= cap_tasks && h_counts[1] <= cap_cells) break;
                     if (attempt == 2) return fail(SWB_E_NOMEM, "swb_align: max-cell list did not fit after two retries");
                     // a partial scan only raised pair scores towards their exact value: the retry stays correct
@@ -739,6 +746,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
                 CU(bo.d_slot_read.alloc(S.h_rp.size(), st));
                 CU(cudaMemcpyAsync(bo.d_slot_read.p, bo.slot_read.data(), S.h_rp.size() * 4, cudaMemcpyHostToDevice, st));
                 res->batches.push_back(std::move(bo));
+                mark("sort + trace issued");
                 return SWB_OK;
             };
 
@@ -769,6 +777,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
                 CU(cudaStreamWaitEvent(st, evl, 0));
             }
             CU(cudaStreamSynchronize(st));        // stages hold host vectors used by async copies
+            mark("class done (sync)");
         }
     }
     if (n_refs > 0 && !wide_reads_all.empty()) {
@@ -832,8 +841,10 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
         CU(assemble_gather_cells(d_desc.p, (int)descs.size(), N, d_order.p, res->f_cells.p, res->f_beg.p, res->f_len.p,
                                  d_words.p, res->f_ops_off.p, d_tmp.p, tmp_bytes, st));
         int64_t total_words = 0;
+        mark("assemble sort + cells issued");
         CU(cudaMemcpyAsync(&total_words, res->f_ops_off.p + N, 8, cudaMemcpyDeviceToHost, st));
         CU(cudaStreamSynchronize(st));
+        mark("total words on the host");
         if (tl4) fprintf(stderr, "[swb assemble] sort + cell gather done at %.3f ms\n", ms4());
         res->total_words = total_words;
         CU(res->f_ops.alloc((size_t)total_words, st));
@@ -843,6 +854,7 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
         launches += 8;
         CU(toc(sp_misc, st));
         CU(cudaStreamSynchronize(st));
+        mark("assembled (sync)");
         if (tl4) fprintf(stderr, "[swb assemble] ops gathered at %.3f ms\n", ms4());
         res->batches.clear();                     // per-batch buffers go back to the pool
         if (tl4) fprintf(stderr, "[swb assemble] batch buffers released at %.3f ms\n", ms4());
@@ -872,8 +884,10 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
     res->stats[7] = (double)n_refs * (double)n_reads;
     res->stats[9] = launches; res->stats[10] = ck_bytes; res->stats[11] = n_batches;
     swb_result *r = res.release();
+    mark("before fetch");
     if (!(flags & SWB_F_NO_FETCH)) {
         int rc = swb_result_fetch(r);
+        mark("fetched");
         if (rc) { swb_result_free(r); return rc; }
     }
     *out = r;
