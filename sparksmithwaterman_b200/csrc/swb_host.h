@@ -58,6 +58,15 @@ struct BlockCache {
         cached += bytes;
         return true;
     }
+    // the pool ran dry: hand this stream's cached blocks back (stream-ordered), the caller retries its allocation
+    size_t spill(cudaStream_t st)
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        size_t freed = 0;
+        for (auto it = free_blocks.begin(); it != free_blocks.end();)
+            if (it->first.first == st) { cudaFreeAsync(it->second, st); freed += it->first.second; cached -= it->first.second; it = free_blocks.erase(it); } else ++it;
+        return freed;
+    }
     // a context goes away: its streams' blocks return to the pool (the caller has synchronised the streams)
     void purge(cudaStream_t st)
     {
@@ -109,6 +118,10 @@ template <class T> struct DevBuf {
             if (p) { n = count; return cudaSuccess; }
         }
         cudaError_t e = cudaMallocAsync(&p, bytes, stream);
+        if (e == cudaErrorMemoryAllocation && BlockCache::get().spill(stream) > 0) {
+            cudaGetLastError();
+            e = cudaMallocAsync(&p, bytes, stream);                // once more with the cached blocks back in the pool
+        }
         if (e == cudaSuccess) n = count; else { p = nullptr; cap_bytes = 0; }
         return e;
     }
