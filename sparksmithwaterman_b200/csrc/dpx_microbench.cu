@@ -109,6 +109,56 @@ __global__ void __launch_bounds__(256) bench_kernel(uint32_t *out, long long *cy
     if (threadIdx.x == 0) cyc[blockIdx.x] = clock64() - c0;
 }
 
+// dependent-issue latency: ONE warp, ONE chain of dependent instructions
+enum LatOp { LAT_VIADDMNMX16 = 0, LAT_VIMNMX3_16, LAT_VIADDMNMX32, LAT_VIADDMNMX32_RELU, LAT_IMAD, LAT_IADD, LAT_SHFL, LAT_LDS, NLAT };
+const char *kLatName[NLAT] = {"viaddmnmx_s16x2", "vimnmx3_s16x2", "viaddmnmx_s32", "viaddmnmx_s32_relu", "imad", "iadd3", "shfl_up", "lds"};
+
+template <int OP>
+__global__ void lat_kernel(uint32_t *out, long long *cyc, int n, uint32_t a0, uint32_t b0, uint32_t one)
+{
+    __shared__ uint32_t sm[64];
+    sm[threadIdx.x] = (threadIdx.x + 1) & 31;
+    sm[threadIdx.x + 32] = a0;
+    __syncthreads();
+    asm volatile("" : "+r"(a0), "+r"(b0), "+r"(one));
+    uint32_t x = a0 + threadIdx.x;
+    const long long c0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < n; ++it) {
+#pragma unroll
+        for (int u = 0; u < 32; ++u) {
+            if (OP == LAT_VIADDMNMX16) x = max2(add2(x, b0), a0);
+            else if (OP == LAT_VIMNMX3_16) x = max2(max2(x, b0), a0);
+            else if (OP == LAT_VIADDMNMX32) x = (uint32_t)__viaddmax_s32((int)x, (int)b0, (int)a0);
+            else if (OP == LAT_VIADDMNMX32_RELU) x = (uint32_t)__viaddmax_s32_relu((int)x, (int)b0, (int)a0);
+            else if (OP == LAT_IMAD) x = x * one + b0;
+            else if (OP == LAT_IADD) x = x + b0;
+            else if (OP == LAT_SHFL) x = __shfl_up_sync(0xffffffffu, x, 1);
+            else if (OP == LAT_LDS) x = sm[x & 31];
+        }
+    }
+    const long long c1 = clock64();
+    out[threadIdx.x] = x;
+    if (threadIdx.x == 0) cyc[0] = c1 - c0;
+}
+
+template <int OP>
+double lat_one(uint32_t *dout, long long *dcyc)
+{
+    const int n = 2000;
+    lat_kernel<OP><<<1, 32>>>(dout, dcyc, n, 3, 0xfffcfffcu, 1);
+    lat_kernel<OP><<<1, 32>>>(dout, dcyc, n, 3, 0xfffcfffcu, 1);
+    cudaDeviceSynchronize();
+    long long c = 0;
+    cudaMemcpy(&c, dcyc, sizeof c, cudaMemcpyDeviceToHost);
+    return (double)c / ((double)n * 32.0);
+}
+template <int OP>
+void lat_all(uint32_t *dout, long long *dcyc, double *r)
+{
+    if constexpr (OP < NLAT) { r[OP] = lat_one<OP>(dout, dcyc); lat_all<OP + 1>(dout, dcyc, r); }
+}
+
 struct MixInfo { const char *name; int alu_ops; int total_ops; };
 // ops per (chain, unroll) slot: ALU-pipe candidates vs all issued
 const MixInfo kInfo[NMIX] = {
@@ -179,6 +229,8 @@ extern "C" int swb_microbench_json(int device, int iters, char *buf, int buflen)
     if (cudaMalloc(&dcyc, sizeof(long long) * 4096) != cudaSuccess) return -1;
     double r[NMIX], ms[NMIX], mhz[NMIX];
     run_all<0>(iters, p.multiProcessorCount, clock_khz, dout, dcyc, r, ms, mhz);
+    double lat[NLAT];
+    lat_all<0>(dout, dcyc, lat);
     cudaFree(dout); cudaFree(dcyc);
     std::string s = "{";
     char tmp[768];
@@ -189,6 +241,11 @@ extern "C" int swb_microbench_json(int device, int iters, char *buf, int buflen)
         snprintf(tmp, sizeof tmp,
                  "%s\"%s\": {\"warp_instr_per_clk_per_sm\": %.3f, \"lane_ops_per_clk_per_sm\": %.2f, \"ms\": %.3f, \"sm_mhz\": %.0f}",
                  m ? ", " : "", kInfo[m].name, r[m], r[m] * 32.0, ms[m], mhz[m]);
+        s += tmp;
+    }
+    s += "}, \"dependent_issue_latency_cycles\": {";
+    for (int m = 0; m < NLAT; ++m) {
+        snprintf(tmp, sizeof tmp, "%s\"%s\": %.2f", m ? ", " : "", kLatName[m], lat[m]);
         s += tmp;
     }
     s += "}, \"note\": \"rates are per REAL SM clock (clock64 inside the kernel); sm_mhz is the effective clock during that run\"}";
