@@ -118,7 +118,7 @@ __device__ __forceinline__ void load_row_codes(const uint8_t *read, int T, int (
 // shared-memory profile [code][KL/4][lane][4] (conflict-free LDS.128), NW + s as an IMAD on the FMA
 // pipe, two DPX ops per cell.  NC = 0: compare + select, row masks (any alphabet, any gap sign).
 template <int KL, int NC>
-__global__ void __launch_bounds__(128, KL >= 32 ? 3 : 4)
+__global__ void __launch_bounds__(128, KL >= 32 ? 2 : 4)
 wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *ticket, int one)
 {
     using G = WGeo<KL>;
@@ -239,6 +239,10 @@ wide_fill_kernel(const WideParams P, const int2 *items, int n_items, uint32_t *t
                     }
                     *reinterpret_cast<int4 *>(seam + 4 * q) = make_int4(sm[0], sm[1], sm[2], sm[3]);
                     if (feeds_below && lane == WL - 1) st_relaxed4(my_brow + s0 + 4 * q, bw[0], bw[1], bw[2], bw[3]);
+                    // the next chunk's top row was requested at this chunk's start; words the band above had not written
+                    // yet are asked for again on the way (the load lands while the chunk computes), so that the poll at
+                    // the next chunk's start rarely has to wait for a round trip
+                    if ((q & 1) && tnext < 0) tnext = ld_relaxed(up_brow + s0 + WCB + WL - 1 + lane);
                 }
             } else {
 #pragma unroll 1
@@ -1194,7 +1198,7 @@ cudaError_t launch_fill_k(const WideParams &P, const int2 *items, int n_items, u
     constexpr int PW = NC > 0 ? NC * KL * WL : 0, SW = 2 * (WL + 16);
     const size_t smem = (size_t)4 * (PW + SW) * sizeof(int32_t);
     static const int env_ctas = getenv("SWB_WIDE_CTAS_PER_SM") ? atoi(getenv("SWB_WIDE_CTAS_PER_SM")) : 0;
-    int per_sm = KL >= 32 ? 3 : 4;                                          // registers (__launch_bounds__)
+    int per_sm = KL >= 32 ? 2 : 4;                                          // registers (__launch_bounds__)
     per_sm = std::min<int>(per_sm, (int)((220 * 1024) / (smem + 1024)));    // shared memory
     if (env_ctas > 0) per_sm = std::min(per_sm, env_ctas);
     per_sm = std::max(per_sm, 1);
