@@ -34,8 +34,8 @@ __device__ __forceinline__ uint32_t imad_add(uint32_t a, uint32_t one, uint32_t 
 }
 
 // SUB: the tile maximum (and with it the pair score the fill leaves) is taken over a SUBSAMPLE of the cells --
-// even rows + the lane's last row, on even steps + the block's last step -- which costs 3.1 instead of 10.5
-// VIMNMX3 per step.  Every cell (r, u) of a tile has a tracked cell of the SAME tile among (r, u), (r+1, u),
+// even rows + the lane's last row, on the odd steps of a block (CB is even: the last step is odd) -- which costs
+// 3.0 instead of 10.5 DPX ops per step.  Every cell (r, u) of a tile has a tracked cell of the SAME tile among (r, u), (r+1, u),
 // (r, u+1), (r+1, u+1), so the tracked maximum M of a tile satisfies  true max - slack <= M <= true max  with
 // slack = max(|gap|, min(|mismatch|, 2|gap|)) (fill_sub_slack).  The locate stage recomputes every tile within
 // slack of the pair's tracked maximum, makes the pair score exact and enumerates the exact maximum cells.
@@ -58,6 +58,10 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
     const uint32_t renorm = (uint32_t)(-(int32_t)(pack2(ag * CB, ag * CB)));   // 32-bit add of -(CB*|gap|) in both halves (no borrow: bias >= CB*|gap| there)
     const uint32_t unbias = (uint32_t)(-(int32_t)base_bias);      // for 32-bit IMAD subtraction (no borrow across halves)
     const uint32_t negbase = pack2(-ag * (8 - t), -ag * (8 - t)); // per-half negation, for the packed s16x2 ops
+    // negfloor += gap in both halves as ONE 32-bit IMAD (FMA pipe) instead of a VIADD.16x2 (ALU pipe, DPX rate): both
+    // halves stay negative, so the low half's add always carries into the high half -- take that carry out of the addend
+    const uint32_t g2c = g2 - 0x10000u, g2c2 = 2u * g2c;
+    static_assert((CB & 1) == 0, "the subsampled tile maximum tracks the odd steps of a block");
     const int my_prof = t * G::KS;
     int cur_rp = -1, ra = 0, rb = -1;
 
@@ -133,7 +137,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
 #pragma unroll
                 for (int u = 0; u < 16; ++u) {
                     floorv = imad_add(floorv, one, gpos);                  // floor of the new column
-                    negfloor = viadd2(negfloor, g2);                        // its negative (packed)
+                    if (!SUB) negfloor = imad_add(negfloor, one, g2c);      // its negative (packed; see g2c)
                     uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
                     if (t == 0) top = floorv;                               // row 0 is all zero
                     const uint32_t c = (win >> (2 * u)) & 3u;
@@ -150,7 +154,10 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     }
                     diag = top;
                     if (!SUB) tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
-                    else if ((u & 1) == 0 || u == CB - 1) tmax = viaddmax(colmax_even<K>(floorv, H), negfloor, tmax);
+                    else if (u & 1) {                                       // odd steps: CB is even, the last step is one
+                        negfloor = imad_add(negfloor, one, g2c2);           // two columns on
+                        tmax = viaddmax(colmax_even<K>(floorv, H), negfloor, tmax);
+                    }
                     tq[u & 7] = top;
                     if ((u & 7) == 7 && own_chunk) stg256(seam + (u >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                 }
@@ -162,7 +169,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                         const int u = uq + uu;
                         const int s = s0 + u;
                         floorv = imad_add(floorv, one, gpos);
-                        negfloor = viadd2(negfloor, g2);
+                        negfloor = imad_add(negfloor, one, g2c);
                         uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
                         if (t == 0) top = floorv;
                         const uint32_t c = (win >> (2 * u)) & 3u;
