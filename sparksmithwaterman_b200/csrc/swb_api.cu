@@ -500,9 +500,16 @@ static int align_leaf(swb_ctx *ctx, const swb_refset *rs, const swb_reads *rd, i
     // everything else goes through the int32 wide path (swb_wide.cu)
     const bool short_scores_ok = rs->two_bit_ok && gap < 0 && std::abs((int64_t)match) <= 8000 &&
                                  std::abs((int64_t)mismatch) <= 8000 && std::abs((int64_t)gap) <= 8000;
+    // reads of 257 .. 511 rows: the LONG classes (K = 40 .. 64) exist for the biased fill and the tile kernels only;
+    // other score sets send such reads through the wide path as before (SWB_NO_LONG_CLASSES=1: always)
+    static const bool no_long = getenv("SWB_NO_LONG_CLASSES") != nullptr;
+    const bool long_kernels_ok = !no_long && tile_trace_ok(match, mismatch, gap);
     auto read_is_short = [&](int32_t m) {
-        return short_scores_ok && m <= MAX_SHORT_ROWS &&
-               (int64_t)std::max({match, mismatch, 0}) * std::min<int64_t>(m, rs->max_len) <= 16000;   // a positive mismatch scores too
+        if (!short_scores_ok) return false;
+        const int64_t smax = (int64_t)std::max({match, mismatch, 0}) * std::min<int64_t>(m, rs->max_len);   // a positive mismatch scores too
+        if (smax > 16000) return false;
+        if (m <= MAX_SHORT_ROWS) return true;
+        return m <= MAX_LONG_ROWS && long_kernels_ok && fill_bias_ok(match, mismatch, gap, smax);
     };
 
     std::lock_guard<std::recursive_mutex> lk(ctx->mu);

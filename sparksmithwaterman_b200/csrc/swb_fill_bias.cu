@@ -39,8 +39,51 @@ __device__ __forceinline__ uint32_t imad_add(uint32_t a, uint32_t one, uint32_t 
 // (r, u+1), (r+1, u+1), so the tracked maximum M of a tile satisfies  true max - slack <= M <= true max  with
 // slack = max(|gap|, min(|mismatch|, 2|gap|)) (fill_sub_slack).  The locate stage recomputes every tile within
 // slack of the pair's tracked maximum, makes the pair score exact and enumerates the exact maximum cells.
+// one column of a lane: K cells.  K <= 32: the lane's KP profile words are loaded up front (5 LDS.128 for K = 19);
+// the LONG classes (K = 40 .. 64) load them a quad at a time inside the row loop -- K score registers plus K profile
+// registers would not fit the 128-register budget of a 16-warp CTA.
+template <int K>
+__device__ __forceinline__ void fill_column(uint32_t (&H)[K], const uint32_t *pcol, uint32_t diag, uint32_t top,
+                                            uint32_t floorv, uint32_t g2, uint32_t one)
+{
+    using G = Geo<K>;
+    uint32_t nw = diag, nn = top;
+    if constexpr (K <= MAX_K_BASE) {
+        uint32_t sv[G::KP];
+        load_profile<G::KP>(pcol, sv);
+#pragma unroll
+        for (int r = 0; r < K; ++r) {
+            const uint32_t tt = imad_add(nw, one, sv[r]);       // NW'' + s''          (FMA pipe)
+            const uint32_t pre = vmax3(tt, H[r], floorv);       // max(t, W'', floor)  (ALU)
+            nw = H[r];
+            H[r] = viaddmax(nn, g2, pre);                       // max(N'' + gap, pre) (ALU)
+            nn = H[r];
+        }
+    } else {
+        const uint4 *p4 = reinterpret_cast<const uint4 *>(pcol);
+#pragma unroll
+        for (int q = 0; q < G::KP / 4; ++q) {
+            const uint4 v = p4[q];
+            const uint32_t sv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+            for (int x = 0; x < 4; ++x) {
+                const int r = 4 * q + x;
+                if (r < K) {
+                    const uint32_t tt = imad_add(nw, one, sv[x]);
+                    const uint32_t pre = vmax3(tt, H[r < K ? r : 0], floorv);
+                    nw = H[r < K ? r : 0];
+                    H[r < K ? r : 0] = viaddmax(nn, g2, pre);
+                    nn = H[r < K ? r : 0];
+                }
+            }
+        }
+    }
+}
+
+constexpr int fill_bias_threads(int K) { return K <= MAX_K_BASE ? 512 : (K <= 48 ? 384 : 256); }
+
 template <int K, bool SUB>
-__global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uint32_t *work_counter, uint32_t one)
+__global__ void __launch_bounds__(fill_bias_threads(K)) fill_bias_kernel(const BatchParams P, uint32_t *work_counter, uint32_t one)
 {
     using G = Geo<K>;
     extern __shared__ __align__(16) uint32_t prof_all[];        // per warp: [4 codes][GL lanes][KS], entries s + |gap|
@@ -141,17 +184,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
                     if (t == 0) top = floorv;                               // row 0 is all zero
                     const uint32_t c = (win >> (2 * u)) & 3u;
-                    uint32_t sv[G::KP];
-                    load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
-                    uint32_t nw = diag, nn = top;
-#pragma unroll
-                    for (int r = 0; r < K; ++r) {
-                        const uint32_t tt = imad_add(nw, one, sv[r]);       // NW'' + s''          (FMA pipe)
-                        const uint32_t pre = vmax3(tt, H[r], floorv);       // max(t, W'', floor)  (ALU)
-                        nw = H[r];
-                        H[r] = viaddmax(nn, g2, pre);                       // max(N'' + gap, pre) (ALU)
-                        nn = H[r];
-                    }
+                    fill_column<K>(H, prof + c * G::CSTRIDE + my_prof, diag, top, floorv, g2, one);
                     diag = top;
                     if (!SUB) tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
                     else if (u & 1) {                                       // odd steps: CB is even, the last step is one
@@ -175,17 +208,7 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                         const uint32_t c = (win >> (2 * u)) & 3u;
                         const bool valid = (s >= t) && (s < n_g + t);
                         if (valid) {
-                            uint32_t sv[G::KP];
-                            load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
-                            uint32_t nw = diag, nn = top;
-#pragma unroll
-                            for (int r = 0; r < K; ++r) {
-                                const uint32_t tt = imad_add(nw, one, sv[r]);
-                                const uint32_t pre = vmax3(tt, H[r], floorv);
-                                nw = H[r];
-                                H[r] = viaddmax(nn, g2, pre);
-                                nn = H[r];
-                            }
+                            fill_column<K>(H, prof + c * G::CSTRIDE + my_prof, diag, top, floorv, g2, one);
                             tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);
                         } else {
                             // outside the matrix: the column is all zero (left of it) or never read (right of it)
@@ -213,11 +236,26 @@ __global__ void __launch_bounds__(512) fill_bias_kernel(const BatchParams P, uin
                     gmax = vmax2(gmax, tmax);
                 }
                 tmax = 0;
-                uint32_t U[K];
+                if constexpr (K <= MAX_K_BASE) {
+                    uint32_t U[K];
 #pragma unroll
-                for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
-                if (s_next < my_steps && b >= skip)                                 // block b is owned by this group
-                    store_checkpoint<K>(rec_lane<K>(P.rec, blk0 + b, t), U, imad_add(diag, one, unbias));
+                    for (int r = 0; r < K; ++r) U[r] = imad_add(H[r], one, unbias);     // H'' - bias >= 0: no borrow
+                    if (s_next < my_steps && b >= skip)                                 // block b is owned by this group
+                        store_checkpoint<K>(rec_lane<K>(P.rec, blk0 + b, t), U, imad_add(diag, one, unbias));
+                } else if (s_next < my_steps && b >= skip) {
+                    // LONG classes: un-bias piece by piece (no second copy of the K score registers)
+                    uint32_t *lane_rec = rec_lane<K>(P.rec, blk0 + b, t);
+#pragma unroll
+                    for (int p = 0; p < G::CKP; ++p) {
+                        uint32_t v[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) {
+                            const int w = 8 * p + e;
+                            v[e] = (w < K) ? imad_add(H[w < K ? w : 0], one, unbias) : (w == K ? imad_add(diag, one, unbias) : 0u);
+                        }
+                        stg256(lane_rec + p * REC_P, v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7]);
+                    }
+                }
             }
         }
         {
@@ -248,7 +286,8 @@ static cudaError_t launch_fill_bias_k2(const BatchParams &P, uint32_t *work_coun
     using G = Geo<K>;
     const int n_quads = (P.n_vrefs + 3) / 4;
     static const int env_warps = getenv("SWB_FILL_WARPS") ? atoi(getenv("SWB_FILL_WARPS")) : 0;
-    const int warps = env_warps > 0 ? env_warps : 16;         // measured: 10/12/14/16 warps -> 42.0/39.8/39.4/39.2 ms
+    const int max_warps = fill_bias_threads(K) / 32;
+    const int warps = std::min(env_warps > 0 ? env_warps : 16, max_warps);   // measured (K = 19): 10/12/14/16 warps -> 42.0/39.8/39.4/39.2 ms
     const int64_t items = (int64_t)n_quads * P.n_rp;
     const int64_t ctas = std::min<int64_t>((items + warps - 1) / warps, (int64_t)sm_count);   // one CTA per SM
     const size_t smem = (size_t)warps * G::PROF_WORDS * sizeof(uint32_t);
@@ -290,6 +329,10 @@ cudaError_t launch_fill_bias(int K, const BatchParams &P, uint32_t *work_counter
         case 19: return launch_fill_bias_k<19>(P, work_counter, sm_count, st);
         case 25: return launch_fill_bias_k<25>(P, work_counter, sm_count, st);
         case 32: return launch_fill_bias_k<32>(P, work_counter, sm_count, st);
+        case 40: return launch_fill_bias_k<40>(P, work_counter, sm_count, st);
+        case 48: return launch_fill_bias_k<48>(P, work_counter, sm_count, st);
+        case 56: return launch_fill_bias_k<56>(P, work_counter, sm_count, st);
+        case 64: return launch_fill_bias_k<64>(P, work_counter, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }

@@ -1,6 +1,6 @@
 // swb_internal.h -- shared declarations of libswb200 (host structs, kernel launch API).
 //
-// Geometry of the short-read path (reads up to 8*32 = 256 rows)
+// Geometry of the short-read path (reads up to 8*32 = 256 rows; up to 511 rows with the LONG classes K = 40 .. 64)
 //   * a GROUP of GL = 8 lanes owns one (read pair, reference) task; lane t owns the K
 //     consecutive read rows t*K+1 .. t*K+K and marches along the reference columns,
 //   * the 8 lanes form a skewed wavefront: at STEP s lane t computes column j = s - t + 1,
@@ -26,12 +26,16 @@ namespace swb {
 
 constexpr int GL = 8;        // lanes per group
 constexpr int CB = 16;       // steps per checkpoint block (multiple of 16; the trace kernel's code window needs 16)
-constexpr int MAX_SHORT_ROWS = GL * 32;
+constexpr int MAX_SHORT_ROWS = GL * 32;       // every short-path kernel (incl. the fallbacks swb_fill.cu / swb_trace.cu)
 static_assert(CB == 16, "the fill kernels store one seam quad per 4 steps of a 16-step chunk");
 
 // rows-per-lane variants compiled for the short path
-constexpr int kNumK = 10;
-constexpr int kKList[kNumK] = {4, 5, 7, 8, 10, 13, 16, 19, 25, 32};   // 8 K >= m: 36/50/75-80/100/125/150/200/250 bp reads fit with <= 7 % padding
+constexpr int kNumK = 14;
+constexpr int kKList[kNumK] = {4, 5, 7, 8, 10, 13, 16, 19, 25, 32,    // 8 K >= m: 36/50/75-80/100/125/150/200/250 bp reads fit with <= 7 % padding
+                               40, 48, 56, 64};                        // LONG classes: 257 .. 511 rows (the reference's read-length sweep
+                                                                       // goes to 500 bp, EngineerData.java:87-104); biased fill + tile kernels only
+constexpr int MAX_K_BASE = 32;                // largest K of the fallback kernels
+constexpr int MAX_LONG_ROWS = 511;            // row index i has KEY_I_BITS = 9 bits in a max-cell key
 
 template <int K> struct Geo {
     static constexpr int KW = ((K + 1 + 3) / 4) * 4;            // checkpoint words per lane (K cells + diag), padded to 16 bytes

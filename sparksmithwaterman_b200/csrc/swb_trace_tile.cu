@@ -282,11 +282,23 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
 // candidate is a real one and the scan finds E == score at once.
 // The step loop is rolled in quads (fully unrolled it thrashed the instruction cache: 68 warps stalled on
 // no_instruction per issue, 1.86 ms instead of 0.19).
+// bit mask over a lane's K rows: 32 bits, 64 for the LONG classes (K = 40 .. 64)
+template <int K> struct RowMask { using type = uint32_t; };
+template <> struct RowMask<40> { using type = uint64_t; };
+template <> struct RowMask<48> { using type = uint64_t; };
+template <> struct RowMask<56> { using type = uint64_t; };
+template <> struct RowMask<64> { using type = uint64_t; };
+__device__ __forceinline__ int mask_ffs(uint32_t m) { return __ffs((int)m); }
+__device__ __forceinline__ int mask_ffs(uint64_t m) { return __ffsll((long long)m); }
+
 template <int K>
 struct TileSweep {
+    using mask_t = typename RowMask<K>::type;
+    static_assert(K <= 8 * (int)sizeof(mask_t), "row mask too narrow for K");
     int rc[K], H[K];
     int diag, S, t, b;
-    uint32_t win, rowok;
+    uint32_t win;
+    mask_t rowok;
     int ulo, uhi;
     const uint32_t *sq;
     bool has_top;
@@ -315,7 +327,7 @@ struct TileSweep {
         for (int r = 0; r < K; ++r) {
             const int row = t * K + r;
             rc[r] = (row < m) ? (int)P.read_codes[off + row] : 0xFE;
-            if (row < m) rowok |= 1u << r;
+            if (row < m) rowok |= (mask_t)1 << r;
         }
         const int64_t blk = (int64_t)rp * P.blocks_per_rp + P.ref_blk_off[ref] + b;
         if (b > 0) {
@@ -402,7 +414,8 @@ __global__ void __launch_bounds__(NT) tile_scan_kernel(const BatchParams P, cons
         int E = max(W.S, 1);                                     // cells below the tracked pair score cannot be maximal
         uint32_t n_hit = 0;
         const int t = W.t;
-        const uint32_t rowok = W.rowok;
+        using mask_t = typename TileSweep<K>::mask_t;
+        const mask_t rowok = W.rowok;
         W.run(P, (int)(T.rp_half & 1u), [&](int j, int cmax, const int (&H)[K]) {
             if (cmax < E) return;
             int vm = 0;
@@ -410,12 +423,12 @@ __global__ void __launch_bounds__(NT) tile_scan_kernel(const BatchParams P, cons
             for (int r = 0; r < K; ++r) vm = max(vm, ((rowok >> r) & 1u) ? H[r] : 0);
             if (vm < E) return;
             if (vm > E) { E = vm; n_hit = 0; }
-            uint32_t rm = 0;
+            mask_t rm = 0;
 #pragma unroll
-            for (int r = 0; r < K; ++r) rm |= (H[r] == E) ? (1u << r) : 0u;
+            for (int r = 0; r < K; ++r) rm |= (H[r] == E) ? ((mask_t)1 << r) : (mask_t)0;
             rm &= rowok;
             while (rm) {
-                const int r = __ffs((int)rm) - 1;
+                const int r = mask_ffs(rm) - 1;
                 rm &= rm - 1;
                 if (n_hit < 4) hitbuf[n_hit * NT + threadIdx.x] = ((uint32_t)(t * K + r + 1) << KEY_J_BITS) | (uint32_t)j;
                 ++n_hit;
@@ -472,16 +485,17 @@ __global__ void __launch_bounds__(NT) tile_emit_kernel(const BatchParams P, cons
             W.setup(P, T, true);
             const int S = h.emax;
             const int t = W.t;
-            const uint32_t rowok = W.rowok;
+            using mask_t = typename TileSweep<K>::mask_t;
+            const mask_t rowok = W.rowok;
             uint32_t seen = 0;
             W.run(P, (int)(T.rp_half & 1u), [&](int j, int cmax, const int (&H)[K]) {
                 if (cmax < S) return;
-                uint32_t rm = 0;
+                mask_t rm = 0;
 #pragma unroll
-                for (int r = 0; r < K; ++r) rm |= (H[r] == S) ? (1u << r) : 0u;
+                for (int r = 0; r < K; ++r) rm |= (H[r] == S) ? ((mask_t)1 << r) : (mask_t)0;
                 rm &= rowok;
                 while (rm) {
-                    const int r = __ffs((int)rm) - 1;
+                    const int r = mask_ffs(rm) - 1;
                     rm &= rm - 1;
                     const uint32_t k = seen < 4 ? base + seen : atomicAdd(count, 1u);
                     ++seen;
@@ -559,6 +573,10 @@ cudaError_t launch_locate(int K, const BatchParams &P, const TileTask *tasks, co
         case 19: return launch_tile_locate_k<19>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
         case 25: return launch_tile_locate_k<25>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
         case 32: return launch_tile_locate_k<32>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 40: return launch_tile_locate_k<40>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 48: return launch_tile_locate_k<48>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 56: return launch_tile_locate_k<56>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
+        case 64: return launch_tile_locate_k<64>(P, tasks, n_tasks, cap_tasks, hits, keys, cap, count, sm_count, phase, st);
     }
     return cudaErrorInvalidValue;
 }
@@ -577,6 +595,10 @@ cudaError_t launch_tile_trace(int K, const BatchParams &P, const uint64_t *keys,
         case 19: return launch_tile_trace_k<19>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 25: return launch_tile_trace_k<25>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
         case 32: return launch_tile_trace_k<32>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 40: return launch_tile_trace_k<40>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 48: return launch_tile_trace_k<48>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 56: return launch_tile_trace_k<56>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
+        case 64: return launch_tile_trace_k<64>(P, keys, n_cells, beginnings, op_lens, ops, ops_stride_words, sm_count, st);
     }
     return cudaErrorInvalidValue;
 }
