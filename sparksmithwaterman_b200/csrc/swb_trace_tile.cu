@@ -91,6 +91,8 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
     const uint8_t *tile8 = reinterpret_cast<const uint8_t *>(tile);
     uint8_t *rcodes_s = reinterpret_cast<uint8_t *>(smem + TG::PROF_WORDS + (size_t)TG::TILE_WORDS * NT);   // [GL*K]
     const int gap = P.gap, match = P.match, mismatch = P.mismatch, sbias = P.seam_bias;
+    const int ag = -gap;                                                          // > 0 (tile_trace_ok)
+    const uint32_t kone = k64k >> 16;                                             // 1, opaque to ptxas: keeps NW + s an IMAD
 
     const uint32_t c_lo = blockIdx.x * (uint32_t)chunk;
     const uint32_t c_hi = min(n_cells, c_lo + (uint32_t)chunk);
@@ -116,7 +118,7 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             const int row = tt * K + r;
             int s = S_PAD;
             if (row < m && cc < 4) s = ((int)P.read_codes[roff + row] == cc) ? match : mismatch;
-            prof[(cc < 4 ? tt * 4 + cc : 4 * GL + tt) * KS + r] = s;
+            prof[(cc < 4 ? tt * 4 + cc : 4 * GL + tt) * KS + r] = s + ag;      // the recompute is column-biased (below)
         }
         for (int idx = threadIdx.x; idx < GL * K; idx += NT)
             rcodes_s[idx] = idx < m ? P.read_codes[roff + idx] : (uint8_t)0xFE;
@@ -185,6 +187,12 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             }
             store_col8<K>(tile, diag, H, k64k);
 
+            // The tile is recomputed COLUMN-BIASED like the fill (swb_fill_bias.cu): column c = u + 1 of the tile holds
+            // H'' = H + |gap| * c (column 0, the checkpoint, is unbiased), so that W + gap is the register itself and the
+            // cell costs an IMAD (NW'' + s + |gap|, FMA pipe) and two DPX ops instead of three DPX ops:
+            //     pre = max3(NW'' + s'', W'', |gap| * c)      the third operand is the biased zero
+            //     H'' = max(N'' + gap, pre)
+            // The bytes the walker reads are biased the same way (see the walk below).
             const int *pbase = prof + t * 4 * KS, *ppad = prof + (4 * GL + t) * KS;
 #pragma unroll
             for (int u = 0; u < CB; ++u) {
@@ -199,17 +207,19 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
                         sv[4 * q] = v.x; sv[4 * q + 1] = v.y; sv[4 * q + 2] = v.z; sv[4 * q + 3] = v.w;
                     }
                 }
-                int nw = diag, nn = top[u];
+                const int floorc = ag * (u + 1);
+                const int topb = top[u] + floorc;
+                int nw = diag, nn = topb;
 #pragma unroll
                 for (int r = 0; r < K; ++r) {
-                    const int x = __viaddmax_s32_relu(nw, sv[r], 0);     // max(NW + s, 0)
-                    const int pre = __viaddmax_s32(H[r], gap, x);        // max(W + gap, .)
+                    const int tt = nw * (int)kone + sv[r];               // NW'' + s''           (IMAD, FMA pipe)
+                    const int pre = __vimax3_s32(tt, H[r], floorc);      // max(., W'', 0'')
                     nw = H[r];
-                    H[r] = __viaddmax_s32(nn, gap, pre);                 // max(N + gap, .)
+                    H[r] = __viaddmax_s32(nn, gap, pre);                 // max(N'' + gap, .)
                     nn = H[r];
                 }
-                diag = top[u];
-                store_col8<K>(tile + (u + 1) * ROWW * NT, top[u], H, k64k);
+                diag = topb;
+                store_col8<K>(tile + (u + 1) * ROWW * NT, topb, H, k64k);
             }
 
             // ---- walk inside the tile (SmithWaterman.java:380-409) ------------------------------------
@@ -237,8 +247,13 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
                     // low byte = the score's low 8 bits; the other bytes are masked after the add
                     const int hn = (int)prmt(u_c, w_c, sel3), hw = (int)prmt(u_l, w_l, sel3 + 1u), hnw = (int)prmt(u_l, w_l, sel3);
                     const int sc = ((uint32_t)*qp == (wsh & 3u)) ? match : mismatch;
-                    const bool eq_a = ((hnw + sc - w_h) & 0xff) == 0, eq_i = ((hn + gap - w_h) & 0xff) == 0,
-                               eq_d = ((hw + gap - w_h) & 0xff) == 0;
+                    // biased bytes: column c holds H + |gap| * c, so with whb = H(r, c) + |gap| * c
+                    //   alignment  H = NW + s    <=>  NW'' + s + |gap| == whb      (NW'' carries |gap| * (c - 1))
+                    //   insertion  H = N + gap   <=>  N'' + gap == whb            (same column)
+                    //   deletion   H = W + gap   <=>  W'' == whb
+                    const int whb = w_h + ag * c;
+                    const bool eq_a = ((hnw + sc + ag - whb) & 0xff) == 0, eq_i = ((hn + gap - whb) & 0xff) == 0,
+                               eq_d = ((hw - whb) & 0xff) == 0;
                     const uint32_t op = TIE_GT ? (eq_d ? 3u : (eq_i ? 2u : 1u)) : (eq_a ? 1u : (eq_i ? 2u : 3u));
                     lastc = c;
                     w_opword |= op << sh;
