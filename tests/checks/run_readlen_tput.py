@@ -12,7 +12,7 @@ import argparse, json, os, subprocess, sys, time
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
-CASES = [(150, 128), (250, 128), (260, 64), (300, 64), (400, 64), (500, 64), (511, 64), (512, 32), (1000, 32), (2000, 16)]
+CASES = [(36, 256), (50, 256), (75, 256), (100, 128), (125, 128), (150, 128), (200, 128), (250, 128), (260, 64), (300, 64), (400, 64), (500, 64), (511, 64), (512, 32), (1000, 32), (2000, 16)]
 
 
 def run(cases):
@@ -47,13 +47,14 @@ def main():
     if a.child:
         print("JSON " + json.dumps(run([c for c in CASES if 256 < c[0] < 512])))
         return
-    rows = run(CASES)
+    # the child first: it must see the whole HBM for its workspace
     env = dict(os.environ, SWB_NO_LONG_CLASSES="1")
     out = subprocess.run([sys.executable, os.path.abspath(__file__), "--child"], env=env, capture_output=True, text=True, timeout=900)
     wide = []
     for line in out.stdout.splitlines():
         if line.startswith("JSON "):
             wide = json.loads(line[5:])
+    rows = run(CASES)
     doc = {"what": "whole batches of one read length x 10,000 references through swb_align (host buffers, incl. traceback)",
            "rows": rows, "rows_with_SWB_NO_LONG_CLASSES": wide}
     if a.out:
