@@ -107,3 +107,23 @@ def test_gappy_paths(engine):
     base = _rand(rnd, 2000)
     reads = [_mutate(rnd, base[300:300 + 2 * m], sub=0.2, indel=0.25)[:m] for m in (270, 340, 430, 500)]
     check_pairs(engine, [base, base[::-1]], reads)
+
+
+def test_scores_only_and_resident_reads(engine):
+    """SWB_F_SCORES_ONLY (the locate scan makes the subsampled fill's scores exact) and the device-resident reads
+    handle (swb_align_resident) with reads of every long class."""
+    import numpy as np
+    rnd = random.Random(61)
+    base = _rand(rnd, 2400)
+    refs = [base, _rand(rnd, 1000), "AT" * 300]
+    reads = [_mutate(rnd, base[m:2 * m])[:m] for m in (260, 333, 401, 470)] + [_rand(rnd, 511), ("AT" * 200)[:385]]
+    rs = engine.load_refset(refs)
+    exp = np.array([[oracle.align(r, q, 5, -3, -4, max_cells=1).score for q in reads] for r in refs], dtype=np.int32)
+    so = rs.align(reads, scores_only=True)
+    assert (so.scores == exp).all()
+    up = rs.upload_reads(reads)
+    res = up.align()
+    assert (res.scores == exp).all()
+    assert (res.ref_totals == so.ref_totals).all()
+    res.free(); up.free()
+    so.free(); rs.free()
