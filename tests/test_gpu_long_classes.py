@@ -127,3 +127,37 @@ def test_scores_only_and_resident_reads(engine):
     assert (res.ref_totals == so.ref_totals).all()
     res.free(); up.free()
     so.free(); rs.free()
+
+
+LONG_SCORE_SETS = [(5, -3, -4), (1, -1, -1), (2, -2, -2), (3, -3, -1), (2, -1, -3), (7, -5, -2), (10, -2, -7), (3, 1, -2)]
+
+
+def _fuzz_workload(rnd):
+    alphabet = rnd.choice(["ACGT", "ACGT", "AT", "acgtACGT"])
+
+    def seq(n):
+        if rnd.random() < 0.15 and n >= 4:                           # tandem repeat
+            unit = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(1, 5)))
+            return (unit * (n // len(unit) + 1))[:n]
+        return "".join(rnd.choice(alphabet) for _ in range(n))
+
+    refs = [seq(rnd.choice([1, 16, 17, 100, 511, 512, 1023, 1500, 2600, 4000])) for _ in range(rnd.randint(1, 5))]
+    if rnd.random() < 0.2:
+        refs.append(seq(rnd.randint(9000, 22000)))                    # segmented fill
+    reads = [seq(rnd.randint(257, 511)) for _ in range(rnd.randint(1, 5))]
+    for _ in range(rnd.randint(1, 3)):                                # planted, mutated substrings
+        r = rnd.choice(refs)
+        if len(r) > 300:
+            m = rnd.randint(257, min(511, len(r)))
+            a = rnd.randrange(0, len(r) - m + 1)
+            reads.append(_mutate(rnd, r[a:a + m], sub=rnd.choice([0.02, 0.1, 0.25]), indel=rnd.choice([0.0, 0.02, 0.2]))[:511])
+    if rnd.random() < 0.3:
+        reads.append(seq(rnd.choice([150, 256, 600])))                # a neighbour class / the wide path in the same call
+    return refs, [q for q in reads if q]
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_fuzz_long_classes(engine, seed):
+    rnd = random.Random(5000 + seed)
+    refs, reads = _fuzz_workload(rnd)
+    check_pairs(engine, refs, reads, LONG_SCORE_SETS[seed % len(LONG_SCORE_SETS)], max_cells=300)
