@@ -248,3 +248,31 @@ def test_running_median_and_refset_info(tmp_path):
     assert "File Name                          |# Sequences\n-----------------------------------+-----------\n" \
            "a.fa                               |          1\nb.fa                               |          2\n" in text
     assert metrics.info_of_lengths([])[0] == [0, 0, (1 << 63) - 1, 0]
+
+
+def test_rows_per_lane_classes_cover_the_short_path():
+    """swb_internal.h: every read length of the s16x2 path (1 .. MAX_LONG_ROWS) has a rows-per-lane class with
+    8 * K >= m, the class list is ascending, the classes above MAX_K_BASE (biased fill + tile kernels only) reach
+    MAX_LONG_ROWS, and the row index of a max-cell key (KEY_I_BITS) can hold it.  Each launcher's switch lists the
+    classes it is compiled for."""
+    import re
+    src = open(os.path.join(ROOT, "sparksmithwaterman_b200", "csrc", "swb_internal.h")).read()
+    gl = int(re.search(r"constexpr int GL = (\d+);", src).group(1))
+    body = re.search(r"kKList\[kNumK\] = \{([^}]*)\}", src, re.S).group(1)
+    ks = [int(x) for x in re.sub(r"//[^\n]*", "", body).replace("\n", " ").split(",") if x.strip()]
+    n = int(re.search(r"constexpr int kNumK = (\d+);", src).group(1))
+    assert len(ks) == n and ks == sorted(ks)
+    k_base = int(re.search(r"constexpr int MAX_K_BASE = (\d+);", src).group(1))
+    long_rows = int(re.search(r"constexpr int MAX_LONG_ROWS = (\d+);", src).group(1))
+    i_bits = int(re.search(r"KEY_I_BITS = (\d+)", src).group(1))
+    assert gl * k_base == 256 and gl * ks[-1] >= long_rows and long_rows < (1 << i_bits)
+    for m in range(1, long_rows + 1):
+        k = next(k for k in ks if gl * k >= m)
+        assert gl * k - m < max(gl * 8, m // 4 + gl), (m, k)        # padding stays small
+    csrc = os.path.join(ROOT, "sparksmithwaterman_b200", "csrc")
+    for fname, fn, wanted in (("swb_fill_bias.cu", "launch_fill_bias_k", ks), ("swb_trace_tile.cu", "launch_tile_trace_k", ks),
+                              ("swb_trace_tile.cu", "launch_tile_locate_k", ks), ("swb_fill.cu", "launch_fill_k", [k for k in ks if k <= k_base]),
+                              ("swb_trace.cu", "launch_trace_k", [k for k in ks if k <= k_base])):
+        text = open(os.path.join(csrc, fname)).read()
+        got = sorted(int(x) for x in re.findall(r"case (\d+):\s+return " + fn + r"<\1>", text))
+        assert got == wanted, (fname, fn, got)
