@@ -177,22 +177,30 @@ __global__ void __launch_bounds__(fill_bias_threads(K)) fill_bias_kernel(const B
             uint32_t tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
             if (fast) {
+                // K <= 32: all 16 steps unrolled (20-31 KB of code).  The LONG classes would be 37-56 KB and stall on
+                // instruction fetch (ncu, K = 64: no_instruction 1.1 warps per issue): two rounds of 8 steps there.
+                constexpr int UNR = K <= MAX_K_BASE ? 16 : 8;
+#pragma unroll 1
+                for (int uq = 0; uq < 16; uq += UNR) {
+                    const uint32_t winq = win >> (2 * uq);
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    floorv = imad_add(floorv, one, gpos);                  // floor of the new column
-                    if (!SUB) negfloor = imad_add(negfloor, one, g2c);      // its negative (packed; see g2c)
-                    uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
-                    if (t == 0) top = floorv;                               // row 0 is all zero
-                    const uint32_t c = (win >> (2 * u)) & 3u;
-                    fill_column<K>(H, prof + c * G::CSTRIDE + my_prof, diag, top, floorv, g2, one);
-                    diag = top;
-                    if (!SUB) tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
-                    else if (u & 1) {                                       // odd steps: CB is even, the last step is one
-                        negfloor = imad_add(negfloor, one, g2c2);           // two columns on
-                        tmax = viaddmax(colmax_even<K>(floorv, H), negfloor, tmax);
+                    for (int uu = 0; uu < UNR; ++uu) {
+                        floorv = imad_add(floorv, one, gpos);                  // floor of the new column
+                        if (!SUB) negfloor = imad_add(negfloor, one, g2c);      // its negative (packed; see g2c)
+                        uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1);
+                        if (t == 0) top = floorv;                               // row 0 is all zero
+                        const uint32_t c = (winq >> (2 * uu)) & 3u;
+                        fill_column<K>(H, prof + c * G::CSTRIDE + my_prof, diag, top, floorv, g2, one);
+                        diag = top;
+                        if (!SUB) tmax = viaddmax(colmax<K>(floorv, H), negfloor, tmax);  // unbiased running maximum
+                        else if (uu & 1) {                                      // odd steps: CB and UNR are even, the last step is one
+                            negfloor = imad_add(negfloor, one, g2c2);           // two columns on
+                            tmax = viaddmax(colmax_even<K>(floorv, H), negfloor, tmax);
+                        }
+                        tq[uu & 7] = top;
+                        if ((uu & 7) == 7 && own_chunk)
+                            stg256(seam + ((uq + uu) >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                     }
-                    tq[u & 7] = top;
-                    if ((u & 7) == 7 && own_chunk) stg256(seam + (u >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                 }
             } else {
 #pragma unroll 1

@@ -194,10 +194,10 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
             //     H'' = max(N'' + gap, pre)
             // The bytes the walker reads are biased the same way (see the walk below).
             const int *pbase = prof + t * 4 * KS, *ppad = prof + (4 * GL + t) * KS;
-#pragma unroll
-            for (int u = 0; u < CB; ++u) {
+            // one column of the tile: u = step inside the block, tv = the (unbiased) boundary value of that step
+            auto column = [&](int u, int tv, uint32_t code) {
                 const bool real = (u >= ulo) && (u <= uhi);
-                const int *pv = real ? pbase + ((win >> (2 * u)) & 3u) * KS : ppad;
+                const int *pv = real ? pbase + code * KS : ppad;
                 int sv[G::KP];
                 {
                     const int4 *p4 = reinterpret_cast<const int4 *>(pv);
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
                     }
                 }
                 const int floorc = ag * (u + 1);
-                const int topb = top[u] + floorc;
+                const int topb = tv + floorc;
                 int nw = diag, nn = topb;
 #pragma unroll
                 for (int r = 0; r < K; ++r) {
@@ -220,6 +220,27 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
                 }
                 diag = topb;
                 store_col8<K>(tile + (u + 1) * ROWW * NT, topb, H, k64k);
+            };
+            if constexpr (K <= MAX_K_BASE) {
+#pragma unroll
+                for (int u = 0; u < CB; ++u) column(u, top[u], (win >> (2 * u)) & 3u);
+            } else {
+                // LONG classes: 16 unrolled columns of 64 rows are 60 KB of code (ncu: no_instruction stalls); rolled in
+                // quads, the quad's four boundary values picked without dynamic register indexing
+#pragma unroll 1
+                for (int q = 0; q < CB / 4; ++q) {
+                    int tv[4];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        int x = top[e];
+#pragma unroll
+                        for (int qq = 1; qq < CB / 4; ++qq) x = (q == qq) ? top[4 * qq + e] : x;
+                        tv[e] = x;
+                    }
+                    const uint32_t wq = win >> (8 * q);
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) column(4 * q + e, tv[e], (wq >> (2 * e)) & 3u);
+                }
             }
 
             // ---- walk inside the tile (SmithWaterman.java:380-409) ------------------------------------
