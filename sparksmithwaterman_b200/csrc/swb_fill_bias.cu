@@ -80,6 +80,8 @@ __device__ __forceinline__ void fill_column(uint32_t (&H)[K], const uint32_t *pc
     }
 }
 
+// from this K on the 16 steps of a block run as two rounds of 8 (code size, see the fast path)
+constexpr int FILL_ROLL_K = 25;
 constexpr int fill_bias_threads(int K) { return K <= MAX_K_BASE ? 512 : (K <= 48 ? 384 : 256); }
 
 template <int K, bool SUB>
@@ -177,9 +179,11 @@ __global__ void __launch_bounds__(fill_bias_threads(K)) fill_bias_kernel(const B
             uint32_t tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
             if (fast) {
-                // K <= 32: all 16 steps unrolled (20-31 KB of code).  The LONG classes would be 37-56 KB and stall on
-                // instruction fetch (ncu, K = 64: no_instruction 1.1 warps per issue): two rounds of 8 steps there.
-                constexpr int UNR = K <= MAX_K_BASE ? 16 : 8;
+                // K <= 19: all 16 steps unrolled (<= 20 KB of code).  Larger classes stall on instruction fetch when fully
+                // unrolled (ncu, K = 64, 56 KB: no_instruction 1.1 warps per issue; K = 32, 31 KB: 250 bp batches 5 % slower):
+                // two rounds of 8 steps there.  Rolling K = 19 as well costs 2 % (35.3 -> 35.9 ms; with the 90 registers
+                // it then needs, 20 warps per CTA: 36.1 ms).
+                constexpr int UNR = K < FILL_ROLL_K ? 16 : 8;
 #pragma unroll 1
                 for (int uq = 0; uq < 16; uq += UNR) {
                     const uint32_t winq = win >> (2 * uq);

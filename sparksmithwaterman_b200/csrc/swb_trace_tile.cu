@@ -34,6 +34,7 @@ namespace swb {
 namespace {
 
 constexpr int NT = 128;                      // threads per CTA
+constexpr int TRACE_ROLL_K = 25;              // from this K on the tile's column loop is rolled in quads (code size)
 
 template <int K> struct TileGeo {
     static constexpr int ROWW = Geo<K>::KW / 4;          // words per tile column: boundary row + K rows, one byte each
@@ -221,12 +222,13 @@ __global__ void __launch_bounds__(NT) tile_trace_kernel(const BatchParams P, con
                 diag = topb;
                 store_col8<K>(tile + (u + 1) * ROWW * NT, topb, H, k64k);
             };
-            if constexpr (K <= MAX_K_BASE) {
+            if constexpr (K < TRACE_ROLL_K) {
 #pragma unroll
                 for (int u = 0; u < CB; ++u) column(u, top[u], (win >> (2 * u)) & 3u);
             } else {
-                // LONG classes: 16 unrolled columns of 64 rows are 60 KB of code (ncu: no_instruction stalls); rolled in
-                // quads, the quad's four boundary values picked without dynamic register indexing
+                // K >= 25: 16 unrolled columns of 32 .. 64 rows are 34 .. 60 KB of code (ncu, K = 64: no_instruction stalls;
+                // K = 32: 250 bp batches 10.3 -> 8.9 ms); rolled in quads, the quad's four boundary values picked without
+                // dynamic register indexing.  K = 19 is faster unrolled (4.0 vs 4.1 ms per step).
 #pragma unroll 1
                 for (int q = 0; q < CB / 4; ++q) {
                     int tv[4];
