@@ -111,25 +111,33 @@ __global__ void __launch_bounds__(512) fill_kernel(const BatchParams P, uint32_t
             uint32_t tq[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 
             if (fast) {
+                // K >= 25: two rounds of 8 steps instead of 16 unrolled ones (49-62 KB of code stall on instruction fetch,
+                // see swb_fill_bias.cu)
+                constexpr int UNR = K < 25 ? 16 : 8;
+#pragma unroll 1
+                for (int uq = 0; uq < 16; uq += UNR) {
+                    const uint32_t winq = win >> (2 * uq);
 #pragma unroll
-                for (int u = 0; u < 16; ++u) {
-                    const uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1) & lmask;
-                    const uint32_t c = (win >> (2 * u)) & 3u;
-                    uint32_t sv[G::KP];
-                    load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
-                    uint32_t nw = diag, nn = top;
+                    for (int uu = 0; uu < UNR; ++uu) {
+                        const uint32_t top = __shfl_up_sync(0xffffffffu, H[K - 1], 1) & lmask;
+                        const uint32_t c = (winq >> (2 * uu)) & 3u;
+                        uint32_t sv[G::KP];
+                        load_profile<G::KP>(prof + c * G::CSTRIDE + my_prof, sv);
+                        uint32_t nw = diag, nn = top;
 #pragma unroll
-                    for (int r = 0; r < K; ++r) {
-                        const uint32_t x = viaddmax_relu(nw, sv[r], zero);
-                        const uint32_t pre = viaddmax(H[r], g2, x);
-                        nw = H[r];
-                        H[r] = viaddmax(nn, g2, pre);
-                        nn = H[r];
+                        for (int r = 0; r < K; ++r) {
+                            const uint32_t x = viaddmax_relu(nw, sv[r], zero);
+                            const uint32_t pre = viaddmax(H[r], g2, x);
+                            nw = H[r];
+                            H[r] = viaddmax(nn, g2, pre);
+                            nn = H[r];
+                        }
+                        diag = top;
+                        tmax = colmax<K>(tmax, H);
+                        tq[uu & 7] = top;
+                        if ((uu & 7) == 7 && own_chunk)
+                            stg256(seam + ((uq + uu) >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                     }
-                    diag = top;
-                    tmax = colmax<K>(tmax, H);
-                    tq[u & 7] = top;
-                    if ((u & 7) == 7 && own_chunk) stg256(seam + (u >> 3) * REC_P, tq[0], tq[1], tq[2], tq[3], tq[4], tq[5], tq[6], tq[7]);
                 }
             } else {
 #pragma unroll 1
