@@ -33,12 +33,6 @@ __device__ __forceinline__ uint32_t imad_add(uint32_t a, uint32_t one, uint32_t 
     return a * one + b;
 }
 
-// SUB: the tile maximum (and with it the pair score the fill leaves) is taken over a SUBSAMPLE of the cells --
-// even rows + the lane's last row, on the odd steps of a block (CB is even: the last step is odd) -- which costs
-// 3.0 instead of 10.5 DPX ops per step.  Every cell (r, u) of a tile has a tracked cell of the SAME tile among (r, u), (r+1, u),
-// (r, u+1), (r+1, u+1), so the tracked maximum M of a tile satisfies  true max - slack <= M <= true max  with
-// slack = max(|gap|, min(|mismatch|, 2|gap|)) (fill_sub_slack).  The locate stage recomputes every tile within
-// slack of the pair's tracked maximum, makes the pair score exact and enumerates the exact maximum cells.
 // one column of a lane: K cells.  K <= 32: the lane's KP profile words are loaded up front (5 LDS.128 for K = 19);
 // the LONG classes (K = 40 .. 64) load them a quad at a time inside the row loop -- K score registers plus K profile
 // registers would not fit the 128-register budget of a 16-warp CTA.
@@ -84,6 +78,12 @@ __device__ __forceinline__ void fill_column(uint32_t (&H)[K], const uint32_t *pc
 constexpr int FILL_ROLL_K = 25;
 constexpr int fill_bias_threads(int K) { return K <= MAX_K_BASE ? 512 : (K <= 48 ? 384 : 256); }
 
+// SUB: the tile maximum (and with it the pair score the fill leaves) is taken over a SUBSAMPLE of the cells --
+// even rows + the lane's last row, on the odd steps of a block (CB is even: the last step is odd) -- which costs
+// 3.0 instead of 10.5 DPX ops per step.  Every cell (r, u) of a tile has a tracked cell of the SAME tile among (r, u), (r+1, u),
+// (r, u+1), (r+1, u+1), so the tracked maximum M of a tile satisfies  true max - slack <= M <= true max  with
+// slack = max(|gap|, min(|mismatch|, 2|gap|)) (fill_sub_slack).  The locate stage recomputes every tile within
+// slack of the pair's tracked maximum, makes the pair score exact and enumerates the exact maximum cells.
 template <int K, bool SUB>
 __global__ void __launch_bounds__(fill_bias_threads(K)) fill_bias_kernel(const BatchParams P, uint32_t *work_counter, uint32_t one)
 {
