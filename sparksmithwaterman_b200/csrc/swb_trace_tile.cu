@@ -15,7 +15,7 @@
 // 8-lane blocks (29k cells) the group-based kernel (swb_trace.cu) recomputes.
 //
 // One thread owns one maximum cell at a time: it recomputes the tile that holds the current
-// cell (unpacked int32 DPX ops, the three-op cell of the fill) into its private column-major
+// cell (unpacked int32, column-biased like the fill: one IMAD + two DPX ops per cell) into its private column-major
 // byte tile in shared memory, walks until the path leaves the tile, and repeats.  No lane
 // ever talks to another lane, so there are no shuffles and no barriers inside a traceback.
 //
